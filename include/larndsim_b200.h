@@ -1,0 +1,282 @@
+/*
+ * larndsim_b200.h -- C ABI of the B200-native larnd-sim charge/light readout chain.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one
+ * Numba `@cuda.jit` kernel (or one piece of CuPy glue) of the reference; the reference
+ * file:line it replaces is cited on each declaration (paths relative to the reference
+ * tree, e.g. larndsim/detsim.py).  The Python host layer in `larnd-sim_b200/` binds these
+ * with ctypes and re-creates the reference's `kernel[grid, block](*arrays)` call
+ * surface on top; INTEGRATION.md shows the binding a larnd-sim maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers + sizes, POD structs, no C++/torch types;
+ *  - every array pointer is a DEVICE pointer unless the name ends in `_host`;
+ *    arrays are C-contiguous with exactly the dtypes the reference CLI passes
+ *    (cli/simulate_pixels.py:930-1087): pixel ids / radii int32, maps int64,
+ *    accumulators float64, induced-current `signals` float32;
+ *  - outputs are caller-allocated and caller-initialised (-1 / 0 fills); kernels only
+ *    write or accumulate in place, exactly like the reference kernels;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is
+ *    what Numba and CuPy use in the reference);
+ *  - return value: 0 ok, <0 argument error, >0 cudaError_t.  Never throws.
+ *    `lsb_last_error()` returns a static description of the last failure.
+ *  - detector/physics/light/simulation constants are read by the host layer from
+ *    `larndsim.consts.*` AT CALL TIME and passed in `lsb_consts` (the reference freezes
+ *    them into the JIT: cli/simulate_pixels.py:459-464).
+ */
+#ifndef LARNDSIM_B200_H
+#define LARNDSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSB_ABI_VERSION 1
+#define LSB_MAX_TPC 128
+
+/* dtype codes for record fields */
+enum lsb_dtype {
+    LSB_NONE = 0, LSB_F32 = 1, LSB_F64 = 2, LSB_I32 = 3, LSB_U32 = 4, LSB_I64 = 5, LSB_U64 = 6
+};
+
+/* segment-record fields the chain touches (cli/dumpTree.py:17-28) */
+enum lsb_field {
+    LSB_F_X = 0, LSB_F_Y, LSB_F_Z,
+    LSB_F_X_START, LSB_F_Y_START, LSB_F_Z_START,
+    LSB_F_X_END, LSB_F_Y_END, LSB_F_Z_END,
+    LSB_F_T, LSB_F_T_START, LSB_F_T_END,
+    LSB_F_T0, LSB_F_T0_START, LSB_F_T0_END,
+    LSB_F_DEDX, LSB_F_DE, LSB_F_DX,
+    LSB_F_N_ELECTRONS, LSB_F_N_PHOTONS,
+    LSB_F_LONG_DIFF, LSB_F_TRAN_DIFF,
+    LSB_F_PIXEL_PLANE,
+    LSB_F_COUNT
+};
+
+/* Layout of one structured-array record, resolved by the host layer from
+ * `arr.dtype.fields` at call time (tests use an all-f8 record, production a 152-byte
+ * f4/u4 record: tests/testQuenching.py:16-19 vs cli/dumpTree.py:17-28). offset<0: absent. */
+typedef struct lsb_track_layout {
+    int32_t itemsize;
+    int32_t offset[LSB_F_COUNT];
+    int32_t dtype[LSB_F_COUNT];
+} lsb_track_layout;
+
+/* Flat snapshot of larndsim.consts.{physics,detector,light,sim,units} and
+ * pixels_from_track.MAX_NEIGHBOR_BACKTRACK_DISTANCE. */
+typedef struct lsb_consts {
+    /* consts/physics.py:7-17 */
+    double box_alpha, box_beta, birks_ab, birks_kb, w_ion;
+    int32_t mode_box, mode_birks;
+    /* consts/detector.py:19-67 */
+    double e_field, lar_density, v_drift, electron_lifetime, long_diff, tran_diff;
+    double time_sampling, time_padding, time_window, time_interval[2];
+    double response_sampling, response_bin_size, pixel_pitch;
+    int32_t n_time_ticks;          /* len(detector.TIME_TICKS) */
+    int32_t n_pixels[2];
+    int32_t n_tpc;                 /* TPC_BORDERS.shape[0] */
+    int32_t default_plane_index;   /* 0xBEEF */
+    int32_t sampled_points;
+    int32_t max_neighbor_backtrack_distance; /* pixels_from_track.py:11 */
+    int32_t pad0_;
+    /* consts/detector.py:92-131 (front-end electronics) */
+    double discrimination_threshold, adc_hold_delay, adc_busy_delay, reset_cycles, clock_cycle;
+    double gain, buffer_risetime, v_cm, v_ref, v_pedestal, adc_counts;
+    double reset_noise_charge, uncorrelated_noise_charge, discriminator_noise;
+    /* consts/units.py */
+    double unit_e, unit_mV, unit_ns, unit_mus;
+    /* consts/light.py:8-61 */
+    double w_ph, scint_prescale, light_tick_size, light_window[2];
+    double singlet_fraction, tau_s, tau_t;
+    double light_response_time, light_oscillation_period, impulse_tick_size;
+    int32_t sipm_response_model, light_trig_mode, enable_lut_smearing, n_op_channel;
+    /* consts/sim.py:26-39 */
+    double min_step_size, mc_truth_threshold;
+    int32_t max_tracks_per_pixel, mc_sample_multiplier, max_adc_values, pad1_;
+    /* consts/detector.py:329-345: TPC_BORDERS[n_tpc][3][2] (x,y,z) x (lo,hi); z[0] = anode */
+    double tpc_borders[LSB_MAX_TPC][3][2];
+} lsb_consts;
+
+/* Layout of the light LUT record (lightLUT.py:104-114, light_sim.py:97,116):
+ * lut[nx][ny][nz][ndet_tpc] of records with float32 fields. */
+typedef struct lsb_lut_layout {
+    int32_t itemsize;
+    int32_t off_vis, off_t0, off_t0_avg, off_time_dist;  /* <0: absent */
+    int32_t n_time_dist;
+    int32_t shape[4];
+} lsb_lut_layout;
+
+/* Layout of light_incidence records [S][ndet] {n_photons_det f4, t0_det f4, ...}
+ * (cli/simulate_pixels.py:758-759). */
+typedef struct lsb_linc_layout {
+    int32_t itemsize;
+    int32_t off_n_photons_det, off_t0_det;
+} lsb_linc_layout;
+
+int         lsb_abi_version(void);
+const char* lsb_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py gpu_launches) */
+int64_t     lsb_launch_count(void);
+
+/* ---- RNG: numba.cuda.random state layout {s0:u8, s1:u8}, 16 bytes ------------------ */
+/* numba/cuda/random.py create_xoroshiro128p_states(n, seed, subsequence_start):
+ * state[i] = jump^(subsequence_start+i)(splitmix64(seed)); host-side, multithreaded. */
+int lsb_rng_create_states_host(uint64_t* states_host, int64_t n, uint64_t seed, uint64_t subsequence_start);
+
+/* ---- per-segment kernels ----------------------------------------------------------- */
+/* larndsim/quenching.py:11-44  quench(tracks, mode) */
+int lsb_quench(const lsb_consts* c, const lsb_track_layout* L, void* tracks, int64_t n, int32_t mode, void* stream);
+/* larndsim/drifting.py:11-58  drift(tracks) */
+int lsb_drift(const lsb_consts* c, const lsb_track_layout* L, void* tracks, int64_t n, void* stream);
+/* larndsim/pixels_from_track.py:43-65  max_pixels(tracks, n_max_pixels); n_max_pixels int64[1], atomic max */
+int lsb_max_pixels(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t n,
+                   int64_t* n_max_pixels, void* stream);
+/* larndsim/pixels_from_track.py:67-109  get_pixels(tracks, active, neighboring, radius_class, n_pixels_list, radius) */
+int lsb_get_pixels(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t n,
+                   int32_t* active_pixels, int32_t max_active,
+                   int32_t* neighboring_pixels, int32_t* neighboring_radius, int32_t max_neighbors,
+                   double* n_pixels_list, int32_t radius, void* stream);
+/* larndsim/detsim.py:18-40  time_intervals(track_starts, time_max, tracks) */
+int lsb_time_intervals(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t n,
+                       double* track_starts, int64_t* time_max, void* stream);
+
+/* ---- glue the reference does with CuPy ---------------------------------------------- */
+/* cli/simulate_pixels.py:953-956  unique_pix = cp.unique(neighboring_pixels); drop -1.
+ * `unique_out` needs room for min(n_entries, max_pixel_id) ids; *n_unique is a device int64. */
+int lsb_unique_pixels(const int32_t* pixels, int64_t n_entries, int64_t max_pixel_id,
+                      int32_t* unique_out, int64_t* n_unique, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+int64_t lsb_unique_pixels_workspace_bytes(int64_t max_pixel_id);
+/* cli/simulate_pixels.py:1021-1025  pixel_index_map[s][p] = index of pixels[s][p] in unique_pix (else -1).
+ * Uses the rank table left in `workspace` by lsb_unique_pixels. */
+int lsb_pixel_index_map(const int32_t* pixels, int64_t n_entries, int64_t max_pixel_id,
+                        const void* workspace, int64_t* pixel_index_map, void* stream);
+/* same, but by binary search in an arbitrary sorted unique_pix (no workspace) */
+int lsb_pixel_index_map_search(const int32_t* pixels, int64_t n_entries, const int32_t* unique_pix,
+                               int64_t n_unique, int64_t* pixel_index_map, void* stream);
+
+/* ---- induced current ---------------------------------------------------------------- */
+/* larndsim/detsim.py:258-348  tracks_current_mc(signals, pixels, tracks, response, rng_states)
+ *  signals f32[S][P][T]; pixels i32[S][P]; response [Rx][Ry][Rt] f32 (response_f64=0) or f64;
+ *  rng_states {u8,u8}[>= S*P], state of (itrk,ipix) at index itrk + S*ipix (detsim.py:324).
+ *  rng_mode 0 ("cloud", production): one sample cloud per (segment,pixel), drawn z,x,y per
+ *    step from that stream and applied to every tick -- what a converged warp of the
+ *    reference does; statistically equivalent, exact when tran_diff=long_diff=0.
+ *  rng_mode 1 ("replay"): the reference's draw pattern thread for thread with ticks
+ *    consumed in order (= the CUDA simulator with 1-thread blocks); sequential per pair. */
+int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
+                          const int32_t* pixels, int32_t P, float* signals, int32_t T,
+                          const void* response, int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64,
+                          uint64_t* rng_states, int64_t n_rng, int32_t rng_mode,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total);
+/* larndsim/detsim.py:351-453  tracks_current(signals, pixels, tracks, response) */
+int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
+                       const int32_t* pixels, int32_t P, float* signals, int32_t T,
+                       const void* response, int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64,
+                       void* stream);
+
+/* ---- per-pixel reduction ------------------------------------------------------------ */
+/* larndsim/detsim.py:529-562  get_track_pixel_map(track_pixel_map, unique_pix, pixels) */
+int lsb_get_track_pixel_map(int64_t* track_pixel_map, int32_t K, const int32_t* unique_pix, int64_t U,
+                            const int32_t* pixels, int64_t S, int32_t P, void* stream);
+/* larndsim/detsim.py:564-607  get_track_pixel_map2(track_pixel_map, unique_pix, pixels, distances, max_distance) */
+int lsb_get_track_pixel_map2(int64_t* track_pixel_map, int32_t K, const int32_t* unique_pix, int64_t U,
+                             const int32_t* pixels, const int32_t* distances, int64_t S, int32_t P,
+                             int32_t max_distance, void* stream);
+/* larndsim/detsim.py:468-527  sum_pixel_signals(pixels_signals, signals, track_starts, pixel_index_map,
+ *                                              track_pixel_map, pixels_tracks_signals, overflow_flag)
+ * Gather formulation: contributions to one pixel are added in ascending segment order, so
+ * sums are reproducible (the reference's float64 atomics are order-free). */
+int lsb_sum_pixel_signals(const lsb_consts* c, double* pixels_signals, int64_t U, int32_t Tt,
+                          const float* signals, int64_t S, int32_t P, int32_t T,
+                          const double* track_starts, const int64_t* pixel_index_map,
+                          const int64_t* track_pixel_map, int32_t K,
+                          double* pixels_tracks_signals, double* overflow_flag, void* stream);
+
+/* ---- front-end electronics ---------------------------------------------------------- */
+/* larndsim/fee.py:517-655  get_adc_values(pixels_signals, pixels_signals_tracks, time_ticks, adc_list,
+ *        adc_ticks_list, time_padding, rng_states, current_fractions, pixel_thresholds) */
+int lsb_get_adc_values(const lsb_consts* c, const double* pixels_signals, const double* pixels_signals_tracks,
+                       int64_t U, int32_t Tt, int32_t K,
+                       const double* time_ticks, int32_t n_time_ticks,
+                       double* adc_list, double* adc_ticks_list, int32_t A, double time_padding,
+                       uint64_t* rng_states, int64_t n_rng,
+                       double* current_fractions, const double* pixel_thresholds, void* stream);
+/* larndsim/fee.py:499-515  digitize(integral_list[, gain]); gain_list may be NULL (scalar gain*mV/e) */
+int lsb_digitize(const lsb_consts* c, const double* integral_list, const double* gain_list, int64_t n,
+                 double* adcs, void* stream);
+
+/* ---- light ---------------------------------------------------------------------------- */
+/* larndsim/lightLUT.py:65-136  calculate_light_incidence(tracks, lut, light_incidence, voxel) */
+int lsb_calculate_light_incidence(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
+                                  const void* lut, const lsb_lut_layout* LL,
+                                  void* light_incidence, const lsb_linc_layout* LI, int32_t ndet,
+                                  int32_t* voxel, const double* op_channel_efficiency,
+                                  const int64_t* op_channel_to_tpc, void* stream);
+/* larndsim/light_sim.py:58-129  sum_light_signals(...) */
+int lsb_sum_light_signals(const lsb_consts* c, const lsb_track_layout* L, const void* segments, int64_t S,
+                          const int32_t* segment_voxel, const int64_t* segment_track_id,
+                          const void* light_inc, const lsb_linc_layout* LI, int32_t ndet_inc,
+                          const int32_t* op_channel, const void* lut, const lsb_lut_layout* LL,
+                          double start_time, float* light_sample_inc, int32_t ndet, int32_t nticks,
+                          int64_t* true_track_id, double* true_photons, int32_t n_true,
+                          const int64_t* sorted_indices, int64_t n_sorted, double t0_profile_length,
+                          void* stream);
+/* larndsim/light_sim.py:148-183  calc_scintillation_effect(6 arrays) */
+int lsb_calc_scintillation_effect(const lsb_consts* c, const float* light_sample_inc,
+                                  const int64_t* inc_true_track_id, const double* inc_true_photons,
+                                  float* light_sample_inc_scint, int64_t* scint_true_track_id,
+                                  double* scint_true_photons, int32_t ndet, int32_t nticks,
+                                  int32_t n_true_in, int32_t n_true_out, void* stream);
+/* larndsim/light_sim.py:220-238  calc_stat_fluctuations(in, out, rng_states) */
+int lsb_calc_stat_fluctuations(const lsb_consts* c, const float* light_sample_inc, float* light_sample_inc_disc,
+                               int32_t ndet, int32_t nticks, uint64_t* rng_states, int64_t n_rng, void* stream);
+/* larndsim/light_sim.py:303-336  calc_light_detector_response(6 arrays);
+ * light_gain = light.LIGHT_GAIN (f64[ndet...]); impulse_model = light.IMPULSE_MODEL (f64[n_impulse]) */
+int lsb_calc_light_detector_response(const lsb_consts* c, const float* light_sample_inc,
+                                     const int64_t* inc_true_track_id, const double* inc_true_photons,
+                                     float* light_response, int64_t* resp_true_track_id,
+                                     double* resp_true_photons, int32_t ndet, int32_t nticks,
+                                     int32_t n_true_in, int32_t n_true_out,
+                                     const double* light_gain, const double* impulse_model, int32_t n_impulse,
+                                     void* stream);
+
+/* ---- fused device-resident batch driver (replaces cli/simulate_pixels.py:907-1117) ---- */
+typedef struct lsb_chain lsb_chain;   /* opaque; owns its device workspace */
+
+typedef struct lsb_chain_result {
+    int64_t n_segments, n_unique_pixels, max_active, max_neighbors, n_ticks;   /* S, U, maxpix, P, T */
+    int64_t n_hits;                   /* adc_list entries above pedestal */
+    int64_t n_samples, n_fma;         /* MC sample points / (sample,tick) LUT reads (roofline) */
+    /* device pointers valid until the next run / destroy */
+    const int32_t* unique_pix;        /* [U] */
+    const int64_t* track_pixel_map;   /* [U][K] */
+    const double*  adc_list;          /* [U][A] integrated charge */
+    const double*  adc_digit;         /* [U][A] digitize(adc_list) */
+    const double*  adc_ticks_list;    /* [U][A] */
+    const double*  current_fractions; /* [U][A][K] */
+    const float*   signals;           /* [S][P][T] */
+    const double*  pixels_signals;    /* [U][Tt] */
+    float stage_ms[12];               /* per-stage CUDA-event times of the last run (if timing enabled) */
+} lsb_chain_result;
+
+lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layout* L,
+                            const void* response, int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64,
+                            int32_t rng_mode, int32_t enable_stage_timing);
+void       lsb_chain_destroy(lsb_chain* h);
+/* tracks on the device, modified in place by quench/drift like the reference */
+int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                  int32_t n_events, lsb_chain_result* out, void* stream);
+/* tracks in (pinned) host memory: H2D, chain, D2H of the packet-level outputs into host buffers
+ * sized by the caller (adc_digit/adc_ticks U_cap*A doubles, unique_pix U_cap int32); the e2e path. */
+int lsb_chain_run_host(lsb_chain* h, void* tracks_host, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                       int32_t n_events, int32_t* unique_pix_host, double* adc_digit_host,
+                       double* adc_ticks_host, int64_t U_cap, lsb_chain_result* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LARNDSIM_B200_H */

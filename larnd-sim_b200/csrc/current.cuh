@@ -1,0 +1,783 @@
+// current.cuh -- induced current on the pixels: tracks_current_mc (detsim.py:258-348) and the
+// deterministic tracks_current (detsim.py:351-453).
+//
+// tracks_current_mc, production ("cloud") mode, is three kernels:
+//   k_mc_pairs      thread per (segment,pixel): tick-independent geometry (detsim.py:275-322), FP64
+//                   where Numba promotes, float32-rounded where Numba keeps float32.
+//   k_mc_sampler    thread per pair: consumes that pair's xoroshiro128+ stream (z,x,y normals per
+//                   step), resolves every sample to {LUT row offset, tick shift, valid tick range}
+//                   with the reference's FP64 round()/window expressions evaluated exactly.
+//   k_mc_accumulate CTA per pair: signal[tick] = charge * sum_samples LUT[row][stride*tick+shift].
+//                   Ticks inside the intersection of all sample windows ("interior", ~98% of the
+//                   work) run an unconditional LDG+FADD stream, 2 instructions per LUT read;
+//                   the few edge ticks and irregular samples take an exact predicated path.
+// Replay mode (k_mc_replay) is the reference's thread-for-thread draw pattern, sequential per pair.
+#pragma once
+#include "common.cuh"
+#include "glue.cuh"
+
+struct PairRec {
+    double x_p, y_p, t_start, z_anode;
+    double sub_start[3];
+    double dir[3];
+    double step, charge, sig_t, sig_l;
+    long long nstep;          // steps * MC_SAMPLE_MULTIPLIER handled in the loops
+    long long sample_off;     // first SampleRec of this pair
+    int valid, s32;
+    int it_first;             // first tick with time_tick >= 0 (T if none)
+    int n_live;               // live samples written by the sampler
+    int n_irregular;          // live samples that need the exact per-tick path
+    int int_lo, int_hi;       // intersection of the live regular samples' tick ranges
+    int uni_lo, uni_hi;       // union of all live samples' tick ranges
+};
+
+struct SampleRec {
+    double t0;
+    int rowoff;               // (i*Ry + j)*Rt
+    int shift;                // k = stride*tick + shift ; INT_MIN: irregular -> exact per-tick path
+    int lo, hi;               // valid ticks [lo, hi]
+};
+#define SHIFT_IRREGULAR (-2147483647 - 1)
+#define OFF_IRREGULAR (-2147483647 - 1)
+
+struct McParams {
+    long long S;              // segments in this launch
+    long long seg0;           // global index of the first segment (multi-pass)
+    long long rng_stride;     // ntrk of detsim.py:324
+    int P, T, Rx, Ry, Rt;
+    int stride;               // TIME_SAMPLING / RESPONSE_SAMPLING if integral, else 0
+};
+
+__device__ __forceinline__ double tick_time(double t_start, int it) { return t_start + (double)it * d_c.time_sampling; }
+
+// overlapping_segment (detsim.py:220-256)
+__device__ void overlapping_segment(double x, double y, const double* start, const double* end, double radius, bool c32,
+                                    double* ns, double* ne) {
+    double dxy0 = x - start[0], dxy1 = y - start[1];
+    double v0 = R32(end[0] - start[0], c32), v1 = R32(end[1] - start[1], c32);
+    double l = R32(sqrt(R32(R32(v0 * v0, c32) + R32(v1 * v1, c32), c32)), c32);
+    v0 = R32(v0 / l, c32); v1 = R32(v1 / l, c32);
+    double s = (dxy0 * v0 + dxy1 * v1) / l;
+    double a = dxy0 - v0 * s * l, b = dxy1 - v1 * s * l;
+    double r = sqrt(a * a + b * b);
+    if (r > radius) { for (int k = 0; k < 3; k++) { ns[k] = start[k]; ne[k] = start[k]; } return; }
+    double s_plus = s + sqrt(radius * radius - r * r) / l;
+    double s_minus = s - sqrt(radius * radius - r * r) / l;
+    if (s_plus > 1) s_plus = 1; else if (s_plus < 0) s_plus = 0;
+    if (s_minus > 1) s_minus = 1; else if (s_minus < 0) s_minus = 0;
+    for (int k = 0; k < 3; k++) {
+        ns[k] = start[k] * (1 - s_minus) + end[k] * s_minus;
+        ne[k] = start[k] * (1 - s_plus) + end[k] * s_plus;
+    }
+}
+
+// ordered segment end points (detsim.py:289-294) and float32-typed direction (:302-305)
+__device__ __forceinline__ void load_endpoints(const Layout& L, const char* t, double* start, double* end, bool& c32) {
+    c32 = fld_f32(L, LSB_F_X_START) && fld_f32(L, LSB_F_Y_START) && fld_f32(L, LSB_F_Z_START) &&
+          fld_f32(L, LSB_F_X_END) && fld_f32(L, LSB_F_Y_END) && fld_f32(L, LSB_F_Z_END);
+    double zs = fld_get(L, t, LSB_F_Z_START), ze = fld_get(L, t, LSB_F_Z_END);
+    if (zs < ze) {
+        start[0] = fld_get(L, t, LSB_F_X_START); start[1] = fld_get(L, t, LSB_F_Y_START); start[2] = zs;
+        end[0] = fld_get(L, t, LSB_F_X_END); end[1] = fld_get(L, t, LSB_F_Y_END); end[2] = ze;
+    } else {
+        end[0] = fld_get(L, t, LSB_F_X_START); end[1] = fld_get(L, t, LSB_F_Y_START); end[2] = zs;
+        start[0] = fld_get(L, t, LSB_F_X_END); start[1] = fld_get(L, t, LSB_F_Y_END); start[2] = ze;
+    }
+}
+__device__ __forceinline__ double seg_length(const double* seg, bool c32) {
+    return R32(sqrt(R32(R32(R32(seg[0] * seg[0], c32) + R32(seg[1] * seg[1], c32), c32) + R32(seg[2] * seg[2], c32), c32)), c32);
+}
+// pixel centre (get_pixel_coordinates detsim.py:180-191 + :285-288); pID=-1 wraps like Python
+__device__ __forceinline__ bool pixel_center(int pID, double& x_p, double& y_p) {
+    long long px, py, pl;
+    id2pixel(pID, px, py, pl);
+    if (pl < 0) pl += d_c.n_tpc;                       // negative index wraps to the last TPC
+    if (pl < 0 || pl >= d_c.n_tpc) return false;
+    const double (*b)[2] = d_c.tpc_borders[pl];
+    x_p = (double)px * d_c.pixel_pitch + b[0][0] + d_c.pixel_pitch / 2;
+    y_p = (double)py * d_c.pixel_pitch + b[1][0] + d_c.pixel_pitch / 2;
+    return true;
+}
+
+__device__ void mc_pair_geometry(const Layout& L, const char* t, int pID, int Rx, int Ry, int T, PairRec& g) {
+    g.valid = 0; g.nstep = 0; g.n_live = 0; g.n_irregular = 0;
+    if (!pixel_center(pID, g.x_p, g.y_p)) return;
+    bool c32;
+    double start[3], end[3];
+    load_endpoints(L, t, start, end, c32);
+    g.s32 = fld_f32(L, LSB_F_TRAN_DIFF) && fld_f32(L, LSB_F_LONG_DIFF);
+    g.t_start = (double)__double2ll_rn((fld_get(L, t, LSB_F_T_START) - fld_get(L, t, LSB_F_T0_START) - d_c.time_padding) /
+                                       d_c.time_sampling) * d_c.time_sampling;
+    double seg[3];
+    for (int k = 0; k < 3; k++) seg[k] = R32(end[k] - start[k], c32);
+    double length = seg_length(seg, c32);
+    for (int k = 0; k < 3; k++) g.dir[k] = R32(seg[k] / length, c32);
+    g.sig_t = fld_get(L, t, LSB_F_TRAN_DIFF);
+    g.sig_l = fld_get(L, t, LSB_F_LONG_DIFF);
+    double impact = sqrt((double)((long long)Rx * Rx + (long long)Ry * Ry)) * d_c.response_bin_size;
+    double ss[3], se[3];
+    overlapping_segment(g.x_p, g.y_p, start, end, impact, c32, ss, se);
+    double sub[3] = {se[0] - ss[0], se[1] - ss[1], se[2] - ss[2]};
+    double sub_len = sqrt(sub[0] * sub[0] + sub[1] * sub[1] + sub[2] * sub[2]);
+    if (sub_len == 0) return;
+    long long ns = __double2ll_rn(sub_len / d_c.min_step_size);
+    g.nstep = ns > 1 ? ns : 1;
+    g.step = sub_len / (double)g.nstep;
+    g.charge = fld_get(L, t, LSB_F_N_ELECTRONS) * (sub_len / length) / (double)(g.nstep * d_c.mc_sample_multiplier);
+    for (int k = 0; k < 3; k++) g.sub_start[k] = ss[k];
+    long long plane = (long long)fld_get(L, t, LSB_F_PIXEL_PLANE);
+    if (plane < 0 || plane >= d_c.n_tpc) { g.nstep = 0; return; }
+    g.z_anode = d_c.tpc_borders[plane][2][0];
+    // first tick with time_tick >= 0 (monotone in it)
+    int f = 0;
+    if (tick_time(g.t_start, 0) < 0) {
+        double e = ceil(-g.t_start / d_c.time_sampling);
+        f = e > (double)T ? T : (int)e;
+        while (f > 0 && tick_time(g.t_start, f - 1) >= 0) f--;
+        while (f < T && tick_time(g.t_start, f) < 0) f++;
+    }
+    g.it_first = f;
+    g.valid = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_mc_pairs(Layout L, const char* __restrict__ tracks, const int32_t* __restrict__ pixels, McParams p,
+                           PairRec* __restrict__ pairs, uint32_t* __restrict__ nsamp) {
+    long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pr >= p.S * p.P) return;
+    long long itrk = pr / p.P;
+    PairRec g;
+    mc_pair_geometry(L, tracks + (p.seg0 + itrk) * L.itemsize, pixels[(p.seg0 + itrk) * p.P + (pr % p.P)], p.Rx, p.Ry, p.T, g);
+    long long n = g.valid ? g.nstep * d_c.mc_sample_multiplier : 0;
+    if (n > 0xffffffffLL) n = 0xffffffffLL;
+    nsamp[pr] = (uint32_t)n;
+    pairs[pr] = g;
+}
+
+__global__ void k_mc_set_offsets(PairRec* __restrict__ pairs, const long long* __restrict__ offs, long long n) {
+    long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pr < n) pairs[pr].sample_off = offs[pr];
+}
+
+struct SampleGeom { bool live; double t0; int rowoff; };
+// one MC sample given its three normals (detsim.py:326-346 without the tick dependence)
+__device__ __forceinline__ SampleGeom mc_sample(const PairRec& g, long long istep, float nz, float nx, float ny,
+                                                int Rx, int Ry, int Rt) {
+    SampleGeom s;
+    double f = (double)istep + 0.5;
+    double x = g.sub_start[0] + g.step * f * g.dir[0];
+    double y = g.sub_start[1] + g.step * f * g.dir[1];
+    double z = g.sub_start[2] + g.step * f * g.dir[2];
+    z += R32((double)nz * g.sig_l, g.s32);
+    s.t0 = fabs(z - g.z_anode) / d_c.v_drift - d_c.time_window;
+    x += R32((double)nx * g.sig_t, g.s32);
+    y += R32((double)ny * g.sig_t, g.s32);
+    double x_dist = fabs(g.x_p - x), y_dist = fabs(g.y_p - y);
+    s.live = true;
+    if (x_dist > d_c.response_bin_size * Rx) s.live = false;
+    if (y_dist > d_c.response_bin_size * Ry) s.live = false;
+    long long i = __double2ll_rn(x_dist / d_c.response_bin_size - 0.5);
+    long long j = __double2ll_rn(y_dist / d_c.response_bin_size - 0.5);
+    if (!(0 <= i && i < Rx && 0 <= j && j < Ry)) s.live = false;
+    s.rowoff = s.live ? (int)((i * Ry + j) * (long long)Rt) : -1;
+    return s;
+}
+__device__ __forceinline__ long long resp_k(double tick, double t0) { return __double2ll_rn((tick - t0) / d_c.response_sampling); }
+
+__global__ void k_mc_sampler(McParams p, PairRec* __restrict__ pairs, SampleRec* __restrict__ samples,
+                             int* __restrict__ offs32, unsigned long long* __restrict__ rng_states) {
+    long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pr >= p.S * p.P) return;
+    PairRec g = pairs[pr];
+    if (!g.valid) return;
+    long long itrk = p.seg0 + pr / p.P;
+    int ipix = (int)(pr % p.P);
+    unsigned long long* sp = rng_states + 2 * (itrk + p.rng_stride * ipix);
+    Rng rng; rng.s0 = sp[0]; rng.s1 = sp[1];
+    SampleRec* out = samples + g.sample_off;
+    int* out32 = offs32 + g.sample_off;
+    int n_live = 0, n_irr = 0, int_lo = 0, int_hi = p.T - 1, uni_lo = p.T, uni_hi = -1;
+    const int M = d_c.mc_sample_multiplier;
+    const double W = d_c.time_window, TS = d_c.time_sampling;
+    for (long long istep = 0; istep < g.nstep; istep++)
+        for (int m = 0; m < M; m++) {
+            float nz = rng_normal_f32(rng);
+            float nx = rng_normal_f32(rng);
+            float ny = rng_normal_f32(rng);
+            SampleGeom s = mc_sample(g, istep, nz, nx, ny, p.Rx, p.Ry, p.Rt);
+            if (!s.live) continue;
+            double t0 = s.t0, t0W = t0 + W;
+            // lower bound: first tick with tick>=0, tick>t0, k>=0 (all monotone in the tick index)
+            double tl = t0 > 0 ? t0 : 0;
+            double e = floor((tl - g.t_start) / TS);
+            int lo = e < 0 ? 0 : (e > (double)p.T ? p.T : (int)e);
+#define LOW_OK(it) (tick_time(g.t_start, (it)) >= 0 && t0 < tick_time(g.t_start, (it)) && resp_k(tick_time(g.t_start, (it)), t0) >= 0)
+            while (lo > 0 && LOW_OK(lo - 1)) lo--;
+            while (lo < p.T && !LOW_OK(lo)) lo++;
+            // upper bound: last tick with tick < t0+W and k < Rt
+            e = ceil((t0W - g.t_start) / TS);
+            int hi = e < -1 ? -1 : (e > (double)(p.T - 1) ? p.T - 1 : (int)e);
+#define HIGH_OK(it) (tick_time(g.t_start, (it)) < t0W && resp_k(tick_time(g.t_start, (it)), t0) < p.Rt)
+            while (hi < p.T - 1 && HIGH_OK(hi + 1)) hi++;
+            while (hi >= 0 && !HIGH_OK(hi)) hi--;
+            if (lo > hi) continue;
+            int shift = SHIFT_IRREGULAR;
+            if (p.stride > 0) {
+                long long klo = resp_k(tick_time(g.t_start, lo), t0), khi = resp_k(tick_time(g.t_start, hi), t0);
+                long long sh = klo - (long long)p.stride * lo;
+                if (khi == (long long)p.stride * hi + sh) shift = (int)sh;
+            }
+            SampleRec r; r.t0 = t0; r.rowoff = s.rowoff; r.shift = shift; r.lo = lo; r.hi = hi;
+            out[n_live] = r;
+            out32[n_live] = (shift == SHIFT_IRREGULAR) ? OFF_IRREGULAR : s.rowoff + shift;
+            n_live++;
+            if (shift != SHIFT_IRREGULAR) { int_lo = lo > int_lo ? lo : int_lo; int_hi = hi < int_hi ? hi : int_hi; }
+            else n_irr++;
+            uni_lo = lo < uni_lo ? lo : uni_lo; uni_hi = hi > uni_hi ? hi : uni_hi;
+        }
+#undef LOW_OK
+#undef HIGH_OK
+    sp[0] = rng.s0; sp[1] = rng.s1;
+    PairRec* gp = pairs + pr;
+    gp->n_live = n_live; gp->n_irregular = n_irr; gp->int_lo = int_lo; gp->int_hi = int_hi; gp->uni_lo = uni_lo; gp->uni_hi = uni_hi;
+}
+
+// ---------------------------------------------------------------------------------------
+#define ACC_TPB 256
+#define ACC_RMAX 8
+#define ACC_CHUNK 256      // samples staged per smem chunk
+
+template <typename TL, int STRIDE, int NFULL>
+__device__ __forceinline__ void acc_interior(const TL* __restrict__ lut, const int* s_off, int ns, int base_tick, bool rem_ok,
+                                             float (&acc)[ACC_RMAX]) {
+    // signal[base_tick + tid + TPB*r] += LUT[off + STRIDE*(base_tick + tid + TPB*r)]
+    const TL* pbase = lut + (long long)STRIDE * (base_tick + (int)threadIdx.x);
+#pragma unroll 2
+    for (int s = 0; s < ns; s++) {
+        int off = s_off[s];
+        if (off == OFF_IRREGULAR) continue;    // irregular sample: handled by the exact path
+        const TL* p = pbase + off;
+#pragma unroll
+        for (int r = 0; r < NFULL; r++) acc[r] += (float)__ldg(p + r * ACC_TPB * STRIDE);
+        if (NFULL < ACC_RMAX) {
+            if (rem_ok) acc[NFULL] += (float)__ldg(p + NFULL * ACC_TPB * STRIDE);
+        }
+    }
+}
+
+template <typename TL, int STRIDE>
+__global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
+                                                           const SampleRec* __restrict__ samples,
+                                                           const int* __restrict__ offs32, const TL* __restrict__ lut,
+                                                           float* __restrict__ signals) {
+    long long pr = blockIdx.x;
+    const PairRec* gp = pairs + pr;
+    if (!gp->valid) return;
+    __shared__ int s_off[ACC_CHUNK];
+    __shared__ SampleRec s_rec[ACC_CHUNK];
+    const int tid = threadIdx.x;
+    const int T = p.T;
+    const int it_first = gp->it_first, n_live = gp->n_live;
+    const double charge = gp->charge, t_start = gp->t_start;
+    const long long soff = gp->sample_off;
+    long long itrk = p.seg0 + pr / p.P;
+    float* out = signals + (itrk * p.P + (pr % p.P)) * (long long)T;
+    const int n_irr = gp->n_irregular;
+    const int uni_lo = gp->uni_lo, uni_hi = gp->uni_hi;
+    int int_lo = gp->int_lo, int_hi = gp->int_hi;
+    if (STRIDE == 0 || n_live - n_irr <= 0 || int_lo > int_hi) { int_lo = 0; int_hi = -1; }   // no interior
+
+    // ---- interior ticks: unconditional gather stream --------------------------------
+    if (STRIDE > 0) {
+        for (int base = int_lo; base <= int_hi; base += ACC_TPB * ACC_RMAX) {
+            int n_int = int_hi - base + 1;
+            if (n_int > ACC_TPB * ACC_RMAX) n_int = ACC_TPB * ACC_RMAX;
+            const int nfull = n_int / ACC_TPB, rem = n_int - nfull * ACC_TPB;
+            const bool rem_ok = tid < rem;
+            float acc[ACC_RMAX];
+            double dacc[ACC_RMAX];
+#pragma unroll
+            for (int r = 0; r < ACC_RMAX; r++) { acc[r] = 0.f; dacc[r] = 0.0; }
+            for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
+                int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
+                __syncthreads();
+                if (tid < ns) s_off[tid] = offs32[soff + c0 + tid];
+                __syncthreads();
+                switch (nfull) {
+                    case 0: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 0>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 1: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 1>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 2: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 2>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 3: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 3>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 4: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 4>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 5: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 5>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 6: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 6>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 7: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 7>(lut, s_off, ns, base, rem_ok, acc); break;
+                    default: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 8>(lut, s_off, ns, base, rem_ok, acc); break;
+                }
+                // flush the float32 partial sums into float64 every chunk (bounds rounding growth)
+#pragma unroll
+                for (int r = 0; r < ACC_RMAX; r++) { dacc[r] += (double)acc[r]; acc[r] = 0.f; }
+            }
+            // irregular samples (off < 0) contribute to interior ticks through the exact path below,
+            // so interior results are written with "+=" semantics into a zeroed output: store now,
+            // the exact path adds on top.
+#pragma unroll
+            for (int r = 0; r < ACC_RMAX; r++) {
+                int it = base + tid + r * ACC_TPB;
+                if (it <= int_hi && (r < nfull || (r == nfull && rem_ok))) out[it] = __double2float_rn(charge * dacc[r]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- (a) ticks >= it_first that no sample covers: the reference stores total_current = 0 ----
+    for (int it = it_first + tid; it < T; it += ACC_TPB)
+        if (n_live == 0 || it < uni_lo || it > uni_hi) out[it] = 0.f;
+
+    // ---- (b) edge ticks: inside the union of the sample windows but outside the interior -------
+    if (STRIDE > 0 && n_live - n_irr > 0) {
+        int n_left, right0;
+        if (int_lo <= int_hi) { n_left = int_lo - uni_lo; right0 = int_hi + 1; }
+        else { n_left = uni_hi - uni_lo + 1; right0 = uni_hi + 1; }
+        int n_edge = n_left + (uni_hi - right0 + 1);
+        for (int e0 = 0; e0 < n_edge; e0 += ACC_TPB) {
+            int e = e0 + tid;
+            bool active = e < n_edge;
+            int it = e < n_left ? uni_lo + e : right0 + (e - n_left);
+            double sum = 0.0;
+            for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
+                int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
+                __syncthreads();
+                if (tid < ns) s_rec[tid] = samples[soff + c0 + tid];
+                __syncthreads();
+                if (!active) continue;
+                for (int s = 0; s < ns; s++) {
+                    const SampleRec& r = s_rec[s];
+                    if (r.shift == SHIFT_IRREGULAR || it < r.lo || it > r.hi) continue;
+                    sum += (double)lut[(long long)r.rowoff + (long long)STRIDE * it + r.shift];
+                }
+            }
+            if (active) out[it] = __double2float_rn(charge * sum);
+        }
+    }
+
+    // ---- (c) irregular samples (tick shift not affine, or non-integral sampling ratio): exact
+    //          per-tick evaluation of detsim.py:333 and :211-218, added on top ----------------
+    if (n_irr > 0) {
+        const double TS = d_c.time_sampling, W = d_c.time_window;
+        __syncthreads();
+        for (int it0 = it_first; it0 < T; it0 += ACC_TPB) {
+            int it = it0 + tid;
+            bool active = it < T;
+            double sum = 0.0;
+            bool any = false;
+            for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
+                int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
+                __syncthreads();
+                if (tid < ns) s_rec[tid] = samples[soff + c0 + tid];
+                __syncthreads();
+                if (!active) continue;
+                for (int s = 0; s < ns; s++) {
+                    const SampleRec& r = s_rec[s];
+                    if (r.shift != SHIFT_IRREGULAR) continue;
+                    double tick = t_start + (double)it * TS;
+                    if (tick < 0) continue;
+                    if (!(r.t0 < tick && tick < r.t0 + W)) continue;
+                    long long k = __double2ll_rn((tick - r.t0) / d_c.response_sampling);
+                    if (0 <= k && k < p.Rt) { sum += (double)lut[(long long)r.rowoff + k]; any = true; }
+                }
+            }
+            if (active && any) out[it] = __double2float_rn((double)out[it] + charge * sum);
+        }
+    }
+}
+
+// replay mode: literal reference order, one thread per pair (detsim.py:324-348)
+template <typename TL>
+__global__ void k_mc_replay(McParams p, const PairRec* __restrict__ pairs, const TL* __restrict__ lut,
+                            float* __restrict__ signals, unsigned long long* __restrict__ rng_states) {
+    long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pr >= p.S * p.P) return;
+    PairRec g = pairs[pr];
+    if (!g.valid) return;
+    long long itrk = p.seg0 + pr / p.P;
+    int ipix = (int)(pr % p.P);
+    unsigned long long* sp = rng_states + 2 * (itrk + p.rng_stride * ipix);
+    Rng rng; rng.s0 = sp[0]; rng.s1 = sp[1];
+    float* out = signals + (itrk * p.P + ipix) * (long long)p.T;
+    const int M = d_c.mc_sample_multiplier;
+    for (int it = g.it_first; it < p.T; it++) {
+        double time_tick = g.t_start + (double)it * d_c.time_sampling;
+        if (time_tick < 0) continue;
+        double total = 0;
+        for (long long istep = 0; istep < g.nstep; istep++)
+            for (int m = 0; m < M; m++) {
+                double f = (double)istep + 0.5;
+                double x = g.sub_start[0] + g.step * f * g.dir[0];
+                double y = g.sub_start[1] + g.step * f * g.dir[1];
+                double z = g.sub_start[2] + g.step * f * g.dir[2];
+                z += R32((double)rng_normal_f32(rng) * g.sig_l, g.s32);
+                double t0 = fabs(z - g.z_anode) / d_c.v_drift - d_c.time_window;
+                if (!(t0 < time_tick && time_tick < t0 + d_c.time_window)) continue;
+                x += R32((double)rng_normal_f32(rng) * g.sig_t, g.s32);
+                y += R32((double)rng_normal_f32(rng) * g.sig_t, g.s32);
+                double x_dist = fabs(g.x_p - x), y_dist = fabs(g.y_p - y);
+                if (x_dist > d_c.response_bin_size * p.Rx) continue;
+                if (y_dist > d_c.response_bin_size * p.Ry) continue;
+                long long i = __double2ll_rn(x_dist / d_c.response_bin_size - 0.5);
+                long long j = __double2ll_rn(y_dist / d_c.response_bin_size - 0.5);
+                long long k = __double2ll_rn((time_tick - t0) / d_c.response_sampling);
+                if (0 <= i && i < p.Rx && 0 <= j && j < p.Ry && 0 <= k && k < p.Rt)
+                    total += g.charge * (double)lut[(i * p.Ry + j) * (long long)p.Rt + k];
+            }
+        out[it] = __double2float_rn(total);
+    }
+    sp[0] = rng.s0; sp[1] = rng.s1;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct McWs {
+    PairRec* pairs; uint32_t* nsamp; long long* offs; long long* block_sums; long long* total;
+    SampleRec* samples; int* offs32; long long sample_cap;
+};
+static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+static inline long long mc_fixed_bytes(long long npair) {
+    return align_up(npair * (long long)sizeof(PairRec), 256) + align_up(npair * 4, 256) + align_up(npair * 8, 256) +
+           align_up((scan_num_blocks(npair) + 1) * 8, 256) + 256;
+}
+LSB_EXPORT int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total) {
+    return mc_fixed_bytes(S * (long long)P) + align_up(max_steps_total * (long long)sizeof(SampleRec), 256) +
+           align_up(max_steps_total * 4, 256);
+}
+static inline bool mc_carve(void* ws, long long bytes, long long npair, McWs& w) {
+    char* p = (char*)ws;
+    long long fixed = mc_fixed_bytes(npair);
+    if (bytes < fixed + 28 * 64) return false;
+    w.pairs = (PairRec*)p; p += align_up(npair * (long long)sizeof(PairRec), 256);
+    w.nsamp = (uint32_t*)p; p += align_up(npair * 4, 256);
+    w.offs = (long long*)p; p += align_up(npair * 8, 256);
+    w.block_sums = (long long*)p; p += align_up((scan_num_blocks(npair) + 1) * 8, 256);
+    w.total = (long long*)p; p += 256;
+    long long rest = bytes - fixed;
+    w.sample_cap = (rest - 512) / 28;
+    w.samples = (SampleRec*)p; p += align_up(w.sample_cap * (long long)sizeof(SampleRec), 256);
+    w.offs32 = (int*)p;
+    return w.sample_cap > 0;
+}
+
+template <typename TL>
+static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut, float* signals, cudaStream_t st) {
+    unsigned grid = (unsigned)(p.S * p.P);
+    if (p.stride == 1) k_mc_accumulate<TL, 1><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, lut, signals);
+    else if (p.stride == 2) k_mc_accumulate<TL, 2><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, lut, signals);
+    else k_mc_accumulate<TL, 0><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, lut, signals);
+    LSB_LAUNCH_CHECK("k_mc_accumulate");
+    return 0;
+}
+
+// statistics of the last call (roofline accounting)
+static long long g_mc_last_samples = 0;
+
+static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixels, float* signals, const void* response,
+                        int f64, unsigned long long* rng, int mode, McParams p, void* ws, long long ws_bytes,
+                        cudaStream_t st, int depth) {
+    McWs w;
+    long long npair = p.S * p.P;
+    if (!mc_carve(ws, ws_bytes, npair, w)) return lsb_fail_arg("tracks_current_mc: workspace too small");
+    k_mc_pairs<<<lsb_blocks(npair, 128), 128, 0, st>>>(L, (const char*)tracks, pixels, p, w.pairs, w.nsamp);
+    LSB_LAUNCH_CHECK("k_mc_pairs");
+    if (mode == 1) {
+        if (f64) k_mc_replay<double><<<lsb_blocks(npair, 64), 64, 0, st>>>(p, w.pairs, (const double*)response, signals, rng);
+        else k_mc_replay<float><<<lsb_blocks(npair, 64), 64, 0, st>>>(p, w.pairs, (const float*)response, signals, rng);
+        LSB_LAUNCH_CHECK("k_mc_replay");
+        return 0;
+    }
+    int rc = exclusive_scan<uint32_t, long long>(w.nsamp, npair, w.offs, w.block_sums, w.total, st);
+    if (rc) return rc;
+    long long total = 0;
+    LSB_CUDA(cudaMemcpyAsync(&total, w.total, 8, cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
+    if (total > w.sample_cap) {
+        if (p.S <= 1) return lsb_fail_arg("tracks_current_mc: workspace too small for a single segment");
+        if (depth > 40) return lsb_fail_arg("tracks_current_mc: workspace split too deep");
+        McParams a = p, b = p;
+        a.S = p.S / 2; b.S = p.S - a.S; b.seg0 = p.seg0 + a.S;
+        rc = mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, a, ws, ws_bytes, st, depth + 1);
+        if (rc) return rc;
+        return mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, b, ws, ws_bytes, st, depth + 1);
+    }
+    g_mc_last_samples += total;
+    if (total == 0) return 0;
+    k_mc_set_offsets<<<lsb_blocks(npair, 256), 256, 0, st>>>(w.pairs, w.offs, npair);
+    LSB_LAUNCH_CHECK("k_mc_set_offsets");
+    k_mc_sampler<<<lsb_blocks(npair, 64), 64, 0, st>>>(p, w.pairs, w.samples, w.offs32, rng);
+    LSB_LAUNCH_CHECK("k_mc_sampler");
+    if (f64) return mc_launch_accumulate<double>(p, w, (const double*)response, signals, st);
+    return mc_launch_accumulate<float>(p, w, (const float*)response, signals, st);
+}
+
+LSB_EXPORT int64_t lsb_tracks_current_mc_last_samples(void) { return g_mc_last_samples; }
+
+static inline int require_current_fields(const lsb_track_layout* L, bool mc) {
+    static const int need[] = {LSB_F_X_START, LSB_F_Y_START, LSB_F_Z_START, LSB_F_X_END, LSB_F_Y_END, LSB_F_Z_END,
+                               LSB_F_T_START, LSB_F_T0_START, LSB_F_TRAN_DIFF, LSB_F_LONG_DIFF, LSB_F_N_ELECTRONS,
+                               LSB_F_PIXEL_PLANE};
+    for (int f : need) if (!layout_has(L, f)) return lsb_fail_arg("tracks lacks a field required by tracks_current");
+    (void)mc;
+    return 0;
+}
+
+LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
+                                     const int32_t* pixels, int32_t P, float* signals, int32_t T, const void* response,
+                                     int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64, uint64_t* rng_states,
+                                     int64_t n_rng, int64_t rng_stride, int32_t rng_mode, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+    LSB_REQUIRE(c && L, "tracks_current_mc: null consts/layout");
+    if (S == 0 || P == 0 || T == 0) return 0;
+    LSB_REQUIRE(tracks && pixels && signals && response && rng_states && workspace, "tracks_current_mc: null pointer");
+    LSB_REQUIRE(Rx > 0 && Ry > 0 && Rt > 0 && (long long)Rx * Ry * Rt < 2147483647LL, "tracks_current_mc: bad response shape");
+    LSB_REQUIRE(rng_mode == 0 || rng_mode == 1, "tracks_current_mc: rng_mode must be 0 (cloud) or 1 (replay)");
+    if (rng_stride <= 0) rng_stride = S;
+    LSB_REQUIRE(n_rng >= (S - 1) + rng_stride * (long long)(P - 1) + 1, "tracks_current_mc: rng_states too short");
+    if (require_current_fields(L, true)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = lsb_upload_consts(c, st); if (rc) return rc;
+    McParams p;
+    p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
+    double ratio = c->time_sampling / c->response_sampling;
+    p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
+    g_mc_last_samples = 0;
+    return mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states,
+                        rng_mode, p, workspace, workspace_bytes, st, 0);
+}
+
+// =======================================================================================
+// tracks_current (detsim.py:351-453): deterministic Gaussian-smeared line charge on a
+// SAMPLED_POINTS^2 x z_steps grid.  CTA per (segment,pixel); the charge grid of one z slab is
+// evaluated once per CTA (rho: detsim.py:120-159) and shared by all ticks through shared memory;
+// accumulation order (iz, ix, iy) and FP64 accumulation follow the reference.
+// =======================================================================================
+#define TC_TPB 256
+#define TC_RMAX 8
+#define TC_MAXNP 64
+
+struct TcPair {
+    double start[3], seg[3], dir[3], sig[3];
+    double x_p, y_p, q, z_anode, t_start;
+    double x_start, y_start, x_step, y_step, z_start_int, z_step;
+    long long z_steps;
+    int valid, c32, s32;
+};
+
+__device__ double rho_dev(const double* pt, const TcPair& g) {
+    const bool c32 = g.c32, s32 = g.s32;
+    const double* seg = g.seg; const double* sig = g.sig; const double* start = g.start;
+    double Dr = seg_length(seg, c32);
+    double ux = R32(seg[0] / Dr, c32), uy = R32(seg[1] / Dr, c32), uz = R32(seg[2] / Dr, c32);
+    double a = R32(ux * ux, c32) / (2 * sig[0] * sig[0]) + R32(uy * uy, c32) / (2 * sig[1] * sig[1]) +
+               R32(uz * uz, c32) / (2 * sig[2] * sig[2]);
+    double sprod = R32(R32(sig[0] * sig[1], s32) * sig[2], s32);
+    double factor = g.q / Dr / (sprod * sqrt(8 * M_PI * M_PI * M_PI));
+    double sqrt_a_2 = 2 * sqrt(a);
+    double x = pt[0], y = pt[1], z = pt[2];
+    double b = -((x - start[0]) / R32(sig[0] * sig[0], s32) * ux + (y - start[1]) / R32(sig[1] * sig[1], s32) * uy +
+                 (z - start[2]) / R32(sig[2] * sig[2], s32) * uz);
+    double delta = (x - start[0]) * (x - start[0]) / (2 * sig[0] * sig[0]) + (y - start[1]) * (y - start[1]) / (2 * sig[1] * sig[1]) +
+                   (z - start[2]) * (z - start[2]) / (2 * sig[2] * sig[2]);
+    double integral = sqrt(M_PI) * (-erf(b / sqrt_a_2) + erf((b + 2 * a * Dr) / sqrt_a_2)) / sqrt_a_2;
+    double expo = 0;
+    if (factor != 0 && integral != 0) expo = exp(b * b / (4 * a) - delta + log(factor) + log(integral));
+    return expo;
+}
+
+// z_interval (detsim.py:42-112)
+__device__ void z_interval_dev(const double* sp, const double* ep, double x_p, double y_p, double tol, bool c32,
+                               double& z_poca, double& z_lo, double& z_hi) {
+    z_poca = z_lo = z_hi = 0;
+    const double *start, *end;
+    if (sp[0] > ep[0]) { start = ep; end = sp; } else if (sp[0] < ep[0]) { start = sp; end = ep; } else return;
+    double xs = start[0], ys = start[1], xe = end[0], ye = end[1];
+    double dxe = R32(xe - xs, c32);
+    double m = R32(R32(ye - ys, c32) / dxe, c32);
+    double q = R32(R32(R32(xe * ys, c32) - R32(xs * ye, c32), c32) / dxe, c32);
+    double a = m, b = -1, cc = q;
+    double x_poca = (b * (b * x_p - a * y_p) - R32(a * cc, c32)) / (R32(a * a, c32) + b * b);
+    double d[3] = {R32(end[0] - start[0], c32), R32(end[1] - start[1], c32), R32(end[2] - start[2], c32)};
+    double length = seg_length(d, c32);
+    double dir3[3] = {R32(d[0] / length, c32), R32(d[1] / length, c32), R32(d[2] / length, c32)};
+    double doca;
+    if (x_poca < start[0]) {
+        doca = sqrt((x_p - start[0]) * (x_p - start[0]) + (y_p - start[1]) * (y_p - start[1]));
+        x_poca = start[0];
+    } else if (x_poca > end[0]) {
+        doca = sqrt((x_p - end[0]) * (x_p - end[0]) + (y_p - end[1]) * (y_p - end[1]));
+        x_poca = end[0];
+    } else {
+        doca = fabs(a * x_p + b * y_p + cc) / sqrt(R32(a * a, c32) + b * b);
+    }
+    double zp = start[2] + (x_poca - start[0]) / dir3[0] * dir3[2];
+    if (tol > doca) {
+        double dx2 = R32(xe - xs, c32), dy2 = R32(ye - ys, c32);
+        double length2D = R32(sqrt(R32(R32(dx2 * dx2, c32) + R32(dy2 * dy2, c32), c32)), c32);
+        double dir2D0 = R32(d[0] / length2D, c32);
+        double deltaL2D = sqrt(tol * tol - doca * doca);
+        double x_plus = x_poca + deltaL2D * dir2D0, x_minus = x_poca - deltaL2D * dir2D0;
+        double plusL = (x_plus - start[0]) / dir3[0], minusL = (x_minus - start[0]) / dir3[0];
+        double plusZ = start[2] + dir3[2] * plusL, minusZ = start[2] + dir3[2] * minusL;
+        z_poca = zp; z_lo = fmin(minusZ, plusZ); z_hi = fmax(minusZ, plusZ);
+    }
+}
+
+template <typename TL>
+__global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char* __restrict__ tracks,
+                                                           const int32_t* __restrict__ pixels, long long S, int P, int T,
+                                                           const TL* __restrict__ lut, int Rx, int Ry, int Rt,
+                                                           float* __restrict__ signals) {
+    __shared__ TcPair g;
+    __shared__ double s_charge[TC_MAXNP * TC_MAXNP];
+    __shared__ int s_i[TC_MAXNP], s_j[TC_MAXNP];
+    __shared__ int s_xok[TC_MAXNP], s_yok[TC_MAXNP];
+    __shared__ int s_anyx;
+    const long long pr = blockIdx.x;
+    const long long itrk = pr / P;
+    const int ipix = (int)(pr % P);
+    const int tid = threadIdx.x;
+    const int NP = d_c.sampled_points;
+    if (tid == 0) {
+        g.valid = 0;
+        const char* t = tracks + itrk * L.itemsize;
+        int pID = pixels[itrk * P + ipix];
+        bool c32;
+        do {
+            if (!pixel_center(pID, g.x_p, g.y_p)) break;
+            double end[3];
+            load_endpoints(L, t, g.start, end, c32);
+            g.c32 = c32;
+            g.s32 = fld_f32(L, LSB_F_TRAN_DIFF) && fld_f32(L, LSB_F_LONG_DIFF);
+            for (int k = 0; k < 3; k++) g.seg[k] = R32(end[k] - g.start[k], c32);
+            double length = seg_length(g.seg, c32);
+            for (int k = 0; k < 3; k++) g.dir[k] = R32(g.seg[k] / length, c32);
+            g.sig[0] = g.sig[1] = fld_get(L, t, LSB_F_TRAN_DIFF);
+            g.sig[2] = fld_get(L, t, LSB_F_LONG_DIFF);
+            double s5x = 5 * g.sig[0], s5y = 5 * g.sig[1];
+            double imp1 = sqrt(s5x * s5x + s5y * s5y);
+            double imp2 = sqrt(d_c.pixel_pitch * d_c.pixel_pitch + d_c.pixel_pitch * d_c.pixel_pitch) / 2;
+            double impact = fmax(imp1, imp2) * 2;
+            double z_poca, z_start, z_end;
+            z_interval_dev(g.start, end, g.x_p, g.y_p, impact, c32, z_poca, z_start, z_end);
+            if (z_poca == 0) break;
+            g.z_start_int = z_start - 4 * g.sig[2];
+            double z_end_int = z_end + 4 * g.sig[2];
+            double l0 = (z_start - g.start[2]) / g.dir[2], l1 = (z_end - g.start[2]) / g.dir[2];
+            g.x_start = g.start[0] + l0 * g.dir[0]; g.y_start = g.start[1] + l0 * g.dir[1];
+            double x_end = g.start[0] + l1 * g.dir[0], y_end = g.start[1] + l1 * g.dir[1];
+            g.y_step = (fabs(y_end - g.y_start) + 8 * g.sig[1]) / (NP - 1);
+            g.x_step = (fabs(x_end - g.x_start) + 8 * g.sig[0]) / (NP - 1);
+            double z_sampling = d_c.time_sampling / 2.;
+            long long zc = (long long)ceil(fabs(z_end_int - g.z_start_int) / z_sampling);
+            g.z_steps = zc > NP ? zc : NP;
+            g.z_step = (z_end_int - g.z_start_int) / (double)(g.z_steps - 1);
+            g.t_start = (double)__double2ll_rn((fld_get(L, t, LSB_F_T_START) - fld_get(L, t, LSB_F_T0_START) - d_c.time_padding) /
+                                               d_c.time_sampling) * d_c.time_sampling;
+            g.q = fld_get(L, t, LSB_F_N_ELECTRONS);
+            long long plane = (long long)fld_get(L, t, LSB_F_PIXEL_PLANE);
+            if (plane < 0 || plane >= d_c.n_tpc) break;
+            g.z_anode = d_c.tpc_borders[plane][2][0];
+            g.valid = 1;
+        } while (0);
+        s_anyx = 0;
+    }
+    __syncthreads();
+    if (!g.valid) return;
+    const double sgx = g.dir[0] >= 0 ? 1.0 : -1.0, sgy = g.dir[1] >= 0 ? 1.0 : -1.0;
+    if (tid < NP) {
+        double x = g.x_start + sgx * (tid * g.x_step - 4 * g.sig[0]);
+        double x_dist = fabs(g.x_p - x);
+        int ok = !(x_dist > d_c.response_bin_size * Rx);
+        long long i = __double2ll_rn(x_dist / d_c.response_bin_size - 0.5);
+        s_xok[tid] = ok; s_i[tid] = (ok && 0 <= i && i < Rx) ? (int)i : -1;
+        if (ok) s_anyx = 1;
+        double y = g.y_start + sgy * (tid * g.y_step - 4 * g.sig[1]);
+        double y_dist = fabs(g.y_p - y);
+        int oky = !(y_dist > d_c.response_bin_size * Ry);
+        long long j = __double2ll_rn(y_dist / d_c.response_bin_size - 0.5);
+        s_yok[tid] = oky; s_j[tid] = (oky && 0 <= j && j < Ry) ? (int)j : -1;
+    }
+    __syncthreads();
+    const int anyx = s_anyx;
+    float* out = signals + (itrk * P + ipix) * (long long)T;
+    const double vol = fabs(g.x_step) * fabs(g.y_step) * fabs(g.z_step);
+    for (int base = 0; base < T; base += TC_TPB * TC_RMAX) {
+        double total[TC_RMAX];
+        bool written[TC_RMAX];
+#pragma unroll
+        for (int r = 0; r < TC_RMAX; r++) { total[r] = 0; written[r] = false; }
+        for (long long iz = 0; iz < g.z_steps; iz++) {
+            double z = g.z_start_int + (double)iz * g.z_step;
+            double t0 = fabs(z - g.z_anode) / d_c.v_drift - d_c.time_window;
+            __syncthreads();
+            for (int c = tid; c < NP * NP; c += TC_TPB) {
+                int ix = c / NP, iy = c % NP;
+                double ch = 0;
+                if (s_xok[ix] && s_yok[iy]) {
+                    double pt[3] = {g.x_start + sgx * (ix * g.x_step - 4 * g.sig[0]),
+                                    g.y_start + sgy * (iy * g.y_step - 4 * g.sig[1]), z};
+                    ch = rho_dev(pt, g) * fabs(g.x_step) * fabs(g.y_step) * fabs(g.z_step);
+                }
+                s_charge[c] = ch;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < TC_RMAX; r++) {
+                int it = base + tid + r * TC_TPB;
+                if (it >= T) continue;
+                double tick = g.t_start + (double)it * d_c.time_sampling;
+                if (tick < 0.) continue;
+                if (!(t0 < tick && tick < t0 + d_c.time_window)) continue;
+                if (anyx) written[r] = true;
+                long long k = __double2ll_rn((tick - t0) / d_c.response_sampling);
+                bool kok = 0 <= k && k < Rt;
+                double tot = total[r];
+                for (int ix = 0; ix < NP; ix++) {
+                    if (!s_xok[ix]) continue;
+                    int i = s_i[ix];
+                    for (int iy = 0; iy < NP; iy++) {
+                        if (!s_yok[iy]) continue;
+                        int j = s_j[iy];
+                        double w = 0;
+                        if (kok && i >= 0 && j >= 0) w = (double)lut[((long long)i * Ry + j) * Rt + k];
+                        tot += w * s_charge[ix * NP + iy];
+                    }
+                }
+                total[r] = tot;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TC_RMAX; r++) {
+            int it = base + tid + r * TC_TPB;
+            if (it < T && written[r]) out[it] = __double2float_rn(total[r]);
+        }
+    }
+    (void)vol;
+}
+
+LSB_EXPORT int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
+                                  const int32_t* pixels, int32_t P, float* signals, int32_t T, const void* response,
+                                  int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64, void* stream) {
+    LSB_REQUIRE(c && L, "tracks_current: null consts/layout");
+    if (S == 0 || P == 0 || T == 0) return 0;
+    LSB_REQUIRE(tracks && pixels && signals && response, "tracks_current: null pointer");
+    LSB_REQUIRE(c->sampled_points >= 2 && c->sampled_points <= TC_MAXNP, "tracks_current: SAMPLED_POINTS must be in [2,64]");
+    if (require_current_fields(L, false)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = lsb_upload_consts(c, st); if (rc) return rc;
+    unsigned grid = (unsigned)(S * P);
+    if (response_f64) k_tracks_current<double><<<grid, TC_TPB, 0, st>>>(make_layout(L), (const char*)tracks, pixels, S, P, T,
+                                                                         (const double*)response, Rx, Ry, Rt, signals);
+    else k_tracks_current<float><<<grid, TC_TPB, 0, st>>>(make_layout(L), (const char*)tracks, pixels, S, P, T,
+                                                          (const float*)response, Rx, Ry, Rt, signals);
+    LSB_LAUNCH_CHECK("k_tracks_current");
+    return 0;
+}

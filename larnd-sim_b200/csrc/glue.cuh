@@ -1,0 +1,248 @@
+// glue.cuh -- device replacements for the CuPy glue of cli/simulate_pixels.py:
+//   unique_pix = cp.unique(neighboring_pixels) minus -1   (:953-956)
+//   pixel_index_map (S sequential broadcast compares)     (:1021-1025)
+//   fee.digitize                                          (fee.py:499-515)
+// plus a generic exclusive scan used by several stages.
+//
+// Pixel ids are bounded (id < Nx*Ny*nTPC <= 14.3M for ND-LAr), so the sorted unique list is a
+// bitmap + popcount prefix scan: integer/HBM-bound, deterministic, no sort.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// exclusive scan  (uint32 in -> int64 out), 3 phases, any n
+// ---------------------------------------------------------------------------------------
+#define SCAN_TPB 256
+#define SCAN_IPT 8
+#define SCAN_TILE (SCAN_TPB * SCAN_IPT)
+
+__device__ __forceinline__ long long block_exclusive_scan_ll(long long v, long long* total) {
+    // 256 threads; returns exclusive prefix of v across the block
+    __shared__ long long warp_sums[SCAN_TPB / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = lane < SCAN_TPB / 32 ? warp_sums[lane] : 0;
+        long long winc = w;
+        for (int o = 1; o < SCAN_TPB / 32; o <<= 1) {
+            long long y = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += y;
+        }
+        if (lane < SCAN_TPB / 32) warp_sums[lane] = winc - w;   // exclusive warp offsets
+        if (lane == SCAN_TPB / 32 - 1 && total) *total = winc;
+    }
+    __syncthreads();
+    long long r = warp_sums[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+template <typename TIn>
+__global__ void k_scan_reduce(const TIn* __restrict__ in, long long n, long long* __restrict__ block_sums) {
+    long long base = (long long)blockIdx.x * SCAN_TILE;
+    long long s = 0;
+    for (int k = 0; k < SCAN_IPT; k++) {
+        long long i = base + k * SCAN_TPB + threadIdx.x;
+        if (i < n) s += (long long)in[i];
+    }
+    __shared__ long long tot;
+    block_exclusive_scan_ll(s, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void k_scan_blocksums(long long* __restrict__ block_sums, long long nb, long long* __restrict__ total_out) {
+    // single block, loops over nb in chunks of SCAN_TPB
+    __shared__ long long carry_s, tot;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < nb; base += SCAN_TPB) {
+        long long i = base + threadIdx.x;
+        long long v = i < nb ? block_sums[i] : 0;
+        long long ex = block_exclusive_scan_ll(v, &tot);
+        long long carry = carry_s;
+        if (i < nb) block_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+template <typename TIn, typename TOut>
+__global__ void k_scan_apply(const TIn* __restrict__ in, long long n, const long long* __restrict__ block_sums,
+                             TOut* __restrict__ out) {
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_IPT;
+    long long v[SCAN_IPT];
+    long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        long long i = base + k;
+        v[k] = i < n ? (long long)in[i] : 0;
+        s += v[k];
+    }
+    long long ex = block_exclusive_scan_ll(s, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        long long i = base + k;
+        if (i < n) out[i] = (TOut)ex;
+        ex += v[k];
+    }
+}
+static inline long long scan_num_blocks(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+// out[i] = sum_{j<i} in[j]; total -> *total_out (device).  block_sums: scratch of scan_num_blocks(n) int64.
+template <typename TIn, typename TOut>
+static int exclusive_scan(const TIn* in, long long n, TOut* out, long long* block_sums, long long* total_out, cudaStream_t st) {
+    if (n <= 0) {
+        if (total_out) LSB_CUDA(cudaMemsetAsync(total_out, 0, sizeof(long long), st));
+        return 0;
+    }
+    long long nb = scan_num_blocks(n);
+    k_scan_reduce<TIn><<<(unsigned)nb, SCAN_TPB, 0, st>>>(in, n, block_sums);
+    LSB_LAUNCH_CHECK("k_scan_reduce");
+    k_scan_blocksums<<<1, SCAN_TPB, 0, st>>>(block_sums, nb, total_out);
+    LSB_LAUNCH_CHECK("k_scan_blocksums");
+    k_scan_apply<TIn, TOut><<<(unsigned)nb, SCAN_TPB, 0, st>>>(in, n, block_sums, out);
+    LSB_LAUNCH_CHECK("k_scan_apply");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// unique pixels
+// workspace: [flags u32 nW][popc u32 nW][prefix i64 nW][block_sums i64 nb]
+// ---------------------------------------------------------------------------------------
+struct UniqueWs {
+    uint32_t* flags; uint32_t* popc; long long* prefix; long long* block_sums; long long nW;
+};
+static inline long long unique_nwords(long long max_id) { return (max_id + 32) / 32; }
+static inline UniqueWs unique_ws(void* ws, long long max_id) {
+    UniqueWs w;
+    w.nW = unique_nwords(max_id);
+    char* p = (char*)ws;
+    w.flags = (uint32_t*)p; p += ((w.nW * 4 + 15) / 16) * 16;
+    w.popc = (uint32_t*)p; p += ((w.nW * 4 + 15) / 16) * 16;
+    w.prefix = (long long*)p; p += w.nW * 8;
+    w.block_sums = (long long*)p;
+    return w;
+}
+LSB_EXPORT int64_t lsb_unique_pixels_workspace_bytes(int64_t max_pixel_id) {
+    long long nW = unique_nwords(max_pixel_id);
+    return 2 * (((nW * 4 + 15) / 16) * 16) + nW * 8 + (scan_num_blocks(nW) + 1) * 8;
+}
+
+__global__ void k_mark_pixels(const int32_t* __restrict__ pixels, long long n, long long max_id, uint32_t* __restrict__ flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t p = pixels[i];
+    if (p < 0 || p > max_id) return;                 // -1 padding is dropped (:956)
+    uint32_t bit = 1u << (p & 31);
+    uint32_t* w = flags + (p >> 5);
+    if (!(*w & bit)) atomicOr(w, bit);
+}
+__global__ void k_popc(const uint32_t* __restrict__ flags, long long nW, uint32_t* __restrict__ popc) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < nW) popc[i] = __popc(flags[i]);
+}
+__global__ void k_emit_unique(const uint32_t* __restrict__ flags, const long long* __restrict__ prefix, long long nW,
+                              int32_t* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nW) return;
+    uint32_t f = flags[i];
+    long long o = prefix[i];
+    while (f) {
+        int b = __ffs(f) - 1;
+        out[o++] = (int32_t)(i * 32 + b);
+        f &= f - 1;
+    }
+}
+__global__ void k_pixel_index_map(const int32_t* __restrict__ pixels, long long n, long long max_id,
+                                  const uint32_t* __restrict__ flags, const long long* __restrict__ prefix,
+                                  long long* __restrict__ map) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t p = pixels[i];
+    long long r = -1;
+    if (p >= 0 && p <= max_id) {
+        uint32_t f = flags[p >> 5];
+        uint32_t bit = 1u << (p & 31);
+        if (f & bit) r = prefix[p >> 5] + __popc(f & (bit - 1));
+    }
+    map[i] = r;
+}
+__global__ void k_pixel_index_map_search(const int32_t* __restrict__ pixels, long long n, const int32_t* __restrict__ uniq,
+                                         long long U, long long* __restrict__ map) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t p = pixels[i];
+    long long lo = 0, hi = U;
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if (uniq[mid] < p) lo = mid + 1; else hi = mid; }
+    map[i] = (lo < U && uniq[lo] == p) ? lo : -1;
+}
+
+LSB_EXPORT int lsb_unique_pixels(const int32_t* pixels, int64_t n_entries, int64_t max_pixel_id, int32_t* unique_out,
+                                 int64_t* n_unique, void* workspace, int64_t workspace_bytes, void* stream) {
+    LSB_REQUIRE(n_unique && workspace && (n_entries == 0 || (pixels && unique_out)), "unique_pixels: null pointer");
+    LSB_REQUIRE(max_pixel_id >= 0, "unique_pixels: max_pixel_id < 0");
+    LSB_REQUIRE(workspace_bytes >= lsb_unique_pixels_workspace_bytes(max_pixel_id), "unique_pixels: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    UniqueWs w = unique_ws(workspace, max_pixel_id);
+    LSB_CUDA(cudaMemsetAsync(w.flags, 0, w.nW * 4, st));
+    if (n_entries > 0) {
+        k_mark_pixels<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pixels, n_entries, max_pixel_id, w.flags);
+        LSB_LAUNCH_CHECK("k_mark_pixels");
+    }
+    k_popc<<<lsb_blocks(w.nW, 256), 256, 0, st>>>(w.flags, w.nW, w.popc);
+    LSB_LAUNCH_CHECK("k_popc");
+    int rc = exclusive_scan<uint32_t, long long>(w.popc, w.nW, w.prefix, w.block_sums, (long long*)n_unique, st);
+    if (rc) return rc;
+    if (n_entries > 0) {
+        k_emit_unique<<<lsb_blocks(w.nW, 256), 256, 0, st>>>(w.flags, w.prefix, w.nW, unique_out);
+        LSB_LAUNCH_CHECK("k_emit_unique");
+    }
+    return 0;
+}
+
+LSB_EXPORT int lsb_pixel_index_map(const int32_t* pixels, int64_t n_entries, int64_t max_pixel_id, const void* workspace,
+                                   int64_t* pixel_index_map, void* stream) {
+    LSB_REQUIRE(workspace && (n_entries == 0 || (pixels && pixel_index_map)), "pixel_index_map: null pointer");
+    if (n_entries == 0) return 0;
+    UniqueWs w = unique_ws((void*)workspace, max_pixel_id);
+    k_pixel_index_map<<<lsb_blocks(n_entries, 256), 256, 0, (cudaStream_t)stream>>>(pixels, n_entries, max_pixel_id, w.flags,
+                                                                                   w.prefix, (long long*)pixel_index_map);
+    LSB_LAUNCH_CHECK("k_pixel_index_map");
+    return 0;
+}
+
+LSB_EXPORT int lsb_pixel_index_map_search(const int32_t* pixels, int64_t n_entries, const int32_t* unique_pix, int64_t n_unique,
+                                          int64_t* pixel_index_map, void* stream) {
+    LSB_REQUIRE(n_entries == 0 || (pixels && pixel_index_map && (unique_pix || n_unique == 0)), "pixel_index_map_search: null pointer");
+    if (n_entries == 0) return 0;
+    k_pixel_index_map_search<<<lsb_blocks(n_entries, 256), 256, 0, (cudaStream_t)stream>>>(pixels, n_entries, unique_pix, n_unique,
+                                                                                          (long long*)pixel_index_map);
+    LSB_LAUNCH_CHECK("k_pixel_index_map_search");
+    return 0;
+}
+
+// fee.py:499-515 digitize
+__global__ void k_digitize(const double* __restrict__ q, const double* __restrict__ gain_list, long long n, double* __restrict__ adcs) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double g = gain_list ? gain_list[i] : d_c.gain * d_c.unit_mV / d_c.unit_e;
+    double v = q[i] * g + d_c.v_pedestal * d_c.unit_mV - d_c.v_cm * d_c.unit_mV;
+    v = fmax(v, 0.0);
+    double a = rint(v * d_c.adc_counts / (d_c.v_ref * d_c.unit_mV - d_c.v_cm * d_c.unit_mV));   // np.around: half to even
+    adcs[i] = fmin(a, d_c.adc_counts - 1);
+}
+LSB_EXPORT int lsb_digitize(const lsb_consts* c, const double* integral_list, const double* gain_list, int64_t n, double* adcs,
+                            void* stream) {
+    LSB_REQUIRE(c && (n == 0 || (integral_list && adcs)), "digitize: null pointer");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = lsb_upload_consts(c, st); if (rc) return rc;
+    k_digitize<<<lsb_blocks(n, 256), 256, 0, st>>>(integral_list, gain_list, n, adcs);
+    LSB_LAUNCH_CHECK("k_digitize");
+    return 0;
+}
