@@ -169,9 +169,15 @@ int lsb_pixel_index_map_search(const int32_t* pixels, int64_t n_entries, const i
 int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
                           const int32_t* pixels, int32_t P, float* signals, int32_t T,
                           const void* response, int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64,
-                          uint64_t* rng_states, int64_t n_rng, int32_t rng_mode,
+                          uint64_t* rng_states, int64_t n_rng, int64_t rng_stride, int32_t rng_mode,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* rng_stride = ntrk of detsim.py:324 (grid size along the segment axis; <=0: S).
+ * workspace: >= lsb_tracks_current_mc_workspace_bytes(S, P, n) for n sample points; if the batch needs
+ * more the call splits it into segment ranges that fit (never fails for a workspace that holds the
+ * samples of one segment). */
 int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total);
+/* sample points drawn by the last lsb_tracks_current_mc call (roofline accounting) */
+int64_t lsb_tracks_current_mc_last_samples(void);
 /* larndsim/detsim.py:351-453  tracks_current(signals, pixels, tracks, response) */
 int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
                        const int32_t* pixels, int32_t P, float* signals, int32_t T,

@@ -167,6 +167,7 @@ def lib():
         _lib.lsb_launch_count.restype = C.c_int64
         _lib.lsb_unique_pixels_workspace_bytes.restype = C.c_int64
         _lib.lsb_tracks_current_mc_workspace_bytes.restype = C.c_int64
+        _lib.lsb_tracks_current_mc_last_samples.restype = C.c_int64
         _lib.lsb_chain_create.restype = C.c_void_p
         if _lib.lsb_abi_version() != 1:
             raise ExtensionMissing("ABI version mismatch in %s" % LIB_PATH)

@@ -1,0 +1,279 @@
+// chain.cuh -- device-resident driver for one batch of the charge readout chain,
+// quench -> drift -> get_pixels -> tracks_current_mc -> sum_pixel_signals -> get_adc_values -> digitize,
+// i.e. the sequence of cli/simulate_pixels.py:907-1117 with the CuPy glue (unique, index maps, fills,
+// linspace) done by the kernels of glue.cuh / pixelmap.cuh.  Everything stays in HBM; the host reads
+// back three scalars per batch (P, U, T) that size the buffers, exactly where the reference
+// synchronises (max_pixels[0], cp.unique, max_length).
+#pragma once
+#include "common.cuh"
+#include "segments.cuh"
+#include "glue.cuh"
+#include "current.cuh"
+#include "pixelmap.cuh"
+#include "fee.cuh"
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int need(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return lsb_fail_cuda(e, "cudaFree"); }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) { p = nullptr; return lsb_fail_cuda(e, "cudaMalloc (chain buffer)"); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { ST_QUENCH_DRIFT = 0, ST_GET_PIXELS, ST_UNIQUE, ST_TIME_INTERVALS, ST_TRACKS_CURRENT, ST_INDEX_MAPS, ST_SUM_PIXELS,
+       ST_GET_ADC, ST_DIGITIZE, ST_COUNT };
+
+struct lsb_chain {
+    lsb_consts c;
+    lsb_track_layout L;
+    const void* response; int Rx, Ry, Rt, f64, rng_mode, timing;
+    DevBuf tracks, scal, active, neigh, nrad, npl, uniq, uniq_ws, starts, signals, mc_ws, pim, tpm, psig, pts, oflow, tticks,
+           integral, adc_digit, adc_ticks, cf, thr, rng, nhits;
+    long long n_rng;
+    int tticks_n; long long tticks_events;
+    cudaEvent_t ev[ST_COUNT + 1];
+};
+
+struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int pad; long long n_hits; };
+
+__global__ void k_chain_max_tran(Layout L, const char* __restrict__ tracks, long long n, unsigned long long* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (i < n) { double t = fld_get(L, tracks + i * L.itemsize, LSB_F_TRAN_DIFF); if (t > v) v = t; }   // NaN/negatives ignored
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, b, o); b = w > b ? w : b; }
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
+}
+__global__ void k_fill_i32(int32_t* p, long long n, int32_t v) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void k_fill_i64(long long* p, long long n, long long v) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void k_fill_f64(double* p, long long n, double v) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void k_max_i32(const int32_t* __restrict__ p, long long n, int* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int v = i < n ? p[i] : -2147483647;
+    for (int o = 16; o > 0; o >>= 1) { int w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+}
+__global__ void k_count_hits(const double* __restrict__ adc_digit, long long n, double pedestal_adc, long long* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int h = (i < n && adc_digit[i] > pedestal_adc) ? 1 : 0;              // fee.py:141 `if adc > digitize(0)`
+    unsigned m = __ballot_sync(0xffffffffu, h);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long*)out, (unsigned long long)__popc(m));
+}
+
+LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layout* L, const void* response, int32_t Rx,
+                                       int32_t Ry, int32_t Rt, int32_t response_f64, int32_t rng_mode, int32_t enable_stage_timing) {
+    if (!c || !L || !response || Rx <= 0 || Ry <= 0 || Rt <= 0) { lsb_fail_arg("chain_create: bad arguments"); return nullptr; }
+    lsb_chain* h = new lsb_chain();
+    h->c = *c; h->L = *L; h->response = response; h->Rx = Rx; h->Ry = Ry; h->Rt = Rt; h->f64 = response_f64;
+    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    return h;
+}
+LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
+    if (!h) return;
+    DevBuf* all[] = {&h->tracks, &h->scal, &h->active, &h->neigh, &h->nrad, &h->npl, &h->uniq, &h->uniq_ws, &h->starts, &h->signals,
+                     &h->mc_ws, &h->pim, &h->tpm, &h->psig, &h->pts, &h->oflow, &h->tticks, &h->integral, &h->adc_digit,
+                     &h->adc_ticks, &h->cf, &h->thr, &h->rng, &h->nhits};
+    for (DevBuf* b : all) b->release();
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+int lsb_rng_create_states_host_impl(uint64_t* states, int64_t n, uint64_t seed, uint64_t subsequence_start);
+
+// cli/simulate_pixels.py:92-104 maybe_create_rng_states: keep evolved states, append fresh ones
+static int chain_grow_rng(lsb_chain* h, long long n, uint64_t seed, cudaStream_t st) {
+    if (n <= h->n_rng) return 0;
+    DevBuf nb;
+    if (nb.need((size_t)n * 16)) return -1;
+    if (h->n_rng) LSB_CUDA(cudaMemcpyAsync(nb.p, h->rng.p, (size_t)h->n_rng * 16, cudaMemcpyDeviceToDevice, st));
+    long long add = n - h->n_rng;
+    uint64_t* host = (uint64_t*)malloc((size_t)add * 16);
+    if (!host) return lsb_fail_arg("chain: out of host memory for rng states");
+    lsb_rng_create_states_host_impl(host, add, seed, 0);
+    cudaError_t e = cudaMemcpyAsync((char*)nb.p + (size_t)h->n_rng * 16, host, (size_t)add * 16, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    free(host);
+    if (e != cudaSuccess) return lsb_fail_cuda(e, "rng state upload");
+    h->rng.release();
+    h->rng = nb;
+    h->n_rng = n;
+    return 0;
+}
+
+#define CH_STAGE(i) do { if (h->timing) cudaEventRecord(h->ev[i], st); } while (0)
+
+LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                             int32_t n_events, lsb_chain_result* out, void* stream) {
+    LSB_REQUIRE(h && out && (tracks_dev || S == 0), "chain_run: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const lsb_consts* c = &h->c;
+    const lsb_track_layout* L = &h->L;
+    memset(out, 0, sizeof(*out));
+    out->n_segments = S;
+    if (S == 0) return 0;
+    const int K = c->max_tracks_per_pixel, A = c->max_adc_values, Tt = c->n_time_ticks;
+    int rc;
+    if ((rc = h->scal.need(sizeof(ChainScalars)))) return rc;
+    ChainScalars* d_s = (ChainScalars*)h->scal.p;
+    ChainScalars hs;
+    LSB_CUDA(cudaMemsetAsync(d_s, 0, sizeof(ChainScalars), st));
+    CH_STAGE(0);
+    // ---- quench, drift (simulate_pixels.py:732,742) -------------------------------------
+    if ((rc = lsb_quench(c, L, tracks_dev, S, quench_mode, st))) return rc;
+    if ((rc = lsb_drift(c, L, tracks_dev, S, st))) return rc;
+    CH_STAGE(1);
+    // ---- max_radius, max_pixels (:918-928) ----------------------------------------------
+    k_chain_max_tran<<<lsb_blocks(S, 256), 256, 0, st>>>(make_layout(L), (const char*)tracks_dev, S, &d_s->max_tran_bits);
+    LSB_LAUNCH_CHECK("k_chain_max_tran");
+    if ((rc = lsb_max_pixels(c, L, tracks_dev, S, (int64_t*)&d_s->max_pixels, st))) return rc;
+    LSB_CUDA(cudaMemcpyAsync(&hs, d_s, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
+    double max_tran; memcpy(&max_tran, &hs.max_tran_bits, 8);
+    const int radius = (int)ceil(max_tran * 5 / c->pixel_pitch);
+    const long long maxpix = hs.max_pixels;
+    const long long P = (2LL * radius + 1) * maxpix + (1 + 2LL * radius) * radius * 2;
+    out->max_active = maxpix; out->max_neighbors = P;
+    if (maxpix == 0 || P == 0) return 0;                                              // :935-941
+    LSB_REQUIRE(P < 100000, "chain_run: unreasonable neighbour row length");
+    // ---- get_pixels (:930-950) ----------------------------------------------------------
+    if ((rc = h->active.need((size_t)S * maxpix * 4)) || (rc = h->neigh.need((size_t)S * P * 4)) ||
+        (rc = h->nrad.need((size_t)S * P * 4)) || (rc = h->npl.need((size_t)S * 8))) return rc;
+    k_fill_i32<<<lsb_blocks(S * maxpix, 256), 256, 0, st>>>((int32_t*)h->active.p, S * maxpix, -1); LSB_LAUNCH_CHECK("k_fill_i32");
+    k_fill_i32<<<lsb_blocks(S * P, 256), 256, 0, st>>>((int32_t*)h->neigh.p, S * P, -1); LSB_LAUNCH_CHECK("k_fill_i32");
+    k_fill_i32<<<lsb_blocks(S * P, 256), 256, 0, st>>>((int32_t*)h->nrad.p, S * P, -1); LSB_LAUNCH_CHECK("k_fill_i32");
+    LSB_CUDA(cudaMemsetAsync(h->npl.p, 0, (size_t)S * 8, st));
+    if ((rc = lsb_get_pixels(c, L, tracks_dev, S, (int32_t*)h->active.p, (int32_t)maxpix, (int32_t*)h->neigh.p, (int32_t*)h->nrad.p,
+                             (int32_t)P, (double*)h->npl.p, radius, st))) return rc;
+    CH_STAGE(2);
+    // ---- unique pixels (:953-956), time_intervals (:1000-1002), max distance class (:1040) --
+    const long long max_id = (long long)c->n_pixels[0] * c->n_pixels[1] * c->n_tpc - 1;
+    const long long ws_bytes = lsb_unique_pixels_workspace_bytes(max_id);
+    long long ucap = S * P < max_id + 1 ? S * P : max_id + 1;
+    if ((rc = h->uniq_ws.need((size_t)ws_bytes)) || (rc = h->uniq.need((size_t)ucap * 4)) || (rc = h->starts.need((size_t)S * 8))) return rc;
+    if ((rc = lsb_unique_pixels((const int32_t*)h->neigh.p, S * P, max_id, (int32_t*)h->uniq.p, (int64_t*)&d_s->n_unique, h->uniq_ws.p,
+                                ws_bytes, st))) return rc;
+    CH_STAGE(3);
+    if ((rc = lsb_time_intervals(c, L, tracks_dev, S, (double*)h->starts.p, (int64_t*)&d_s->t_max, st))) return rc;
+    k_max_i32<<<lsb_blocks(S * P, 256), 256, 0, st>>>((const int32_t*)h->nrad.p, S * P, &d_s->max_dist); LSB_LAUNCH_CHECK("k_max_i32");
+    LSB_CUDA(cudaMemcpyAsync(&hs, d_s, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
+    const long long U = hs.n_unique, T = hs.t_max;
+    const int max_distance = hs.max_dist + 1;
+    out->n_unique_pixels = U; out->n_ticks = T;
+    if (U == 0 || T <= 0) return 0;
+    LSB_REQUIRE(T < 2147483647LL, "chain_run: tick count overflow");
+    CH_STAGE(4);
+    // ---- tracks_current_mc (:1007-1016) -------------------------------------------------
+    if ((rc = h->signals.need((size_t)S * P * T * 4))) return rc;
+    LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st));
+    long long need_rng = S * P;
+    long long need_rng2 = 128LL * ((U + 127) / 128);
+    if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
+    {
+        // sample workspace: MIN_STEP_SIZE bounds the samples of a (segment,pixel); start from a typical
+        // figure and let the kernel split the batch if it does not fit
+        long long guess = S * 4000LL;
+        long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, guess);
+        if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
+        if ((rc = lsb_tracks_current_mc(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
+                                        h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, h->n_rng, S, h->rng_mode,
+                                        h->mc_ws.p, (int64_t)h->mc_ws.cap, st))) return rc;
+        out->n_samples = lsb_tracks_current_mc_last_samples();
+    }
+    CH_STAGE(5);
+    // ---- pixel_index_map (:1021-1025), track_pixel_map (:1031-1042) ---------------------
+    if ((rc = h->pim.need((size_t)S * P * 8)) || (rc = h->tpm.need((size_t)U * K * 8))) return rc;
+    if ((rc = lsb_pixel_index_map((const int32_t*)h->neigh.p, S * P, max_id, h->uniq_ws.p, (int64_t*)h->pim.p, st))) return rc;
+    k_fill_i64<<<lsb_blocks(U * K, 256), 256, 0, st>>>((long long*)h->tpm.p, U * K, -1); LSB_LAUNCH_CHECK("k_fill_i64");
+    if ((rc = lsb_get_track_pixel_map2((int64_t*)h->tpm.p, K, (const int32_t*)h->uniq.p, U, (const int32_t*)h->neigh.p,
+                                       (const int32_t*)h->nrad.p, S, (int32_t)P, max_distance, st))) return rc;
+    CH_STAGE(6);
+    // ---- sum_pixel_signals (:1052-1063) -------------------------------------------------
+    if ((rc = h->psig.need((size_t)U * Tt * 8)) || (rc = h->pts.need((size_t)U * Tt * K * 8)) || (rc = h->oflow.need((size_t)U * 8))) return rc;
+    LSB_CUDA(cudaMemsetAsync(h->psig.p, 0, (size_t)U * Tt * 8, st));
+    LSB_CUDA(cudaMemsetAsync(h->pts.p, 0, (size_t)U * Tt * K * 8, st));
+    LSB_CUDA(cudaMemsetAsync(h->oflow.p, 0, (size_t)U * 8, st));
+    if ((rc = lsb_sum_pixel_signals(c, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, S, (int32_t)P, (int32_t)T,
+                                    (const double*)h->starts.p, (const int64_t*)h->pim.p, (const int64_t*)h->tpm.p, K,
+                                    (double*)h->pts.p, (double*)h->oflow.p, st))) return rc;
+    CH_STAGE(7);
+    // ---- get_adc_values (:1072-1095) ----------------------------------------------------
+    if (h->tticks_n != Tt + 1 || h->tticks_events != n_events) {
+        // numpy/cupy linspace(0, n_events*TIME_INTERVAL[1], Tt+1): i*step, last element = stop
+        if ((rc = h->tticks.need((size_t)(Tt + 1) * 8))) return rc;
+        double* tt = (double*)malloc(sizeof(double) * (size_t)(Tt + 1));
+        if (!tt) return lsb_fail_arg("chain: out of host memory");
+        double stop = (double)n_events * c->time_interval[1];
+        double step = stop / (double)Tt;
+        for (int i = 0; i <= Tt; i++) tt[i] = (double)i * step + 0.0;
+        tt[Tt] = stop;
+        cudaError_t e = cudaMemcpyAsync(h->tticks.p, tt, sizeof(double) * (size_t)(Tt + 1), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        free(tt);
+        if (e != cudaSuccess) return lsb_fail_cuda(e, "time_ticks upload");
+        h->tticks_n = Tt + 1; h->tticks_events = n_events;
+    }
+    if ((rc = h->integral.need((size_t)U * A * 8)) || (rc = h->adc_digit.need((size_t)U * A * 8)) ||
+        (rc = h->adc_ticks.need((size_t)U * A * 8)) || (rc = h->cf.need((size_t)U * A * K * 8)) || (rc = h->thr.need((size_t)U * 8))) return rc;
+    LSB_CUDA(cudaMemsetAsync(h->integral.p, 0, (size_t)U * A * 8, st));
+    LSB_CUDA(cudaMemsetAsync(h->adc_ticks.p, 0, (size_t)U * A * 8, st));
+    LSB_CUDA(cudaMemsetAsync(h->cf.p, 0, (size_t)U * A * K * 8, st));
+    k_fill_f64<<<lsb_blocks(U, 256), 256, 0, st>>>((double*)h->thr.p, U, c->discrimination_threshold * c->unit_e); LSB_LAUNCH_CHECK("k_fill_f64");
+    if ((rc = chain_grow_rng(h, need_rng2, rng_seed, st))) return rc;
+    if ((rc = lsb_get_adc_values(c, (const double*)h->psig.p, (const double*)h->pts.p, U, Tt, K, (const double*)h->tticks.p, Tt + 1,
+                                 (double*)h->integral.p, (double*)h->adc_ticks.p, A, 0.0, (uint64_t*)h->rng.p, h->n_rng,
+                                 (double*)h->cf.p, (const double*)h->thr.p, st))) return rc;
+    CH_STAGE(8);
+    // ---- digitize (:1102) ---------------------------------------------------------------
+    if ((rc = lsb_digitize(c, (const double*)h->integral.p, nullptr, U * A, (double*)h->adc_digit.p, st))) return rc;
+    {
+        double g = c->gain * c->unit_mV / c->unit_e;
+        double v = 0.0 * g + c->v_pedestal * c->unit_mV - c->v_cm * c->unit_mV; v = v > 0 ? v : 0;
+        double ped = nearbyint(v * c->adc_counts / (c->v_ref * c->unit_mV - c->v_cm * c->unit_mV));
+        ped = ped < c->adc_counts - 1 ? ped : c->adc_counts - 1;
+        k_count_hits<<<lsb_blocks(U * A, 256), 256, 0, st>>>((const double*)h->adc_digit.p, U * A, ped, &d_s->n_hits);
+        LSB_LAUNCH_CHECK("k_count_hits");
+    }
+    CH_STAGE(9);
+    LSB_CUDA(cudaMemcpyAsync(&hs, d_s, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
+    out->n_hits = hs.n_hits;
+    out->unique_pix = (const int32_t*)h->uniq.p; out->track_pixel_map = (const int64_t*)h->tpm.p;
+    out->adc_list = (const double*)h->integral.p; out->adc_digit = (const double*)h->adc_digit.p;
+    out->adc_ticks_list = (const double*)h->adc_ticks.p; out->current_fractions = (const double*)h->cf.p;
+    out->signals = (const float*)h->signals.p; out->pixels_signals = (const double*)h->psig.p;
+    if (h->timing)
+        for (int i = 0; i < ST_COUNT; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) out->stage_ms[i] = ms; }
+    return 0;
+}
+
+LSB_EXPORT int lsb_chain_run_host(lsb_chain* h, void* tracks_host, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                                  int32_t n_events, int32_t* unique_pix_host, double* adc_digit_host, double* adc_ticks_host,
+                                  int64_t U_cap, lsb_chain_result* out, void* stream) {
+    LSB_REQUIRE(h && out && (tracks_host || S == 0), "chain_run_host: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = (size_t)S * h->L.itemsize;
+    int rc;
+    if ((rc = h->tracks.need(bytes ? bytes : 1))) return rc;
+    if (S) LSB_CUDA(cudaMemcpyAsync(h->tracks.p, tracks_host, bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = lsb_chain_run(h, h->tracks.p, S, quench_mode, rng_seed, n_events, out, st))) return rc;
+    // Numba semantics: the record array is copied back after quench/drift modified it in place
+    if (S) LSB_CUDA(cudaMemcpyAsync(tracks_host, h->tracks.p, bytes, cudaMemcpyDeviceToHost, st));
+    const long long U = out->n_unique_pixels, A = h->c.max_adc_values;
+    if (U > 0 && out->unique_pix) {
+        LSB_REQUIRE(U <= U_cap, "chain_run_host: U_cap too small");
+        if (unique_pix_host) LSB_CUDA(cudaMemcpyAsync(unique_pix_host, out->unique_pix, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+        if (adc_digit_host) LSB_CUDA(cudaMemcpyAsync(adc_digit_host, out->adc_digit, (size_t)U * A * 8, cudaMemcpyDeviceToHost, st));
+        if (adc_ticks_host) LSB_CUDA(cudaMemcpyAsync(adc_ticks_host, out->adc_ticks_list, (size_t)U * A * 8, cudaMemcpyDeviceToHost, st));
+    }
+    LSB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -44,7 +44,7 @@ static inline unsigned int lsb_blocks(long long n, int tpb) { return (unsigned i
 // ---------------------------------------------------------------------------------------
 // constants: one POD snapshot in constant memory, refreshed when the host copy changes
 // ---------------------------------------------------------------------------------------
-extern __constant__ lsb_consts d_c;
+__constant__ lsb_consts d_c;   // single translation unit (lsb.cu)
 int lsb_upload_consts(const lsb_consts* c, cudaStream_t st);
 
 // record layout is passed by value to kernels
@@ -155,3 +155,25 @@ __device__ __forceinline__ float rng_normal_f32(Rng& r) {
     float b = cosf(__fmul_rn(6.283185307179586f, u2));
     return __fmul_rn(a, b);
 }
+
+// ---------------------------------------------------------------------------------------
+// stream-ordered temporaries (cudaMallocAsync from the default pool; the pool keeps freed blocks,
+// so steady-state calls do not reach the driver).  Freed when the guard leaves scope.
+// ---------------------------------------------------------------------------------------
+void lsb_pool_init_once();
+struct TmpPool {
+    cudaStream_t st;
+    void* ptrs[24];
+    int n;
+    explicit TmpPool(cudaStream_t s) : st(s), n(0) { lsb_pool_init_once(); }
+    template <typename T>
+    cudaError_t get(T** p, long long count) {
+        *p = nullptr;
+        if (n >= 24) return cudaErrorMemoryAllocation;
+        size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+        cudaError_t e = cudaMallocAsync((void**)p, bytes, st);
+        if (e == cudaSuccess) ptrs[n++] = (void*)*p;
+        return e;
+    }
+    ~TmpPool() { for (int i = n - 1; i >= 0; i--) cudaFreeAsync(ptrs[i], st); }
+};

@@ -1,0 +1,85 @@
+// lsb.cu -- the one translation unit of liblarndsim_b200.so (sm_100a only).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+//        (see __graft_entry__.build()).  The C ABI is declared in include/larndsim_b200.h.
+#include "common.cuh"
+
+char g_lsb_error[512] = "";
+long long g_lsb_launches = 0;
+
+static lsb_consts g_consts_host;
+static bool g_consts_valid = false;
+
+int lsb_upload_consts(const lsb_consts* c, cudaStream_t st) {
+    if (g_consts_valid && memcmp(&g_consts_host, c, sizeof(lsb_consts)) == 0) return 0;
+    if (c->n_tpc < 0 || c->n_tpc > LSB_MAX_TPC) return lsb_fail_arg("consts: n_tpc out of range");
+    // kernels of earlier calls (any stream) may still read the old snapshot
+    LSB_CUDA(cudaDeviceSynchronize());
+    memcpy(&g_consts_host, c, sizeof(lsb_consts));
+    g_consts_valid = false;
+    LSB_CUDA(cudaMemcpyToSymbolAsync(d_c, &g_consts_host, sizeof(lsb_consts), 0, cudaMemcpyHostToDevice, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
+    g_consts_valid = true;
+    return 0;
+}
+
+void lsb_pool_init_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+    unsigned long long thr = ~0ULL;     // keep freed blocks cached: steady-state calls never reach the driver
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+}
+
+#include "segments.cuh"
+#include "glue.cuh"
+#include "current.cuh"
+#include "pixelmap.cuh"
+#include "fee.cuh"
+#include "light.cuh"
+#include "chain.cuh"
+
+LSB_EXPORT int lsb_abi_version(void) { return LSB_ABI_VERSION; }
+LSB_EXPORT const char* lsb_last_error(void) { return g_lsb_error; }
+LSB_EXPORT int64_t lsb_launch_count(void) { return g_lsb_launches; }
+
+// numba/cuda/random.py: init_xoroshiro128p_states_cpu -- splitmix64(seed) -> s0 = s1, then one
+// 2^64 jump per subsequence.  Host side like the reference (create_xoroshiro128p_states runs on the CPU).
+static inline uint64_t h_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline void h_next(uint64_t* s) {
+    uint64_t s0 = s[0], s1 = s[1];
+    s1 ^= s0;
+    s[0] = h_rotl(s0, 55) ^ s1 ^ (s1 << 14);
+    s[1] = h_rotl(s1, 36);
+}
+static void h_jump(uint64_t* s) {
+    static const uint64_t J[2] = {0xbeac0467eba5facbULL, 0xd86b048b86aa9922ULL};
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < 2; i++)
+        for (int bit = 0; bit < 64; bit++) {
+            if (J[i] & (1ULL << bit)) { a ^= s[0]; b ^= s[1]; }
+            h_next(s);
+        }
+    s[0] = a; s[1] = b;
+}
+int lsb_rng_create_states_host_impl(uint64_t* states, int64_t n, uint64_t seed, uint64_t subsequence_start) {
+    if (n < 1) return 0;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    states[0] = z; states[1] = z;
+    for (uint64_t i = 0; i < subsequence_start; i++) h_jump(states);
+    for (int64_t i = 1; i < n; i++) {
+        states[2 * i] = states[2 * i - 2]; states[2 * i + 1] = states[2 * i - 1];
+        h_jump(states + 2 * i);
+    }
+    return 0;
+}
+LSB_EXPORT int lsb_rng_create_states_host(uint64_t* states_host, int64_t n, uint64_t seed, uint64_t subsequence_start) {
+    LSB_REQUIRE(states_host || n == 0, "rng_create_states_host: null pointer");
+    return lsb_rng_create_states_host_impl(states_host, n, seed, subsequence_start);
+}

@@ -1,0 +1,253 @@
+"""Test infrastructure: ctypes wrapper of the CPU oracle (oracle/liblarnd_oracle.so) and the
+comparison of the CUDA chain with it.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs import this; nothing here is on the product path."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from larndsim_b200 import _abi, consts as lconsts, synth  # noqa: E402
+
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liblarnd_oracle.so")
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        if not os.path.exists(ORACLE_LIB):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        _orc = C.CDLL(ORACLE_LIB)
+        _orc.orc_unique_pixels.restype = C.c_int64
+    return _orc
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def rng_states(n, seed, subsequence_start=0):
+    st = np.zeros((int(n), 2), dtype=np.uint64)
+    oracle_lib().orc_rng_create_states(P(st), C.c_int64(int(n)), C.c_uint64(int(seed)), C.c_uint64(int(subsequence_start)))
+    return st
+
+
+class Oracle:
+    """NumPy-in / NumPy-out calls of the C restatement; constants from an ``lsb_consts`` snapshot."""
+
+    def __init__(self, c=None):
+        self.c = c if c is not None else lconsts.snapshot()
+        self.lib = oracle_lib()
+
+    def _L(self, tracks):
+        return _abi.track_layout(tracks.dtype)
+
+    def quench(self, tracks, mode):
+        L = self._L(tracks)
+        return self.lib.orc_quench(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(len(tracks)), C.c_int32(int(mode)))
+
+    def drift(self, tracks):
+        L = self._L(tracks)
+        return self.lib.orc_drift(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(len(tracks)))
+
+    def max_pixels(self, tracks):
+        L = self._L(tracks)
+        out = np.zeros(1, dtype=np.int64)
+        self.lib.orc_max_pixels(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(len(tracks)), P(out))
+        return int(out[0])
+
+    def get_pixels(self, tracks, max_active, P_, radius):
+        L = self._L(tracks)
+        S = len(tracks)
+        act = np.full((S, max_active), -1, dtype=np.int32)
+        nb = np.full((S, P_), -1, dtype=np.int32)
+        nr = np.full((S, P_), -1, dtype=np.int32)
+        npl = np.zeros(S, dtype=np.float64)
+        self.lib.orc_get_pixels(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(S), P(act), C.c_int32(max_active), P(nb), P(nr),
+                                C.c_int32(P_), P(npl), C.c_int32(radius))
+        return act, nb, nr, npl
+
+    def time_intervals(self, tracks):
+        L = self._L(tracks)
+        ts = np.zeros(len(tracks), dtype=np.float64)
+        tm = np.zeros(1, dtype=np.int64)
+        self.lib.orc_time_intervals(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(len(tracks)), P(ts), P(tm))
+        return ts, int(tm[0])
+
+    def unique_pixels(self, pixels):
+        flat = np.ascontiguousarray(pixels.reshape(-1))
+        out = np.zeros(flat.size, dtype=np.int32)
+        n = self.lib.orc_unique_pixels(P(flat), C.c_int64(flat.size), P(out))
+        return out[:n].copy()
+
+    def pixel_index_map(self, pixels, uniq):
+        flat = np.ascontiguousarray(pixels.reshape(-1))
+        out = np.zeros(flat.size, dtype=np.int64)
+        self.lib.orc_pixel_index_map(P(flat), C.c_int64(flat.size), P(uniq), C.c_int64(uniq.size), P(out))
+        return out.reshape(pixels.shape)
+
+    def tracks_current_mc(self, tracks, pixels, T, response, states, mode):
+        L = self._L(tracks)
+        S, P_ = pixels.shape
+        sig = np.zeros((S, P_, T), dtype=np.float32)
+        r = np.ascontiguousarray(response)
+        self.lib.orc_tracks_current_mc(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(S), P(pixels), C.c_int32(P_), P(sig),
+                                       C.c_int32(T), P(r), C.c_int32(r.shape[0]), C.c_int32(r.shape[1]), C.c_int32(r.shape[2]),
+                                       C.c_int32(1 if r.dtype == np.float64 else 0), P(states), C.c_int32(mode))
+        return sig
+
+    def tracks_current(self, tracks, pixels, T, response):
+        L = self._L(tracks)
+        S, P_ = pixels.shape
+        sig = np.zeros((S, P_, T), dtype=np.float32)
+        r = np.ascontiguousarray(response)
+        self.lib.orc_tracks_current(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(S), P(pixels), C.c_int32(P_), P(sig),
+                                    C.c_int32(T), P(r), C.c_int32(r.shape[0]), C.c_int32(r.shape[1]), C.c_int32(r.shape[2]),
+                                    C.c_int32(1 if r.dtype == np.float64 else 0))
+        return sig
+
+    def track_pixel_map(self, uniq, pixels, K):
+        tpm = np.full((uniq.size, K), -1, dtype=np.int64)
+        self.lib.orc_get_track_pixel_map(P(tpm), C.c_int32(K), P(uniq), C.c_int64(uniq.size), P(pixels),
+                                         C.c_int64(pixels.shape[0]), C.c_int32(pixels.shape[1]))
+        return tpm
+
+    def track_pixel_map2(self, uniq, pixels, dist, max_distance, K):
+        tpm = np.full((uniq.size, K), -1, dtype=np.int64)
+        self.lib.orc_get_track_pixel_map2(P(tpm), C.c_int32(K), P(uniq), C.c_int64(uniq.size), P(pixels), P(dist),
+                                          C.c_int64(pixels.shape[0]), C.c_int32(pixels.shape[1]), C.c_int32(max_distance))
+        return tpm
+
+    def sum_pixel_signals(self, signals, track_starts, pim, tpm, Tt):
+        U, K = tpm.shape
+        S, P_, T = signals.shape
+        ps = np.zeros((U, Tt), dtype=np.float64)
+        pts = np.zeros((U, Tt, K), dtype=np.float64)
+        of = np.zeros(U, dtype=np.float64)
+        self.lib.orc_sum_pixel_signals(C.byref(self.c), P(ps), C.c_int64(U), C.c_int32(Tt), P(signals), C.c_int64(S), C.c_int32(P_),
+                                       C.c_int32(T), P(track_starts), P(pim), P(tpm), C.c_int32(K), P(pts), P(of))
+        return ps, pts, of
+
+    def get_adc_values(self, ps, pts, time_ticks, A, time_padding, states, thresholds):
+        U, Tt = ps.shape
+        K = pts.shape[2]
+        adc = np.zeros((U, A), dtype=np.float64)
+        ticks = np.zeros((U, A), dtype=np.float64)
+        cf = np.zeros((U, A, K), dtype=np.float64)
+        self.lib.orc_get_adc_values(C.byref(self.c), P(ps), P(pts), C.c_int64(U), C.c_int32(Tt), C.c_int32(K), P(time_ticks),
+                                    C.c_int32(time_ticks.size), P(adc), P(ticks), C.c_int32(A), C.c_double(time_padding),
+                                    P(states), P(cf), P(thresholds))
+        return adc, ticks, cf
+
+    def digitize(self, q, gain=None):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        out = np.zeros_like(q)
+        g = None if gain is None else np.ascontiguousarray(np.broadcast_to(gain, q.shape), dtype=np.float64)
+        self.lib.orc_digitize(C.byref(self.c), P(q), P(g), C.c_int64(q.size), P(out))
+        return out
+
+
+def production_tracks(n, config="module0", seed=12345, kind="cosmic", dtype=None):
+    mod = lconsts.load_snapshot(config)
+    dt = dtype if dtype is not None else synth.segment_dtype
+    if kind == "cosmic":
+        return synth.cosmic_segments(n, mod.detector, seed=seed, dtype=dt)
+    return synth.beam_spill_segments(n, mod.detector, seed=seed, dtype=dt)
+
+
+def oracle_front(tracks, orc, quench_mode=2):
+    """quench .. time_intervals on the CPU, mirroring cli/simulate_pixels.py:732-1002."""
+    c = orc.c
+    orc.quench(tracks, quench_mode)
+    orc.drift(tracks)
+    max_radius = int(np.ceil(max(tracks["tran_diff"]) * 5 / c.pixel_pitch))
+    maxpix = orc.max_pixels(tracks)
+    P_ = (2 * max_radius + 1) * maxpix + (1 + 2 * max_radius) * max_radius * 2
+    act, nb, nr, npl = orc.get_pixels(tracks, maxpix, P_, max_radius)
+    uniq = orc.unique_pixels(nb)
+    ts, T = orc.time_intervals(tracks)
+    return dict(radius=max_radius, maxpix=maxpix, P=P_, active=act, neigh=nb, nrad=nr, npl=npl, uniq=uniq, starts=ts, T=T)
+
+
+def oracle_back(orc, front, signals, states, n_events=1):
+    """pixel_index_map .. digitize on the CPU from given `signals` (cli/simulate_pixels.py:1021-1102)."""
+    c = orc.c
+    K, A, Tt = c.max_tracks_per_pixel, c.max_adc_values, c.n_time_ticks
+    pim = orc.pixel_index_map(front["neigh"], front["uniq"])
+    tpm = orc.track_pixel_map2(front["uniq"], front["neigh"], front["nrad"], int(front["nrad"].max()) + 1, K)
+    ps, pts, of = orc.sum_pixel_signals(signals, front["starts"], pim, tpm, Tt)
+    time_ticks = np.linspace(0, n_events * c.time_interval[1], Tt + 1)
+    thr = np.full(len(front["uniq"]), c.discrimination_threshold * c.unit_e)
+    adc, ticks, cf = orc.get_adc_values(ps, pts, time_ticks, A, 0.0, states, thr)
+    return dict(pim=pim, tpm=tpm, ps=ps, pts=pts, overflow=of, adc=adc, ticks=ticks, cf=cf, digit=orc.digitize(adc))
+
+
+def rel_err(a, b):
+    """max |a-b| / (|b| + 1e-2 * max|b| per waveform): elementwise relative error with a floor that keeps
+    zero crossings of bipolar waveforms from dominating."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    scale = np.abs(b).max(axis=-1, keepdims=True)
+    den = np.abs(b) + 1e-2 * scale
+    den[den == 0] = 1.0
+    return float((np.abs(a - b) / den).max())
+
+
+def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="cosmic", rng_seed=1, response=None):
+    """Run the fused CUDA chain on a synthetic batch and compare with the oracle stage by stage."""
+    import torch
+    from larndsim_b200 import chain as lchain, _launch as ll
+    mod = lconsts.load_snapshot(config)
+    if not noise:
+        mod.detector.RESET_NOISE_CHARGE = 0
+        mod.detector.UNCORRELATED_NOISE_CHARGE = 0
+        mod.detector.DISCRIMINATOR_NOISE = 0
+    tracks = production_tracks(n_segments, config, seed, kind)
+    if response is None:
+        response = synth.response_lut(mod.detector)
+    c = lconsts.snapshot()
+    launches0 = ll.lib().lsb_launch_count()
+    ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud")
+    dtr = ll.DeviceRecords(host=tracks)
+    res = ch.run(dtr, rng_seed=rng_seed, n_events=1)
+    torch.cuda.synchronize()
+    launches = ll.lib().lsb_launch_count() - launches0
+    g_tracks = dtr.copy_to_host()
+    # ---- oracle ----
+    orc = Oracle(c)
+    otr = tracks.copy()
+    front = oracle_front(otr, orc, quench_mode=c.mode_birks)
+    S, P_ = front["neigh"].shape
+    out = dict(S=S, U=len(front["uniq"]), T=front["T"], launches=int(launches), n_hits=res.n_hits)
+    out["tracks_equal"] = bool(g_tracks.tobytes() == otr.tobytes())
+    out["shape_equal"] = (res.max_neighbors == P_ and res.n_ticks == front["T"] and res.n_unique_pixels == len(front["uniq"]))
+    out["unique_equal"] = out["shape_equal"] and bool(np.array_equal(res.unique_pix.cpu().numpy(), front["uniq"]))
+    n_rng = max(S * P_, 128 * ((out["U"] + 127) // 128))
+    states = rng_states(S * P_, rng_seed)
+    if n_rng > S * P_:
+        states = np.concatenate([states, rng_states(n_rng - S * P_, rng_seed)])
+    o_sig = orc.tracks_current_mc(otr, front["neigh"], front["T"], response, states, 0)
+    g_sig = res.signals.cpu().numpy()
+    out["signals_relerr"] = rel_err(g_sig, o_sig)
+    out["signals_sum"] = (float(g_sig.astype(np.float64).sum()), float(o_sig.astype(np.float64).sum()))
+    back = oracle_back(orc, front, g_sig, states)
+    out["tpm_equal"] = bool(np.array_equal(res.track_pixel_map.cpu().numpy(), back["tpm"]))
+    out["pixels_signals_equal"] = bool(np.array_equal(res.pixels_signals.cpu().numpy(), back["ps"]))
+    g_digit = res.adc_digit.cpu().numpy()
+    out["adc_mismatch"] = int((g_digit != back["digit"]).sum())
+    out["adc_list_equal"] = bool(np.array_equal(res.adc_list.cpu().numpy(), back["adc"]))
+    out["ticks_equal"] = bool(np.array_equal(res.adc_ticks_list.cpu().numpy(), back["ticks"]))
+    g_cf = res.current_fractions.cpu().numpy()
+    out["cf_equal"] = bool(np.array_equal(g_cf, back["cf"]))
+    out["cf_maxdiff"] = float(np.abs(g_cf - back["cf"]).max()) if g_cf.size else 0.0
+    out["n_hits_oracle"] = int((back["digit"] > orc.digitize(np.zeros(1))[0]).sum())
+    ch.close()
+    return out

@@ -1,0 +1,280 @@
+"""Parity of every CUDA kernel with the CPU oracle, called through the drop-in modules (which go through
+the C ABI) with the argument kinds the reference CLI uses: host structured arrays and device arrays."""
+import numpy as np
+import pytest
+
+import helpers as h
+from larndsim_b200 import consts as lc, synth
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = ["module0", "2x2", "ndlar"]
+
+
+def _tracks(n, config, seed=3, kind="cosmic", dtype=None):
+    return h.production_tracks(n, config, seed, kind, dtype)
+
+
+def _f8_tracks(n, config, seed=5):
+    return h.production_tracks(n, config, seed, "cosmic", synth.test_dtype_f8)
+
+
+@pytest.mark.parametrize("config", CONFIGS)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_quench_drift_bitexact(cuda, config, mode):
+    from larndsim_b200 import quenching, drifting
+    for tr in (_tracks(3000, config), _f8_tracks(500, config), _tracks(2000, config, kind="beam")):
+        tr["dEdx"][:3] = [0.0, 1e10, 2.1]
+        ref = tr.copy()
+        orc = h.Oracle()
+        assert orc.quench(ref, mode) == 0
+        orc.drift(ref)
+        got = tr.copy()
+        quenching.quench[(len(got) + 255) // 256, 256](got, mode)
+        drifting.drift[(len(got) + 255) // 256, 256](got)
+        assert got.tobytes() == ref.tobytes()
+        assert (ref["pixel_plane"] != 0xBEEF).all() or config != "module0"
+
+
+def test_quench_invalid_mode_raises(cuda):
+    from larndsim_b200 import quenching
+    lc.load_snapshot("module0")
+    with pytest.raises(ValueError):
+        quenching.quench[1, 256](_tracks(10, "module0"), 7)
+
+
+def test_empty_inputs(cuda):
+    from larndsim_b200 import quenching, drifting, pixels_from_track
+    lc.load_snapshot("module0")
+    tr = _tracks(10, "module0")[:0]
+    quenching.quench[1, 256](tr, 2)
+    drifting.drift[1, 256](tr)
+    m = np.array([0])
+    pixels_from_track.max_pixels[1, 128](tr, m)
+    assert m[0] == 0
+
+
+@pytest.mark.parametrize("config", CONFIGS)
+@pytest.mark.parametrize("kind", ["cosmic", "beam"])
+def test_pixels_and_maps_bitexact(cuda, config, kind):
+    from larndsim_b200 import quenching, drifting, pixels_from_track, detsim
+    import torch
+    tr = _tracks(4000, config, kind=kind)
+    orc = h.Oracle()
+    front = h.oracle_front(tr.copy(), orc)
+    quenching.quench[16, 256](tr, 2)
+    drifting.drift[16, 256](tr)
+    m = np.array([0])
+    pixels_from_track.max_pixels[32, 128](tr, m)
+    assert m[0] == front["maxpix"]
+    S, P_ = front["neigh"].shape
+    act = torch.full((S, front["maxpix"]), -1, dtype=torch.int32, device="cuda")
+    nb = torch.full((S, P_), -1, dtype=torch.int32, device="cuda")
+    nr = torch.full((S, P_), -1, dtype=torch.int32, device="cuda")
+    npl = torch.zeros(S, dtype=torch.float64, device="cuda")
+    pixels_from_track.get_pixels[32, 128](tr, act, nb, nr, npl, front["radius"])
+    assert np.array_equal(act.cpu().numpy(), front["active"])
+    assert np.array_equal(nb.cpu().numpy(), front["neigh"])
+    assert np.array_equal(nr.cpu().numpy(), front["nrad"])
+    assert np.array_equal(npl.cpu().numpy(), front["npl"])
+    uniq, pim = detsim.unique_pixels(nb)
+    assert np.array_equal(uniq.cpu().numpy(), front["uniq"])
+    assert np.array_equal(pim.cpu().numpy(), orc.pixel_index_map(front["neigh"], front["uniq"]))
+    ts = torch.empty(S, dtype=torch.float64, device="cuda")
+    tm = torch.zeros(1, dtype=torch.int64, device="cuda")
+    detsim.time_intervals[32, 128](ts, tm, tr)
+    assert np.array_equal(ts.cpu().numpy(), front["starts"]) and int(tm.item()) == front["T"]
+    for K in (50, 3):
+        tpm = torch.full((len(uniq), K), -1, dtype=torch.int64, device="cuda")
+        detsim.get_track_pixel_map2[(len(uniq) + 31) // 32, 32](tpm, uniq, nb, nr, int(nr.max().item()) + 1)
+        assert np.array_equal(tpm.cpu().numpy(), orc.track_pixel_map2(front["uniq"], front["neigh"], front["nrad"],
+                                                                       int(front["nrad"].max()) + 1, K))
+        tpm1 = np.full((len(uniq), K), -1, dtype=np.int64)       # host array: copy-in / copy-out path
+        detsim.get_track_pixel_map[(len(uniq) + 31) // 32, 32](tpm1, front["uniq"], front["neigh"])
+        assert np.array_equal(tpm1, orc.track_pixel_map(front["uniq"], front["neigh"], K))
+
+
+def test_track_pixel_map_unsorted_unique_falls_back(cuda):
+    from larndsim_b200 import detsim
+    lc.load_snapshot("module0")
+    tr = _tracks(300, "module0")
+    orc = h.Oracle()
+    front = h.oracle_front(tr, orc)
+    uniq = front["uniq"][::-1].copy()
+    tpm = np.full((len(uniq), 50), -1, dtype=np.int64)
+    detsim.get_track_pixel_map2[1, 32](tpm, uniq, front["neigh"], front["nrad"], 3)
+    assert np.array_equal(tpm, orc.track_pixel_map2(uniq, front["neigh"], front["nrad"], 3, 50))
+
+
+def _mc_setup(n, config, seed=11, sigma0=False):
+    mod = lc.load_snapshot(config)
+    tr = _tracks(n, config, seed=seed)
+    orc = h.Oracle()
+    front = h.oracle_front(tr, orc)
+    if sigma0:
+        tr["tran_diff"] = 0
+        tr["long_diff"] = 0
+    resp = synth.response_lut(mod.detector)
+    return mod, tr, orc, front, resp
+
+
+@pytest.mark.parametrize("config", ["module0", "2x2"])
+@pytest.mark.parametrize("mode", ["cloud", "replay"])
+def test_tracks_current_mc_vs_oracle(cuda, config, mode):
+    """Same RNG states in, same stream discipline: waveforms agree to 1e-5 (float32 outputs; the oracle
+    accumulates in float64 like the reference, the kernel in float32 partial sums)."""
+    from larndsim_b200 import detsim, rng
+    import torch
+    n = 24 if mode == "cloud" else 3
+    mod, tr, orc, front, resp = _mc_setup(n, config)
+    S, P_ = front["neigh"].shape
+    T = front["T"] if mode == "cloud" else 96
+    if mode == "replay":
+        # keep the sequential oracle cheap: a short tick window around the arrival time
+        mod.detector.TIME_PADDING = 12.0
+        mod.detector.TIME_WINDOW = 11.0
+        resp = np.ascontiguousarray(resp[:, :, -140:])
+        orc = h.Oracle()
+    st0 = h.rng_states(S * P_, 1)
+    st_ref = st0.copy()
+    ref = orc.tracks_current_mc(tr, front["neigh"], T, resp, st_ref, 1 if mode == "replay" else 0)
+    detsim.MC_MODE = mode
+    try:
+        sig = torch.zeros((S, P_, T), dtype=torch.float32, device="cuda")
+        states = rng.create_xoroshiro128p_states(S * P_, 1)
+        assert np.array_equal(states.copy_to_host().view(np.uint64).reshape(-1, 2), st0)
+        detsim.tracks_current_mc[(S, P_, (T + 63) // 64), (1, 1, 64)](sig, front["neigh"], tr, resp, states)
+    finally:
+        detsim.MC_MODE = "cloud"
+    got = sig.cpu().numpy()
+    assert (ref != 0).sum() > 100
+    assert h.rel_err(got, ref) < 1e-5
+    assert np.array_equal((got != 0), (ref != 0))
+    assert np.array_equal(states.copy_to_host().view(np.uint64).reshape(-1, 2), st_ref)   # streams advanced identically
+
+
+def test_tracks_current_mc_sigma0_is_rng_independent(cuda):
+    """tran_diff = long_diff = 0: the normals are multiplied by 0, cloud and replay modes must agree."""
+    from larndsim_b200 import detsim, rng
+    import torch
+    mod, tr, orc, front, resp = _mc_setup(6, "module0", sigma0=True)
+    S, P_ = front["neigh"].shape
+    T = front["T"]
+    out = {}
+    for mode in ("cloud", "replay"):
+        detsim.MC_MODE = mode
+        sig = torch.zeros((S, P_, T), dtype=torch.float32, device="cuda")
+        detsim.tracks_current_mc[(S, P_, (T + 63) // 64), (1, 1, 64)](sig, front["neigh"], tr, resp,
+                                                                     rng.create_xoroshiro128p_states(S * P_, 5))
+        out[mode] = sig.cpu().numpy()
+    detsim.MC_MODE = "cloud"
+    ref = orc.tracks_current_mc(tr, front["neigh"], T, resp, h.rng_states(S * P_, 9), 1)
+    assert h.rel_err(out["cloud"], ref) < 1e-5 and h.rel_err(out["replay"], ref) < 1e-5
+    # charge conservation: sum(I dt) of the collecting pixels is of the order of the drifted charge
+    q = out["cloud"].astype(np.float64).sum() * mod.detector.TIME_SAMPLING
+    assert 0.5 * tr["n_electrons"].sum() < q < 1.5 * tr["n_electrons"].sum()
+
+
+def test_tracks_current_f64_response(cuda):
+    from larndsim_b200 import detsim, rng
+    import torch
+    mod, tr, orc, front, resp = _mc_setup(8, "module0")
+    resp64 = resp.astype(np.float64) * (1 + 1e-9)
+    S, P_ = front["neigh"].shape
+    st = h.rng_states(S * P_, 2)
+    ref = orc.tracks_current_mc(tr, front["neigh"], front["T"], resp64, st, 0)
+    sig = torch.zeros((S, P_, front["T"]), dtype=torch.float32, device="cuda")
+    detsim.tracks_current_mc[(S, P_, 31), (1, 1, 64)](sig, front["neigh"], tr, resp64, rng.create_xoroshiro128p_states(S * P_, 2))
+    assert h.rel_err(sig.cpu().numpy(), ref) < 1e-5
+
+
+def test_tracks_current_deterministic_vs_oracle(cuda):
+    """tracks_current (detsim.py:351-453) on a reduced SAMPLED_POINTS grid, 1e-5 on float32 waveforms."""
+    from larndsim_b200 import detsim
+    import torch
+    mod, tr, orc, front, resp = _mc_setup(3, "module0")
+    mod.detector.SAMPLED_POINTS = 8
+    orc = h.Oracle()
+    S, P_ = front["neigh"].shape
+    T = front["T"]
+    ref = orc.tracks_current(tr, front["neigh"], T, resp)
+    sig = torch.zeros((S, P_, T), dtype=torch.float32, device="cuda")
+    detsim.tracks_current[(S, P_, (T + 63) // 64), (1, 1, 64)](sig, front["neigh"], tr, resp)
+    got = sig.cpu().numpy()
+    assert (ref != 0).sum() > 100
+    assert h.rel_err(got, ref) < 1e-5
+
+
+@pytest.mark.parametrize("K", [50, 2])
+def test_sum_pixel_signals_and_adc_bitexact(cuda, K):
+    """sum_pixel_signals + get_adc_values + digitize from identical inputs: float64 sums in the oracle's
+    order, hits / timestamps / fractions bit for bit, RNG streams advanced identically (noise on)."""
+    from larndsim_b200 import detsim, fee, rng
+    import torch
+    mod, tr, orc, front, resp = _mc_setup(40, "module0", seed=21)
+    mod.sim.MAX_TRACKS_PER_PIXEL = K
+    orc = h.Oracle()
+    S, P_ = front["neigh"].shape
+    st = h.rng_states(S * P_, 4)
+    sig = orc.tracks_current_mc(tr, front["neigh"], front["T"], resp, st, 0)
+    st_fee = st.copy()
+    back = h.oracle_back(orc, front, sig, st_fee)
+    U, Tt, A = len(front["uniq"]), orc.c.n_time_ticks, orc.c.max_adc_values
+    assert (back["overflow"] != 0).any() == (K == 2)
+    ps = torch.zeros((U, Tt), dtype=torch.float64, device="cuda")
+    pts = torch.zeros((U, Tt, K), dtype=torch.float64, device="cuda")
+    of = torch.zeros(U, dtype=torch.float64, device="cuda")
+    detsim.sum_pixel_signals[(S, P_, 31), (1, 1, 64)](ps, sig, front["starts"], back["pim"], back["tpm"], pts, of)
+    assert np.array_equal(ps.cpu().numpy(), back["ps"])
+    assert np.array_equal(pts.cpu().numpy(), back["pts"])
+    assert np.array_equal(of.cpu().numpy(), back["overflow"])
+    time_ticks = np.linspace(0, orc.c.time_interval[1], Tt + 1)
+    adc = torch.zeros((U, A), dtype=torch.float64, device="cuda")
+    tks = torch.zeros((U, A), dtype=torch.float64, device="cuda")
+    cf = torch.zeros((U, A, K), dtype=torch.float64, device="cuda")
+    thr = torch.full((U,), orc.c.discrimination_threshold * orc.c.unit_e, dtype=torch.float64, device="cuda")
+    states = rng.DeviceRecords(host=st.view(rng.xoroshiro128p_dtype).reshape(-1))
+    fee.get_adc_values[(U + 127) // 128, 128](ps, pts, time_ticks, adc, tks, 0, states, cf, thr)
+    assert (back["adc"] != 0).sum() > 10
+    assert np.array_equal(adc.cpu().numpy(), back["adc"])
+    assert np.array_equal(tks.cpu().numpy(), back["ticks"])
+    assert np.array_equal(cf.cpu().numpy(), back["cf"])
+    assert np.array_equal(states.copy_to_host().view(np.uint64).reshape(-1, 2), st_fee)
+    dg = fee.digitize(adc)
+    assert np.array_equal(dg.cpu().numpy(), back["digit"])
+    assert np.array_equal(fee.digitize(back["adc"]), back["digit"])            # NumPy in -> NumPy out
+
+
+def test_adc_noise_off_and_low_threshold(cuda):
+    """Noise constants 0 (the RNG still advances) and a low threshold so pixels fire several times,
+    reset windows and busy ticks are exercised."""
+    from larndsim_b200 import fee, rng
+    import torch
+    mod, tr, orc, front, resp = _mc_setup(30, "module0", seed=33)
+    for k in ("RESET_NOISE_CHARGE", "UNCORRELATED_NOISE_CHARGE", "DISCRIMINATOR_NOISE"):
+        setattr(mod.detector, k, 0)
+    mod.detector.DISCRIMINATION_THRESHOLD = 1500.0
+    orc = h.Oracle()
+    S, P_ = front["neigh"].shape
+    st = h.rng_states(max(S * P_, 128 * ((len(front["uniq"]) + 127) // 128)), 4)
+    sig = orc.tracks_current_mc(tr, front["neigh"], front["T"], resp, st, 0)
+    st_fee = st.copy()
+    back = h.oracle_back(orc, front, sig, st_fee)
+    U, Tt, A, K = len(front["uniq"]), orc.c.n_time_ticks, orc.c.max_adc_values, orc.c.max_tracks_per_pixel
+    assert ((back["adc"] != 0).sum(axis=1) > 1).any()
+    adc = np.zeros((U, A)); tks = np.zeros((U, A)); cf = np.zeros((U, A, K))
+    states = rng.DeviceRecords(host=st.view(rng.xoroshiro128p_dtype).reshape(-1))
+    fee.get_adc_values[(U + 127) // 128, 128](back["ps"], back["pts"], np.linspace(0, orc.c.time_interval[1], Tt + 1), adc, tks, 0,
+                                              states, cf, np.full(U, 1500.0))
+    assert np.array_equal(adc, back["adc"]) and np.array_equal(tks, back["ticks"]) and np.array_equal(cf, back["cf"])
+    assert np.array_equal(states.copy_to_host().view(np.uint64).reshape(-1, 2), st_fee)
+
+
+@pytest.mark.parametrize("config,kind,n", [("module0", "cosmic", 200), ("2x2", "beam", 300), ("ndlar", "beam", 200)])
+def test_chain_vs_oracle(cuda, config, kind, n):
+    r = h.chain_vs_oracle(n_segments=n, config=config, seed=17, noise=True, kind=kind)
+    assert r["tracks_equal"] and r["shape_equal"] and r["unique_equal"] and r["tpm_equal"]
+    assert r["signals_relerr"] < 1e-5
+    assert r["pixels_signals_equal"] and r["adc_list_equal"] and r["ticks_equal"] and r["cf_equal"]
+    assert r["adc_mismatch"] == 0 and r["n_hits"] == r["n_hits_oracle"] and r["n_hits"] > 0
+    assert r["launches"] > 10
