@@ -247,21 +247,33 @@ __global__ void k_mc_sampler(McParams p, PairRec* __restrict__ pairs, SampleRec*
 #define ACC_RMAX 8
 #define ACC_CHUNK 256      // samples staged per smem chunk
 
+// Samples are summed in float32 in groups of ACC_GROUP and the group sums are added in float64: samples
+// that hit the same LUT row with the same tick shift contribute identical values, so a plain float32
+// running sum would round in the same direction every time (error growing linearly with the count).
+#define ACC_GROUP 8
 template <typename TL, int STRIDE, int NFULL>
 __device__ __forceinline__ void acc_interior(const TL* __restrict__ lut, const int* s_off, int ns, int base_tick, bool rem_ok,
-                                             float (&acc)[ACC_RMAX]) {
+                                             double (&dacc)[ACC_RMAX]) {
     // signal[base_tick + tid + TPB*r] += LUT[off + STRIDE*(base_tick + tid + TPB*r)]
     const TL* pbase = lut + (long long)STRIDE * (base_tick + (int)threadIdx.x);
-#pragma unroll 2
-    for (int s = 0; s < ns; s++) {
-        int off = s_off[s];
-        if (off == OFF_IRREGULAR) continue;    // irregular sample: handled by the exact path
-        const TL* p = pbase + off;
+    for (int s0 = 0; s0 < ns; s0 += ACC_GROUP) {
+        float acc[ACC_RMAX];
 #pragma unroll
-        for (int r = 0; r < NFULL; r++) acc[r] += (float)__ldg(p + r * ACC_TPB * STRIDE);
-        if (NFULL < ACC_RMAX) {
-            if (rem_ok) acc[NFULL] += (float)__ldg(p + NFULL * ACC_TPB * STRIDE);
+        for (int r = 0; r < ACC_RMAX; r++) acc[r] = 0.f;
+#pragma unroll
+        for (int u = 0; u < ACC_GROUP; u++) {
+            int s = s0 + u;
+            int off = s < ns ? s_off[s] : OFF_IRREGULAR;
+            if (off == OFF_IRREGULAR) continue;    // irregular sample: handled by the exact path
+            const TL* p = pbase + off;
+#pragma unroll
+            for (int r = 0; r < NFULL; r++) acc[r] += (float)__ldg(p + r * ACC_TPB * STRIDE);
+            if (NFULL < ACC_RMAX) {
+                if (rem_ok) acc[NFULL] += (float)__ldg(p + NFULL * ACC_TPB * STRIDE);
+            }
         }
+#pragma unroll
+        for (int r = 0; r < ACC_RMAX; r++) if (r <= NFULL) dacc[r] += (double)acc[r];
     }
 }
 
@@ -294,29 +306,25 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
             if (n_int > ACC_TPB * ACC_RMAX) n_int = ACC_TPB * ACC_RMAX;
             const int nfull = n_int / ACC_TPB, rem = n_int - nfull * ACC_TPB;
             const bool rem_ok = tid < rem;
-            float acc[ACC_RMAX];
             double dacc[ACC_RMAX];
 #pragma unroll
-            for (int r = 0; r < ACC_RMAX; r++) { acc[r] = 0.f; dacc[r] = 0.0; }
+            for (int r = 0; r < ACC_RMAX; r++) dacc[r] = 0.0;
             for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
                 int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
                 __syncthreads();
                 if (tid < ns) s_off[tid] = offs32[soff + c0 + tid];
                 __syncthreads();
                 switch (nfull) {
-                    case 0: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 0>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 1: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 1>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 2: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 2>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 3: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 3>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 4: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 4>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 5: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 5>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 6: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 6>(lut, s_off, ns, base, rem_ok, acc); break;
-                    case 7: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 7>(lut, s_off, ns, base, rem_ok, acc); break;
-                    default: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 8>(lut, s_off, ns, base, rem_ok, acc); break;
+                    case 0: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 0>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 1: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 1>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 2: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 2>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 3: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 3>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 4: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 4>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 5: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 5>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 6: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 6>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    case 7: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 7>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    default: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 8>(lut, s_off, ns, base, rem_ok, dacc); break;
                 }
-                // flush the float32 partial sums into float64 every chunk (bounds rounding growth)
-#pragma unroll
-                for (int r = 0; r < ACC_RMAX; r++) { dacc[r] += (double)acc[r]; acc[r] = 0.f; }
             }
             // irregular samples (off < 0) contribute to interior ticks through the exact path below,
             // so interior results are written with "+=" semantics into a zeroed output: store now,

@@ -153,6 +153,67 @@ class Oracle:
         return out
 
 
+class OracleLight:
+    """Light-chain calls of the oracle (lightLUT.py / light_sim.py restatements)."""
+
+    def __init__(self, c=None):
+        self.c = c if c is not None else lconsts.snapshot()
+        self.lib = oracle_lib()
+
+    def light_incidence(self, tracks, lut, ndet, eff, ch2tpc):
+        L = _abi.track_layout(tracks.dtype)
+        LL = _abi.lut_layout(lut.dtype, lut.shape)
+        linc = np.zeros((len(tracks), ndet), dtype=[("segment_id", "u4"), ("n_photons_det", "f4"), ("t0_det", "f4")])
+        LI = _abi.linc_layout(linc.dtype)
+        vox = np.zeros((len(tracks), 3), dtype=np.int32)
+        eff = np.ascontiguousarray(eff, dtype=np.float64)
+        ch2tpc = np.ascontiguousarray(ch2tpc, dtype=np.int64)
+        self.lib.orc_calculate_light_incidence(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(len(tracks)), P(lut), C.byref(LL),
+                                               P(linc), C.byref(LI), C.c_int32(ndet), P(vox), P(eff), P(ch2tpc))
+        return linc, vox
+
+    def sum_light_signals(self, tracks, vox, seg_ids, linc, op_channel, lut, t_start, nticks, n_true, sorted_idx, prof_len):
+        L = _abi.track_layout(tracks.dtype)
+        LL = _abi.lut_layout(lut.dtype, lut.shape)
+        LI = _abi.linc_layout(linc.dtype)
+        nd = len(op_channel)
+        inc = np.zeros((nd, nticks), dtype=np.float32)
+        tid = np.full((nd, nticks, n_true), -1, dtype=np.int64)
+        tph = np.zeros((nd, nticks, n_true), dtype=np.float64)
+        self.lib.orc_sum_light_signals(C.byref(self.c), C.byref(L), P(tracks), C.c_int64(len(tracks)), P(vox), P(seg_ids), P(linc),
+                                       C.byref(LI), C.c_int32(linc.shape[1]), P(op_channel), P(lut), C.byref(LL),
+                                       C.c_double(float(t_start)), P(inc), C.c_int32(nd), C.c_int32(nticks), P(tid), P(tph),
+                                       C.c_int32(n_true), P(sorted_idx), C.c_int64(sorted_idx.shape[1]), C.c_double(float(prof_len)))
+        return inc, tid, tph
+
+    def scintillation(self, inc, tid, tph):
+        nd, nticks = inc.shape
+        out = np.zeros_like(inc)
+        oid = np.full_like(tid, -1)
+        oph = np.zeros_like(tph)
+        self.lib.orc_calc_scintillation_effect(C.byref(self.c), P(inc), P(tid), P(tph), P(out), P(oid), P(oph), C.c_int32(nd),
+                                               C.c_int32(nticks), C.c_int32(tid.shape[2]), C.c_int32(oid.shape[2]))
+        return out, oid, oph
+
+    def stat_fluctuations(self, inc, states):
+        nd, nticks = inc.shape
+        out = np.zeros_like(inc)
+        self.lib.orc_calc_stat_fluctuations(C.byref(self.c), P(inc), P(out), C.c_int32(nd), C.c_int32(nticks), P(states))
+        return out
+
+    def detector_response(self, inc, tid, tph, gain, impulse):
+        nd, nticks = inc.shape
+        out = np.zeros_like(inc)
+        oid = np.full_like(tid, -1)
+        oph = np.zeros_like(tph)
+        gain = np.ascontiguousarray(gain, dtype=np.float64)
+        impulse = np.ascontiguousarray(impulse, dtype=np.float64)
+        self.lib.orc_calc_light_detector_response(C.byref(self.c), P(inc), P(tid), P(tph), P(out), P(oid), P(oph), C.c_int32(nd),
+                                                  C.c_int32(nticks), C.c_int32(tid.shape[2]), C.c_int32(oid.shape[2]), P(gain),
+                                                  P(impulse), C.c_int32(impulse.size))
+        return out, oid, oph
+
+
 def production_tracks(n, config="module0", seed=12345, kind="cosmic", dtype=None):
     mod = lconsts.load_snapshot(config)
     dt = dtype if dtype is not None else synth.segment_dtype
@@ -188,6 +249,39 @@ def oracle_back(orc, front, signals, states, n_events=1):
     return dict(pim=pim, tpm=tpm, ps=ps, pts=pts, overflow=of, adc=adc, ticks=ticks, cf=cf, digit=orc.digitize(adc))
 
 
+#: The oracle evaluates exp/log/erf with glibc, the CUDA kernels with libdevice (what the reference's
+#: Numba-CUDA build calls): both are <= 1 ulp but not bit-identical, exactly like the reference's own GPU
+#: and CUDA-simulator builds.  float64 record fields that go through a transcendental are therefore
+#: compared to a few ulp; everything stored as float32 / integer must be identical.
+F64_RTOL = 1e-14
+
+
+def records_equal(a, b, f64_rtol=0.0):
+    """Field-by-field equality of two structured arrays (padding bytes are not data)."""
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    for name in a.dtype.names:
+        x, y = a[name], b[name]
+        if x.dtype.kind == "f":
+            if np.array_equal(x, y, equal_nan=True):
+                continue
+            if x.dtype.itemsize == 8 and f64_rtol > 0 and np.allclose(x, y, rtol=f64_rtol, atol=0, equal_nan=True):
+                continue
+            return False
+        elif not np.array_equal(x, y):
+            return False
+    return True
+
+
+def rel_err_peak(a, b):
+    """max |a-b| / (|b| + max|b| per waveform) -- allclose(rtol, atol = rtol * peak)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.abs(b) + np.abs(b).max(axis=-1, keepdims=True)
+    den[den == 0] = 1.0
+    return float((np.abs(a - b) / den).max())
+
+
 def rel_err(a, b):
     """max |a-b| / (|b| + 1e-2 * max|b| per waveform): elementwise relative error with a floor that keeps
     zero crossings of bipolar waveforms from dominating."""
@@ -205,12 +299,12 @@ def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="c
     """Run the fused CUDA chain on a synthetic batch and compare with the oracle stage by stage."""
     import torch
     from larndsim_b200 import chain as lchain, _launch as ll
+    tracks = production_tracks(n_segments, config, seed, kind)
     mod = lconsts.load_snapshot(config)
     if not noise:
         mod.detector.RESET_NOISE_CHARGE = 0
         mod.detector.UNCORRELATED_NOISE_CHARGE = 0
         mod.detector.DISCRIMINATOR_NOISE = 0
-    tracks = production_tracks(n_segments, config, seed, kind)
     if response is None:
         response = synth.response_lut(mod.detector)
     c = lconsts.snapshot()
@@ -227,7 +321,7 @@ def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="c
     front = oracle_front(otr, orc, quench_mode=c.mode_birks)
     S, P_ = front["neigh"].shape
     out = dict(S=S, U=len(front["uniq"]), T=front["T"], launches=int(launches), n_hits=res.n_hits)
-    out["tracks_equal"] = bool(g_tracks.tobytes() == otr.tobytes())
+    out["tracks_equal"] = records_equal(g_tracks, otr)
     out["shape_equal"] = (res.max_neighbors == P_ and res.n_ticks == front["T"] and res.n_unique_pixels == len(front["uniq"]))
     out["unique_equal"] = out["shape_equal"] and bool(np.array_equal(res.unique_pix.cpu().numpy(), front["uniq"]))
     n_rng = max(S * P_, 128 * ((out["U"] + 127) // 128))
@@ -243,7 +337,10 @@ def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="c
     out["pixels_signals_equal"] = bool(np.array_equal(res.pixels_signals.cpu().numpy(), back["ps"]))
     g_digit = res.adc_digit.cpu().numpy()
     out["adc_mismatch"] = int((g_digit != back["digit"]).sum())
-    out["adc_list_equal"] = bool(np.array_equal(res.adc_list.cpu().numpy(), back["adc"]))
+    g_adc = res.adc_list.cpu().numpy()
+    out["adc_list_equal"] = bool(np.array_equal(g_adc, back["adc"]))
+    out["adc_list_relerr"] = float(np.abs(g_adc - back["adc"]).max() / max(np.abs(back["adc"]).max(), 1e-300))
+    out["adc_pattern_equal"] = bool(np.array_equal(g_adc != 0, back["adc"] != 0))
     out["ticks_equal"] = bool(np.array_equal(res.adc_ticks_list.cpu().numpy(), back["ticks"]))
     g_cf = res.current_fractions.cpu().numpy()
     out["cf_equal"] = bool(np.array_equal(g_cf, back["cf"]))

@@ -216,14 +216,21 @@ def host_kernel(module, name):
     ns["xoroshiro128p_uniform_float32"] = nbrandom.xoroshiro128p_uniform_float32
     ns["xoroshiro128p_normal_float32"] = nbrandom.xoroshiro128p_normal_float32
     # device functions declared with cuda.jit(device=True) need host versions
+    # error_model="numpy": no Python exceptions on x/0 etc., like the CUDA target (quenching.py:33 relies
+    # on log(0.93)/0 = -inf).  @nb.njit helpers of the reference are re-jitted the same way.
+    jit = nb.njit(error_model="numpy")
     for k, v in list(ns.items()):
         pf = getattr(v, "py_func", None)
-        if pf is not None and type(v).__module__.startswith("numba.cuda"):
-            ns[k] = nb.njit(_rebuild(pf, ns))
+        if pf is None or not callable(pf):
+            continue
+        tmod = type(v).__module__
+        if tmod.startswith("numba.cuda") or tmod.startswith("numba.core.dispatcher") or tmod.startswith("numba.core.registry"):
+            if getattr(pf, "__module__", "").startswith("larndsim"):
+                ns[k] = jit(_rebuild(pf, ns))
     exec(compile(thread_src, "<ref:%s thread>" % name, "exec"), ns)
-    ns[name + "__thread"] = nb.njit(ns[name + "__thread"])
+    ns[name + "__thread"] = jit(ns[name + "__thread"])
     exec(compile(grid_src, "<ref:%s grid>" % name, "exec"), ns)
-    gridfn = nb.njit(ns[name + "__grid"])
+    gridfn = jit(ns[name + "__grid"])
 
     def run(grid_shape, *args):
         if isinstance(grid_shape, int):
