@@ -241,13 +241,14 @@ int lsb_calc_scintillation_effect(const lsb_consts* c, const float* light_sample
 int lsb_calc_stat_fluctuations(const lsb_consts* c, const float* light_sample_inc, float* light_sample_inc_disc,
                                int32_t ndet, int32_t nticks, uint64_t* rng_states, int64_t n_rng, void* stream);
 /* larndsim/light_sim.py:303-336  calc_light_detector_response(6 arrays);
- * light_gain = light.LIGHT_GAIN (f64[ndet...]); impulse_model = light.IMPULSE_MODEL (f64[n_impulse]) */
+ * light_gain = light.LIGHT_GAIN (device f64[ndet...]); impulse_model_host = light.IMPULSE_MODEL (HOST f64[n_impulse]:
+ * the tap weights are evaluated once per call on the host) */
 int lsb_calc_light_detector_response(const lsb_consts* c, const float* light_sample_inc,
                                      const int64_t* inc_true_track_id, const double* inc_true_photons,
                                      float* light_response, int64_t* resp_true_track_id,
                                      double* resp_true_photons, int32_t ndet, int32_t nticks,
                                      int32_t n_true_in, int32_t n_true_out,
-                                     const double* light_gain, const double* impulse_model, int32_t n_impulse,
+                                     const double* light_gain, const double* impulse_model_host, int32_t n_impulse,
                                      void* stream);
 
 /* ---- fused device-resident batch driver (replaces cli/simulate_pixels.py:907-1117) ---- */

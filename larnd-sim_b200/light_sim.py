@@ -94,10 +94,11 @@ def calc_light_detector_response(light_sample_inc, light_sample_inc_true_track_i
     g = _l.dev(gain, name="LIGHT_GAIN")
     imp = getattr(light, "IMPULSE_MODEL", None)
     if imp is not None:
-        impd = _l.dev(np.ascontiguousarray(imp, dtype=np.float64), name="IMPULSE_MODEL")
-        imp_c, n_imp = impd.c, impd.size
+        # the tap weights are evaluated on the host once per call: IMPULSE_MODEL stays a host array
+        imph = np.ascontiguousarray(imp, dtype=np.float64)
+        imp_c, n_imp = imph.ctypes.data_as(C.c_void_p), imph.size
     else:
-        impd, imp_c, n_imp = None, None, 0
+        imph, imp_c, n_imp = None, None, 0
     _l.check(_l.lib().lsb_calc_light_detector_response(C.byref(c), a.c, ai.c, ap.c, o.c, oi.c, op.c, C.c_int32(ndet),
                                                        C.c_int32(nticks), C.c_int32(n_in), C.c_int32(n_out), g.c, imp_c,
                                                        C.c_int32(n_imp), _l.stream()), "calc_light_detector_response")
