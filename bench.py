@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the charge-readout chain (BASELINE.json metric: segments/s quench -> ADC).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path (quench -> drift -> get_pixels -> tracks_current_mc -> unique / index
+maps -> sum_pixel_signals -> get_adc_values -> digitize) over one batch of synthetic segments.  Workload at
+N=1: BASELINE.json configs[1] -- module0 geometry, 1e4 synthetic cosmic-muon segments, noise on.  For N>1
+(torchrun, one rank per GPU) every rank processes its own batch of the same size (different muons:
+independent (event, module) units), no collective inside the chain; the per-step hit
+packets are gathered to rank 0 over NCCL.  ``value`` = segments of all ranks / max-over-ranks device time.
+
+``--impl reference`` times the CPU implementation of the same path: the reference's kernels are Numba
+Python and cannot travel to the GPU box, so this arm runs the C restatement pinned to them
+(oracle/larnd_oracle.c, OpenMP on all host cores) on a bounded sample of the same batch.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIG = "module0"
+N_SEGMENTS = 10000
+METRIC = "segments/s quench->ADC (module0, 1e4 synthetic cosmic-muon segments per batch)"
+
+
+def make_batch(seed):
+    from larndsim_b200 import consts as lc, synth
+    mod = lc.load_snapshot(CONFIG)
+    tracks = synth.cosmic_segments(N_SEGMENTS, mod.detector, seed=seed)
+    response = synth.response_lut(mod.detector)
+    return mod, tracks, response
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_chain(tracks, response, n_sample, rng_seed=1):
+    """The CPU restatement of the chain on the first n_sample segments; returns seconds."""
+    import helpers as h
+    sub = tracks[:n_sample].copy()
+    orc = h.Oracle()
+    t0 = time.perf_counter()
+    front = h.oracle_front(sub, orc, quench_mode=orc.c.mode_birks)
+    S, P_ = front["neigh"].shape
+    n_rng = max(S * P_, 128 * ((len(front["uniq"]) + 127) // 128))
+    states = h.rng_states(n_rng, rng_seed)
+    sig = orc.tracks_current_mc(sub, front["neigh"], front["T"], response, states, 0)
+    back = h.oracle_back(orc, front, sig, states)
+    dt = time.perf_counter() - t0
+    return dt, int((back["digit"] > orc.digitize(np.zeros(1))[0]).sum())
+
+
+def omp_threads():
+    n = os.environ.get("OMP_NUM_THREADS")
+    return int(n) if n else (os.cpu_count() or 1)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    mod, tracks, response = make_batch(12345)
+    n_sample = 256
+    for _ in range(args.warmup):
+        cpu_chain(tracks, response, 32)
+    times = []
+    for _ in range(args.steps):
+        dt, hits = cpu_chain(tracks, response, n_sample)
+        times.append(dt)
+    total = sum(times)
+    value = n_sample * args.steps / total
+    cores = omp_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments), charge readout quench->ADC",
+                       "sample": "first %d of the 1e4-segment batch per step" % n_sample},
+            "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": "port",
+                             "sample": "first %d segments of the batch, CPU restatement pinned to the reference's golden vectors "
+                                       "(the reference itself is Numba Python and does not exist on the GPU box)" % n_sample},
+            "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def parse_profile(txt):
+    out = {}
+    for ln in txt.strip().split("\n"):
+        f = ln.split()
+        if len(f) == 3:
+            out[f[0]] = (int(f[1]), float(f[2]))
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from larndsim_b200 import _launch as ll, chain as lchain, consts as lc
+    lib = ll.lib()
+    lib.lsb_profile_end.restype = C.c_int64
+    mod, tracks, response = make_batch(12345 + 1000 * rank)
+    S = len(tracks)
+    itemsize = tracks.dtype.itemsize
+    ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud", stage_timing=True)
+    raw = torch.from_numpy(tracks.view(np.uint8).reshape(-1).copy())
+    pinned_in = raw.pin_memory()
+    n_total = args.warmup + args.steps
+    dev_copies = [ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda()) for _ in range(n_total)]
+    A, K = int(lc.snapshot().max_adc_values), int(lc.snapshot().max_tracks_per_pixel)
+
+    def gather_packets(res):
+        """hit packets (pixel id, ADC, timestamp) of this batch -> rank 0 (north_star: NCCL only here)."""
+        if world == 1:
+            return
+        digit = res.adc_digit
+        ped = digit.min()
+        idx = torch.nonzero(digit > ped)
+        rec = torch.stack([res.unique_pix[idx[:, 0]].to(torch.float64), digit[idx[:, 0], idx[:, 1]],
+                           res.adc_ticks_list[idx[:, 0], idx[:, 1]]], dim=1).contiguous()
+        n = torch.tensor([rec.shape[0]], device="cuda", dtype=torch.int64)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        mx = int(max(c.item() for c in counts))
+        pad = torch.zeros((mx, 3), device="cuda", dtype=torch.float64)
+        pad[: rec.shape[0]] = rec
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident inputs ----------------
+    res = None
+    for i in range(args.warmup):
+        res = ch.run(dev_copies[i], rng_seed=1)
+        gather_packets(res)
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.lsb_launch_count()
+    lib.lsb_profile_begin(ll.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_acc = {}
+    e0.record()
+    for i in range(args.steps):
+        res = ch.run(dev_copies[args.warmup + i], rng_seed=1)
+        gather_packets(res)
+        for k, v in res.stage_ms.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    e1.record()
+    sync()
+    buf = C.create_string_buffer(1 << 16)
+    lib.lsb_profile_end(buf, C.c_int64(len(buf)))
+    prof = parse_profile(buf.value.decode())
+    launches = lib.lsb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * S * args.steps / (ms_max * 1e-3)
+    U, T, P_ = res.n_unique_pixels, res.n_ticks, res.max_neighbors
+    n_samples = res.n_samples
+
+    # ---------------- e2e: host buffers through the public chain call ----------------
+    ucap = int(U * 1.2) + 1024
+    up_h = torch.empty(ucap, dtype=torch.int32).pin_memory()
+    adc_h = torch.empty((ucap, A), dtype=torch.float64).pin_memory()
+    tk_h = torch.empty((ucap, A), dtype=torch.float64).pin_memory()
+    host_batches = [raw.clone().pin_memory() for _ in range(2 + args.steps)]
+    for i in range(2):
+        ch.run_host(host_batches[i], up_h, adc_h, tk_h, rng_seed=1)
+    sync()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        r2 = ch.run_host(host_batches[2 + i], up_h, adc_h, tk_h, rng_seed=1)
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * args.steps / (float(t.item()) * 1e-3)
+    h2d = S * itemsize
+    d2h = S * itemsize + r2.n_unique_pixels * 4 + 2 * r2.n_unique_pixels * A * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = measured_peaks()
+    Tt = int(lc.snapshot().n_time_ticks)
+    kern = [(k, v) for k, v in prof.items() if not k.startswith("(")]
+    total_kernel_ms = sum(v[1] for _, v in kern)
+    top_name, (top_cnt, top_ms) = max(kern, key=lambda kv: kv[1][1])
+    per_launch_ms = top_ms / max(top_cnt, 1)
+    # algorithmic HBM bytes per launch of each candidate (DESIGN.md "kernels and their rooflines")
+    alg = {
+        "k_mc_accumulate": 4.0 * S * P_ * T + 4.0 * n_samples + 152.0 * S * P_,
+        "k_fee_fractions": 8.0 * U * Tt * K + 8.0 * U * A * K,
+        "k_sum_pixel_signals": 4.0 * S * P_ * T + 2 * 8.0 * U * Tt + 2 * 8.0 * (S * P_ * 0.61) * T,
+        "memset_pts": 8.0 * U * Tt * K,
+        "k_fee_trigger": 8.0 * U * Tt + 2 * 8.0 * U * A,
+    }
+    launches_per_step = top_cnt / args.steps
+    bytes_per_launch = alg.get(top_name, 0.0) / max(launches_per_step, 1e-9) if top_name in alg else None
+    roofline = {"kernel": top_name, "bound": "hbm", "share_of_kernel_time": top_ms / total_kernel_ms,
+                "ms_per_launch": per_launch_ms, "launches_per_step": launches_per_step,
+                "achieved": (bytes_per_launch / (per_launch_ms * 1e-3) / 1e9) if bytes_per_launch else None,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
+    roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
+    if top_name == "k_mc_accumulate":
+        # not an HBM-bound kernel: its limiter is the L1/LSU gather rate (one LUT word per FADD).  Report the
+        # FP32 figure of SURVEY 8(d) beside the HBM one.
+        n_fma = float(n_samples) * T * 0.98
+        roofline["fp32"] = {"achieved_tflops": 2.0 * n_fma / (top_ms / args.steps * 1e-3) / 1e12,
+                            "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz (spec arithmetic)",
+                            "lut_reads_per_s": n_fma / (top_ms / args.steps * 1e-3)}
+    kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
+               sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+
+    # ---------------- CPU baseline (bounded sample) ----------------
+    n_cpu = 256
+    cpu_chain(tracks, response, 16)
+    cpu_s, _ = cpu_chain(tracks, response, n_cpu)
+    cpu = {"value": n_cpu / cpu_s, "unit": "segments/s", "cores": omp_threads(), "kind": "port",
+           "sample": "first %d segments of the same batch, %.1f s; C/OpenMP restatement of the reference kernels (oracle/), "
+                     "pinned to the reference's golden vectors" % (n_cpu, cpu_s)}
+
+    line = {"metric": METRIC, "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 index/gating + f32 LUT accumulation (signals f32, pixel sums f64)", "data": "synthetic",
+            "config": {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments), charge readout quench->ADC, noise on",
+                       "segments_per_batch": S, "pixels_per_segment_row": P_, "unique_pixels": U, "ticks": T, "hits": res.n_hits,
+                       "mc_sample_points": n_samples, "rng": "cloud (one sample cloud per segment x pixel)",
+                       "l2": "per-step working set (signals %.2f GB, per-segment pixel waveforms %.2f GB) >> 126 MB L2; fresh input copy each step"
+                             % (4.0 * S * P_ * T / 1e9, 8.0 * U * Tt * K / 1e9),
+                       "parallelism": "1 batch per rank, no collective in the chain; NCCL gather of hit packets to rank 0" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": float(t.item()) / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}, "kernels": kernels}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1 and args.impl == "ours":
+        # convenience: re-launch under torchrun, one rank per GPU
+        port = 29500 + (os.getpid() % 500)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        import __graft_entry__ as ge
+        if not os.path.exists(ge.LIB):
+            raise SystemExit("CUDA extension not built: run python __graft_entry__.py")
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,12 @@ const char* lsb_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py gpu_launches) */
 int64_t     lsb_launch_count(void);
 
+/* per-kernel device timing for bench.py: between begin and end, one CUDA event is recorded on the
+ * launching stream after every kernel launch / memset of this library; lsb_profile_end writes
+ * "name count total_ms" lines (sorted by total time) into `out` and returns the bytes needed. */
+int         lsb_profile_begin(void* stream);
+int64_t     lsb_profile_end(char* out, int64_t cap);
+
 /* ---- RNG: numba.cuda.random state layout {s0:u8, s1:u8}, 16 bytes ------------------ */
 /* numba/cuda/random.py create_xoroshiro128p_states(n, seed, subsequence_start):
  * state[i] = jump^(subsequence_start+i)(splitmix64(seed)); host-side, multithreaded. */
@@ -274,6 +280,10 @@ lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layout* L,
                             const void* response, int32_t Rx, int32_t Ry, int32_t Rt, int32_t response_f64,
                             int32_t rng_mode, int32_t enable_stage_timing);
 void       lsb_chain_destroy(lsb_chain* h);
+/* dense=1: materialise pixels_tracks_signals [U][Tt][K] exactly like cli/simulate_pixels.py:1053-1055 and
+ * run get_adc_values on it; dense=0 (default): read the per-segment waveforms from `signals` through the
+ * (pixel, slot) entry list -- same numbers, no 0.8 MB/pixel tensor. */
+int        lsb_chain_set_dense(lsb_chain* h, int32_t dense);
 /* tracks on the device, modified in place by quench/drift like the reference */
 int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
                   int32_t n_events, lsb_chain_result* out, void* stream);

@@ -35,7 +35,8 @@ struct lsb_chain {
     lsb_track_layout L;
     const void* response; int Rx, Ry, Rt, f64, rng_mode, timing;
     DevBuf tracks, scal, active, neigh, nrad, npl, uniq, uniq_ws, starts, signals, mc_ws, pim, tpm, psig, pts, oflow, tticks,
-           integral, adc_digit, adc_ticks, cf, thr, rng, nhits;
+           integral, adc_digit, adc_ticks, cf, thr, rng, nhits, sx_slot, sx_counts, sx_cursor, sx_raw, sx_offs, sx_bsums, sx_sorted;
+    int dense;                // 1: materialise pixels_tracks_signals like the reference (parity / debugging)
     long long n_rng;
     int tticks_n; long long tticks_events;
     cudaEvent_t ev[ST_COUNT + 1];
@@ -72,15 +73,21 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     if (!c || !L || !response || Rx <= 0 || Ry <= 0 || Rt <= 0) { lsb_fail_arg("chain_create: bad arguments"); return nullptr; }
     lsb_chain* h = new lsb_chain();
     h->c = *c; h->L = *L; h->response = response; h->Rx = Rx; h->Ry = Ry; h->Rt = Rt; h->f64 = response_f64;
-    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
+    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->dense = 0; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
     return h;
+}
+LSB_EXPORT int lsb_chain_set_dense(lsb_chain* h, int32_t dense) {
+    LSB_REQUIRE(h, "chain_set_dense: null handle");
+    h->dense = dense ? 1 : 0;
+    return 0;
 }
 LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
     if (!h) return;
     DevBuf* all[] = {&h->tracks, &h->scal, &h->active, &h->neigh, &h->nrad, &h->npl, &h->uniq, &h->uniq_ws, &h->starts, &h->signals,
                      &h->mc_ws, &h->pim, &h->tpm, &h->psig, &h->pts, &h->oflow, &h->tticks, &h->integral, &h->adc_digit,
-                     &h->adc_ticks, &h->cf, &h->thr, &h->rng, &h->nhits};
+                     &h->adc_ticks, &h->cf, &h->thr, &h->rng, &h->nhits, &h->sx_slot, &h->sx_counts, &h->sx_cursor, &h->sx_raw,
+                     &h->sx_offs, &h->sx_bsums, &h->sx_sorted};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -173,7 +180,7 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
     CH_STAGE(4);
     // ---- tracks_current_mc (:1007-1016) -------------------------------------------------
     if ((rc = h->signals.need((size_t)S * P * T * 4))) return rc;
-    LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st));
+    LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
     long long need_rng = S * P;
     long long need_rng2 = 128LL * ((U + 127) / 128);
     if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
@@ -197,13 +204,27 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
                                        (const int32_t*)h->nrad.p, S, (int32_t)P, max_distance, st))) return rc;
     CH_STAGE(6);
     // ---- sum_pixel_signals (:1052-1063) -------------------------------------------------
-    if ((rc = h->psig.need((size_t)U * Tt * 8)) || (rc = h->pts.need((size_t)U * Tt * K * 8)) || (rc = h->oflow.need((size_t)U * 8))) return rc;
-    LSB_CUDA(cudaMemsetAsync(h->psig.p, 0, (size_t)U * Tt * 8, st));
-    LSB_CUDA(cudaMemsetAsync(h->pts.p, 0, (size_t)U * Tt * K * 8, st));
+    // default: the dense per-segment tensor pixels_tracks_signals [U][Tt][K] (0.8 MB per pixel) is NOT
+    // materialised; get_adc_values reads the per-segment waveforms straight from `signals` through the
+    // (pixel, slot) entry list.  dense=1 reproduces the reference's buffers.
+    if ((rc = h->psig.need((size_t)U * Tt * 8)) || (rc = h->oflow.need((size_t)U * 8))) return rc;
+    if (h->dense && (rc = h->pts.need((size_t)U * Tt * K * 8))) return rc;
+    LSB_CUDA(cudaMemsetAsync(h->psig.p, 0, (size_t)U * Tt * 8, st)); LSB_MARK("memset_psig", st);
+    if (h->dense) { LSB_CUDA(cudaMemsetAsync(h->pts.p, 0, (size_t)U * Tt * K * 8, st)); LSB_MARK("memset_pts", st); }
     LSB_CUDA(cudaMemsetAsync(h->oflow.p, 0, (size_t)U * 8, st));
-    if ((rc = lsb_sum_pixel_signals(c, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, S, (int32_t)P, (int32_t)T,
-                                    (const double*)h->starts.p, (const int64_t*)h->pim.p, (const int64_t*)h->tpm.p, K,
-                                    (double*)h->pts.p, (double*)h->oflow.p, st))) return rc;
+    SumCtx sx;
+    {
+        long long ne = S * P;
+        if ((rc = h->sx_slot.need((size_t)ne * 4)) || (rc = h->sx_counts.need((size_t)U * 4)) || (rc = h->sx_cursor.need((size_t)U * 4)) ||
+            (rc = h->sx_raw.need((size_t)ne * 4)) || (rc = h->sx_offs.need((size_t)U * 8)) ||
+            (rc = h->sx_bsums.need((size_t)(scan_num_blocks(U) + 1) * 8)) || (rc = h->sx_sorted.need((size_t)ne * sizeof(SumEntry)))) return rc;
+        sx.slot_of = (int*)h->sx_slot.p; sx.counts = (int*)h->sx_counts.p; sx.cursor = (int*)h->sx_cursor.p; sx.raw = (int*)h->sx_raw.p;
+        sx.offs = (long long*)h->sx_offs.p; sx.bsums = (long long*)h->sx_bsums.p; sx.sorted = (SumEntry*)h->sx_sorted.p;
+        if ((rc = lsb_upload_consts(c, st))) return rc;
+        if ((rc = sum_build_entries(sx, U, S, (int)P, (const double*)h->starts.p, (const long long*)h->pim.p, (const long long*)h->tpm.p, K,
+                                    (double*)h->oflow.p, st))) return rc;
+        if ((rc = sum_run(sx, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, (int)T, K, h->dense ? (double*)h->pts.p : nullptr, st))) return rc;
+    }
     CH_STAGE(7);
     // ---- get_adc_values (:1072-1095) ----------------------------------------------------
     if (h->tticks_n != Tt + 1 || h->tticks_events != n_events) {
@@ -225,12 +246,17 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
         (rc = h->adc_ticks.need((size_t)U * A * 8)) || (rc = h->cf.need((size_t)U * A * K * 8)) || (rc = h->thr.need((size_t)U * 8))) return rc;
     LSB_CUDA(cudaMemsetAsync(h->integral.p, 0, (size_t)U * A * 8, st));
     LSB_CUDA(cudaMemsetAsync(h->adc_ticks.p, 0, (size_t)U * A * 8, st));
-    LSB_CUDA(cudaMemsetAsync(h->cf.p, 0, (size_t)U * A * K * 8, st));
+    LSB_CUDA(cudaMemsetAsync(h->cf.p, 0, (size_t)U * A * K * 8, st)); LSB_MARK("memset_cf", st);
     k_fill_f64<<<lsb_blocks(U, 256), 256, 0, st>>>((double*)h->thr.p, U, c->discrimination_threshold * c->unit_e); LSB_LAUNCH_CHECK("k_fill_f64");
     if ((rc = chain_grow_rng(h, need_rng2, rng_seed, st))) return rc;
-    if ((rc = lsb_get_adc_values(c, (const double*)h->psig.p, (const double*)h->pts.p, U, Tt, K, (const double*)h->tticks.p, Tt + 1,
-                                 (double*)h->integral.p, (double*)h->adc_ticks.p, A, 0.0, (uint64_t*)h->rng.p, h->n_rng,
-                                 (double*)h->cf.p, (const double*)h->thr.p, st))) return rc;
+    {
+        FeeSparse sp; sp.signals = (const float*)h->signals.p; sp.T = (int)T; sp.offs = sx.offs; sp.counts = sx.counts;
+        sp.sorted = sx.sorted; sp.n_entries_cap = S * P;
+        LSB_REQUIRE(h->n_rng >= U, "chain_run: rng_states shorter than the number of pixels");
+        if ((rc = fee_run(c, (const double*)h->psig.p, h->dense ? (const double*)h->pts.p : nullptr, h->dense ? nullptr : &sp, U, Tt, K,
+                          (const double*)h->tticks.p, Tt + 1, (double*)h->integral.p, (double*)h->adc_ticks.p, A, 0.0,
+                          (uint64_t*)h->rng.p, (double*)h->cf.p, (const double*)h->thr.p, st))) return rc;
+    }
     CH_STAGE(8);
     // ---- digitize (:1102) ---------------------------------------------------------------
     if ((rc = lsb_digitize(c, (const double*)h->integral.p, nullptr, U * A, (double*)h->adc_digit.p, st))) return rc;

@@ -30,12 +30,19 @@ static inline int lsb_fail_cuda(cudaError_t e, const char* where) {
         cudaError_t e__ = (call);                                          \
         if (e__ != cudaSuccess) return lsb_fail_cuda(e__, #call);          \
     } while (0)
-#define LSB_LAUNCH_CHECK(name)                                             \
+// per-kernel timing (bench.py): when a profile session is open, an event is recorded after every
+// launch / memset; the interval since the previous mark on the stream is attributed to `name`.
+void lsb_profile_mark(const char* name, cudaStream_t st);
+extern int g_lsb_profiling;
+#define LSB_MARK(name, st) do { if (g_lsb_profiling) lsb_profile_mark(name, st); } while (0)
+#define LSB_LAUNCH_CHECK_ST(name, st)                                      \
     do {                                                                   \
         g_lsb_launches++;                                                  \
         cudaError_t e__ = cudaGetLastError();                              \
         if (e__ != cudaSuccess) return lsb_fail_cuda(e__, name);           \
+        LSB_MARK(name, st);                                                \
     } while (0)
+#define LSB_LAUNCH_CHECK(name) LSB_LAUNCH_CHECK_ST(name, st)
 #define LSB_REQUIRE(cond, what)                                            \
     do { if (!(cond)) return lsb_fail_arg(what); } while (0)
 

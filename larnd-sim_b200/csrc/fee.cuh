@@ -15,6 +15,7 @@
 // FIR weights exp((jc-ic)*dt/tau)*(1-exp(-dt/tau)) are evaluated once on the host in float64.
 #pragma once
 #include "common.cuh"
+#include "pixelmap.cuh"
 
 #define FEE_MAX_TAPS 256
 
@@ -26,6 +27,7 @@ struct FeeParams {
     long long reset_ticks;       // round(RESET_CYCLES*CLOCK_CYCLE/dt)
     long long busy_ticks;        // round(ADC_BUSY_DELAY*CLOCK_CYCLE/dt)
     int max_adc, n_w;
+    int n_taps;                  // ceil(back)+1 taps jc = floor(ic-back) .. ic
 };
 __constant__ double d_fee_w[FEE_MAX_TAPS];
 
@@ -174,6 +176,96 @@ __global__ void __launch_bounds__(128) k_fee_fractions(FeeParams fp, const doubl
     }
 }
 
+// Sparse variant for the fused chain: the dense [U][Tt][K] tensor is never materialised.  One thread per
+// (pixel, slot) pair -- the entry list built for sum_pixel_signals says which signals[segment][pixel] row
+// feeds slot k of pixel p -- walks the pixel's windows with an 11-deep (FEE_RING) register ring of
+// x = I*dt, adding x*w in the reference's order.  Taps the reference does not visit (before the last
+// reset, beyond the waveform) enter as +0.0, which leaves a float64 sum unchanged.  Values are the
+// float32 samples the dense tensor would hold, so the fractions are bit-identical to the dense path.
+#define FEE_RING 11
+__global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, const float* __restrict__ signals, int T, long long U,
+                                                              int Tt, int K, const long long* __restrict__ offs,
+                                                              const int* __restrict__ counts, const SumEntry* __restrict__ sorted,
+                                                              long long n_sorted_total, const int* __restrict__ entry_pixel,
+                                                              const FeeWindow* __restrict__ windows,
+                                                              const int* __restrict__ n_windows, int A, double* __restrict__ cf) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_sorted_total) return;
+    const int p = entry_pixel[i];
+    if (p < 0) return;                                                   // unused tail of the entry array
+    const SumEntry* L = sorted + offs[p];
+    const int n = counts[p];
+    const int me = (int)(i - offs[p]);
+    const int slot = L[me].slot;
+    for (int q = 0; q < me; q++) if (L[q].slot == slot) return;          // an earlier entry owns this (pixel, slot)
+    int n_same = 0;
+    for (int q = me + 1; q < n; q++) if (L[q].slot == slot) n_same++;
+    const float* row = signals + (long long)L[me].e * T;
+    const long long start = L[me].start_tick;
+    const int nw = n_windows[p];
+    const FeeWindow* W = windows + (long long)p * (A + 1);
+    for (int iw = 0; iw < nw; iw++) {
+        const FeeWindow w = W[iw];
+        double* out = cf + ((long long)p * A + iw) * K + slot;
+        double acc = (w.flags & 2) ? 0.0 : *out;
+        if (fp.BR > 0) {
+            double ring[FEE_RING];
+#pragma unroll
+            for (int r = 0; r < FEE_RING; r++) ring[r] = 0.0;
+            for (long long ic0 = w.ic0; ic0 <= w.ic1; ic0 += FEE_RING) {
+#pragma unroll
+                for (int r = 0; r < FEE_RING; r++) {
+                    const long long ic = ic0 + r;
+                    if (ic <= w.ic1) {
+                        double v = 0.0;
+                        if (ic < Tt) {
+                            long long it = ic - start;
+                            if (it >= 0 && it < T) v = (double)__ldg(row + it);
+                            if (n_same) {
+                                for (int q = me + 1; q < n; q++)
+                                    if (L[q].slot == slot) {
+                                        long long it2 = ic - L[q].start_tick;
+                                        if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
+                                    }
+                            }
+                        }
+                        ring[r] = v * fp.TS;
+                        // taps jc = ic-10 .. ic (ascending): ring slot of jc = (r - (ic - jc)) mod FEE_RING
+#pragma unroll
+                        for (int d = FEE_RING - 1; d >= 0; d--) {
+                            if (d < fp.n_taps) {
+                                const double x = ring[(r - d + 2 * FEE_RING) % FEE_RING];
+                                acc += x * d_fee_w[d];
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            long long hi = w.ic1 < Tt - 1 ? w.ic1 : Tt - 1;
+            for (long long ic = w.ic0; ic <= hi; ic++) {
+                double v = 0.0;
+                long long it = ic - start;
+                if (it >= 0 && it < T) v = (double)__ldg(row + it);
+                for (int q = me + 1; n_same && q < n; q++)
+                    if (L[q].slot == slot) {
+                        long long it2 = ic - L[q].start_tick;
+                        if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
+                    }
+                acc += v * fp.TS;
+            }
+        }
+        if (w.flags & 1) acc /= w.true_q;
+        *out = acc;
+    }
+}
+__global__ void k_entry_pixel(const long long* __restrict__ offs, const int* __restrict__ counts, long long U, int* __restrict__ entry_pixel) {
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= U) return;
+    long long o = offs[p];
+    for (int q = 0; q < counts[p]; q++) entry_pixel[o + q] = (int)p;
+}
+
 static int fee_params(const lsb_consts* c, FeeParams& fp, double* w_host) {
     fp.TS = c->time_sampling; fp.BR = c->buffer_risetime; fp.e = c->unit_e;
     fp.back = fp.BR > 0 ? 10 * fp.BR / fp.TS : 0.0;
@@ -182,12 +274,52 @@ static int fee_params(const lsb_consts* c, FeeParams& fp, double* w_host) {
     fp.reset_ticks = llrint(c->reset_cycles * c->clock_cycle / fp.TS);
     fp.busy_ticks = llrint(c->adc_busy_delay * c->clock_cycle / fp.TS);
     fp.max_adc = c->max_adc_values;
-    fp.n_w = 0;
+    fp.n_w = 0; fp.n_taps = 1;
     if (fp.BR > 0) {
         long long n = (long long)ceil(fp.back) + 2;
         if (n > FEE_MAX_TAPS) return lsb_fail_arg("get_adc_values: 10*BUFFER_RISETIME/TIME_SAMPLING too large (max 254 taps)");
-        fp.n_w = (int)n;
+        fp.n_w = (int)n; fp.n_taps = (int)ceil(fp.back) + 1;
         for (long long d = 0; d < n; d++) w_host[d] = exp((double)(-d) * fp.TS / fp.BR) * (1 - exp(-fp.TS / fp.BR));
+    }
+    return 0;
+}
+
+// sparse context: the (pixel, slot) entries of sum_pixel_signals and the per-segment waveforms
+struct FeeSparse { const float* signals; int T; const long long* offs; const int* counts; const SumEntry* sorted; long long n_entries_cap; };
+
+static int fee_run(const lsb_consts* c, const double* pixels_signals, const double* pst, const FeeSparse* sp, long long U, int Tt,
+                   int K, const double* time_ticks, int n_time_ticks, double* adc_list, double* adc_ticks_list, int A,
+                   double time_padding, uint64_t* rng_states, double* current_fractions, const double* pixel_thresholds,
+                   cudaStream_t st) {
+    FeeParams fp;
+    double w_host[FEE_MAX_TAPS];
+    if (fee_params(c, fp, w_host)) return -1;
+    if (fp.n_w > 0) LSB_CUDA(cudaMemcpyToSymbolAsync(d_fee_w, w_host, sizeof(double) * fp.n_w, 0, cudaMemcpyHostToDevice, st));
+    TmpPool tp(st);
+    FeeWindow* windows; int* n_windows;
+    LSB_CUDA(tp.get(&windows, U * (long long)(A + 1)));
+    LSB_CUDA(tp.get(&n_windows, U));
+    k_fee_trigger<<<lsb_blocks(U, 128), 128, 0, st>>>(fp, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list, adc_ticks_list, A,
+                                                     time_padding, (unsigned long long*)rng_states, pixel_thresholds, windows, n_windows);
+    LSB_LAUNCH_CHECK("k_fee_trigger");
+    if (K > 0 && A > 0) {
+        const bool ring_ok = fp.BR <= 0 || fp.n_taps <= FEE_RING;
+        if (sp && ring_ok) {
+            int* entry_pixel;
+            LSB_CUDA(tp.get(&entry_pixel, sp->n_entries_cap));
+            LSB_CUDA(cudaMemsetAsync(entry_pixel, 0xff, sp->n_entries_cap * 4, st));
+            k_entry_pixel<<<lsb_blocks(U, 256), 256, 0, st>>>(sp->offs, sp->counts, U, entry_pixel);
+            LSB_LAUNCH_CHECK("k_entry_pixel");
+            // entries are packed at the front of `sorted` (exclusive scan of the bucket sizes); unused tail has pixel -1
+            k_fee_fractions_sparse<<<lsb_blocks(sp->n_entries_cap, 128), 128, 0, st>>>(
+                fp, sp->signals, sp->T, U, Tt, K, sp->offs, sp->counts, sp->sorted, sp->n_entries_cap, entry_pixel, windows,
+                n_windows, A, current_fractions);
+            LSB_LAUNCH_CHECK("k_fee_fractions_sparse");
+        } else {
+            if (!pst) return lsb_fail_arg("get_adc_values: dense per-segment waveforms required for this rise time");
+            k_fee_fractions<<<lsb_blocks(U * 32, 128), 128, 0, st>>>(fp, pst, U, Tt, K, windows, n_windows, A, current_fractions);
+            LSB_LAUNCH_CHECK("k_fee_fractions");
+        }
     }
     return 0;
 }
@@ -204,22 +336,6 @@ LSB_EXPORT int lsb_get_adc_values(const lsb_consts* c, const double* pixels_sign
     LSB_REQUIRE(K == 0 || (pixels_signals_tracks && current_fractions), "get_adc_values: null per-segment arrays");
     LSB_REQUIRE(n_rng >= U, "get_adc_values: rng_states shorter than the number of pixels");
     LSB_REQUIRE(n_time_ticks >= 1 && Tt >= 0 && A >= 0, "get_adc_values: bad sizes");
-    cudaStream_t st = (cudaStream_t)stream;
-    FeeParams fp;
-    double w_host[FEE_MAX_TAPS];
-    if (fee_params(c, fp, w_host)) return -1;
-    if (fp.n_w > 0) LSB_CUDA(cudaMemcpyToSymbolAsync(d_fee_w, w_host, sizeof(double) * fp.n_w, 0, cudaMemcpyHostToDevice, st));
-    TmpPool tp(st);
-    FeeWindow* windows; int* n_windows;
-    LSB_CUDA(tp.get(&windows, U * (long long)(A + 1)));
-    LSB_CUDA(tp.get(&n_windows, U));
-    k_fee_trigger<<<lsb_blocks(U, 128), 128, 0, st>>>(fp, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list, adc_ticks_list, A,
-                                                     time_padding, (unsigned long long*)rng_states, pixel_thresholds, windows, n_windows);
-    LSB_LAUNCH_CHECK("k_fee_trigger");
-    if (K > 0 && A > 0) {
-        k_fee_fractions<<<lsb_blocks(U * 32, 128), 128, 0, st>>>(fp, pixels_signals_tracks, U, Tt, K, windows, n_windows, A,
-                                                               current_fractions);
-        LSB_LAUNCH_CHECK("k_fee_fractions");
-    }
-    return 0;
+    return fee_run(c, pixels_signals, pixels_signals_tracks, nullptr, U, Tt, K, time_ticks, n_time_ticks, adc_list, adc_ticks_list,
+                   A, time_padding, rng_states, current_fractions, pixel_thresholds, (cudaStream_t)stream);
 }

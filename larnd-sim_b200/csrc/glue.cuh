@@ -210,7 +210,8 @@ LSB_EXPORT int lsb_pixel_index_map(const int32_t* pixels, int64_t n_entries, int
     LSB_REQUIRE(workspace && (n_entries == 0 || (pixels && pixel_index_map)), "pixel_index_map: null pointer");
     if (n_entries == 0) return 0;
     UniqueWs w = unique_ws((void*)workspace, max_pixel_id);
-    k_pixel_index_map<<<lsb_blocks(n_entries, 256), 256, 0, (cudaStream_t)stream>>>(pixels, n_entries, max_pixel_id, w.flags,
+    cudaStream_t st = (cudaStream_t)stream;
+    k_pixel_index_map<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pixels, n_entries, max_pixel_id, w.flags,
                                                                                    w.prefix, (long long*)pixel_index_map);
     LSB_LAUNCH_CHECK("k_pixel_index_map");
     return 0;
@@ -220,7 +221,8 @@ LSB_EXPORT int lsb_pixel_index_map_search(const int32_t* pixels, int64_t n_entri
                                           int64_t* pixel_index_map, void* stream) {
     LSB_REQUIRE(n_entries == 0 || (pixels && pixel_index_map && (unique_pix || n_unique == 0)), "pixel_index_map_search: null pointer");
     if (n_entries == 0) return 0;
-    k_pixel_index_map_search<<<lsb_blocks(n_entries, 256), 256, 0, (cudaStream_t)stream>>>(pixels, n_entries, unique_pix, n_unique,
+    cudaStream_t st = (cudaStream_t)stream;
+    k_pixel_index_map_search<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pixels, n_entries, unique_pix, n_unique,
                                                                                           (long long*)pixel_index_map);
     LSB_LAUNCH_CHECK("k_pixel_index_map_search");
     return 0;

@@ -1,6 +1,7 @@
 // lsb.cu -- the one translation unit of liblarndsim_b200.so (sm_100a only).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 //        (see __graft_entry__.build()).  The C ABI is declared in include/larndsim_b200.h.
+#include <algorithm>
 #include "common.cuh"
 
 char g_lsb_error[512] = "";
@@ -32,6 +33,53 @@ void lsb_pool_init_once() {
     if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
     unsigned long long thr = ~0ULL;     // keep freed blocks cached: steady-state calls never reach the driver
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+}
+
+// ---- per-kernel timing --------------------------------------------------------------------
+#include <map>
+#include <string>
+#include <vector>
+int g_lsb_profiling = 0;
+struct ProfMark { const char* name; cudaEvent_t ev; };
+static std::vector<ProfMark> g_prof_marks;
+static std::vector<cudaEvent_t> g_prof_pool;
+void lsb_profile_mark(const char* name, cudaStream_t st) {
+    cudaEvent_t ev;
+    if (!g_prof_pool.empty()) { ev = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    g_prof_marks.push_back({name, ev});
+}
+LSB_EXPORT int lsb_profile_begin(void* stream) {
+    for (auto& m : g_prof_marks) g_prof_pool.push_back(m.ev);
+    g_prof_marks.clear();
+    g_lsb_profiling = 1;
+    lsb_profile_mark("(begin)", (cudaStream_t)stream);
+    return 0;
+}
+// writes "name count total_ms\n" lines, sorted by total time; returns the number of bytes needed
+LSB_EXPORT int64_t lsb_profile_end(char* out, int64_t cap) {
+    g_lsb_profiling = 0;
+    if (!g_prof_marks.empty()) cudaEventSynchronize(g_prof_marks.back().ev);
+    std::map<std::string, std::pair<long long, double>> acc;
+    for (size_t i = 1; i < g_prof_marks.size(); i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof_marks[i - 1].ev, g_prof_marks[i].ev) != cudaSuccess) continue;
+        auto& a = acc[g_prof_marks[i].name];
+        a.first++; a.second += ms;
+    }
+    std::vector<std::pair<double, std::string>> order;
+    for (auto& kv : acc) order.push_back({-kv.second.second, kv.first});
+    std::sort(order.begin(), order.end());
+    std::string txt;
+    char line[256];
+    for (auto& o : order) {
+        auto& a = acc[o.second];
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", o.second.c_str(), a.first, a.second);
+        txt += line;
+    }
+    if (out && cap > 0) { size_t n = txt.size() < (size_t)cap - 1 ? txt.size() : (size_t)cap - 1; memcpy(out, txt.data(), n); out[n] = 0; }
+    return (int64_t)txt.size() + 1;
 }
 
 #include "segments.cuh"

@@ -212,6 +212,7 @@ __global__ void k_sum_sort(const long long* __restrict__ pim, const int* __restr
 
 #define SUM_TPB 256
 #define SUM_CHUNK 64
+template <bool WITH_PTS>
 __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restrict__ pixels_signals, long long U, int Tt,
                                                                const float* __restrict__ signals, int T,
                                                                const long long* __restrict__ offs, const int* __restrict__ counts,
@@ -238,10 +239,39 @@ __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restric
             float s = __ldg(signals + (long long)s_e[i].e * T + itick);
             if (s == 0.f) continue;                            // x + 0 == x: skipping is exact
             acc += (double)s;
-            prow[s_e[i].slot] += (double)s;
+            if (WITH_PTS) prow[s_e[i].slot] += (double)s;
         }
     }
     if (active) pixels_signals[p * Tt + t] = acc;
+}
+
+// entries of every pixel, sorted by flat (segment,pixel) index, in caller-provided buffers
+struct SumCtx {
+    int* slot_of; int* counts; int* cursor; int* raw; long long* offs; long long* bsums; SumEntry* sorted;
+};
+static int sum_build_entries(const SumCtx& x, long long U, long long S, int P, const double* track_starts,
+                             const long long* pim, const long long* tpm, int K, double* overflow_flag, cudaStream_t st) {
+    long long n_entries = S * P;
+    LSB_CUDA(cudaMemsetAsync(x.counts, 0, U * 4, st));
+    LSB_CUDA(cudaMemsetAsync(x.cursor, 0, U * 4, st));
+    k_sum_bucket<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pim, n_entries, P, U, tpm, K, x.slot_of, x.counts, overflow_flag);
+    LSB_LAUNCH_CHECK("k_sum_bucket");
+    int rc = exclusive_scan<int, long long>(x.counts, U, x.offs, x.bsums, nullptr, st);
+    if (rc) return rc;
+    k_sum_fill<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pim, x.slot_of, n_entries, x.offs, x.cursor, x.raw);
+    LSB_LAUNCH_CHECK("k_sum_fill");
+    k_sum_sort<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pim, x.slot_of, n_entries, P, x.offs, x.counts, x.raw, track_starts, x.sorted);
+    LSB_LAUNCH_CHECK("k_sum_sort");
+    return 0;
+}
+static int sum_run(const SumCtx& x, double* pixels_signals, long long U, int Tt, const float* signals, int T, int K, double* pts,
+                   cudaStream_t st) {
+    if (T <= 0 || Tt <= 0) return 0;
+    dim3 grid((unsigned)U, (unsigned)((Tt + SUM_TPB - 1) / SUM_TPB));
+    if (pts) k_sum_pixel_signals<true><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, pts);
+    else k_sum_pixel_signals<false><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, nullptr);
+    LSB_LAUNCH_CHECK("k_sum_pixel_signals");
+    return 0;
 }
 
 LSB_EXPORT int lsb_sum_pixel_signals(const lsb_consts* c, double* pixels_signals, int64_t U, int32_t Tt, const float* signals,
@@ -257,30 +287,16 @@ LSB_EXPORT int lsb_sum_pixel_signals(const lsb_consts* c, double* pixels_signals
     cudaStream_t st = (cudaStream_t)stream;
     int rc = lsb_upload_consts(c, st); if (rc) return rc;
     TmpPool tp(st);
-    int* slot_of; int* counts; int* cursor; int* raw; long long* offs; long long* bsums; SumEntry* sorted;
-    LSB_CUDA(tp.get(&slot_of, n_entries));
-    LSB_CUDA(tp.get(&counts, U));
-    LSB_CUDA(tp.get(&cursor, U));
-    LSB_CUDA(tp.get(&raw, n_entries));
-    LSB_CUDA(tp.get(&offs, U));
-    LSB_CUDA(tp.get(&bsums, scan_num_blocks(U) + 1));
-    LSB_CUDA(tp.get(&sorted, n_entries));
-    LSB_CUDA(cudaMemsetAsync(counts, 0, U * 4, st));
-    LSB_CUDA(cudaMemsetAsync(cursor, 0, U * 4, st));
-    k_sum_bucket<<<lsb_blocks(n_entries, 256), 256, 0, st>>>((const long long*)pixel_index_map, n_entries, P, U,
-                                                            (const long long*)track_pixel_map, K, slot_of, counts, overflow_flag);
-    LSB_LAUNCH_CHECK("k_sum_bucket");
-    rc = exclusive_scan<int, long long>(counts, U, offs, bsums, nullptr, st);
+    SumCtx x;
+    LSB_CUDA(tp.get(&x.slot_of, n_entries));
+    LSB_CUDA(tp.get(&x.counts, U));
+    LSB_CUDA(tp.get(&x.cursor, U));
+    LSB_CUDA(tp.get(&x.raw, n_entries));
+    LSB_CUDA(tp.get(&x.offs, U));
+    LSB_CUDA(tp.get(&x.bsums, scan_num_blocks(U) + 1));
+    LSB_CUDA(tp.get(&x.sorted, n_entries));
+    rc = sum_build_entries(x, U, S, P, track_starts, (const long long*)pixel_index_map, (const long long*)track_pixel_map, K,
+                           overflow_flag, st);
     if (rc) return rc;
-    k_sum_fill<<<lsb_blocks(n_entries, 256), 256, 0, st>>>((const long long*)pixel_index_map, slot_of, n_entries, offs, cursor, raw);
-    LSB_LAUNCH_CHECK("k_sum_fill");
-    k_sum_sort<<<lsb_blocks(n_entries, 256), 256, 0, st>>>((const long long*)pixel_index_map, slot_of, n_entries, P, offs, counts,
-                                                          raw, track_starts, sorted);
-    LSB_LAUNCH_CHECK("k_sum_sort");
-    if (T > 0 && Tt > 0) {
-        dim3 grid((unsigned)U, (unsigned)((Tt + SUM_TPB - 1) / SUM_TPB));
-        k_sum_pixel_signals<<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, offs, counts, sorted, K, pixels_tracks_signals);
-        LSB_LAUNCH_CHECK("k_sum_pixel_signals");
-    }
-    return 0;
+    return sum_run(x, pixels_signals, U, Tt, signals, T, K, pixels_tracks_signals, st);
 }

@@ -295,7 +295,7 @@ def rel_err(a, b):
     return float((np.abs(a - b) / den).max())
 
 
-def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="cosmic", rng_seed=1, response=None):
+def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="cosmic", rng_seed=1, response=None, dense=False):
     """Run the fused CUDA chain on a synthetic batch and compare with the oracle stage by stage."""
     import torch
     from larndsim_b200 import chain as lchain, _launch as ll
@@ -309,7 +309,7 @@ def chain_vs_oracle(n_segments=64, config="module0", seed=7, noise=True, kind="c
         response = synth.response_lut(mod.detector)
     c = lconsts.snapshot()
     launches0 = ll.lib().lsb_launch_count()
-    ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud")
+    ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud", dense=dense)
     dtr = ll.DeviceRecords(host=tracks)
     res = ch.run(dtr, rng_seed=rng_seed, n_events=1)
     torch.cuda.synchronize()

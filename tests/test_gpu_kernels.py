@@ -283,8 +283,8 @@ def test_adc_noise_off_and_low_threshold(cuda):
 
 @pytest.mark.parametrize("config,kind,n", [("module0", "cosmic", 200), ("2x2", "beam", 300), ("ndlar", "beam", 200)])
 def test_chain_vs_oracle(cuda, config, kind, n):
-    for noise in (True, False):
-        r = h.chain_vs_oracle(n_segments=n, config=config, seed=17, noise=noise, kind=kind)
+    for noise, dense in ((True, False), (False, False), (True, True)):
+        r = h.chain_vs_oracle(n_segments=n, config=config, seed=17, noise=noise, kind=kind, dense=dense)
         assert r["tracks_equal"] and r["shape_equal"] and r["unique_equal"] and r["tpm_equal"]
         assert r["signals_relerr"] < 1e-5
         assert r["pixels_signals_equal"] and r["ticks_equal"] and r["cf_equal"] and r["adc_pattern_equal"]
