@@ -177,23 +177,15 @@ def run_ours(args, rank, world, local_rank):
     dev_copies = [ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda()) for _ in range(n_total)]
     A, K = int(lc.snapshot().max_adc_values), int(lc.snapshot().max_tracks_per_pixel)
 
+    from larndsim_b200 import dist as ldist
+
     def gather_packets(res):
         """hit packets (pixel id, ADC, timestamp) of this batch -> rank 0 (north_star: NCCL only here)."""
         if world == 1:
             return
         digit = res.adc_digit
-        ped = digit.min()
-        idx = torch.nonzero(digit > ped)
-        rec = torch.stack([res.unique_pix[idx[:, 0]].to(torch.float64), digit[idx[:, 0], idx[:, 1]],
-                           res.adc_ticks_list[idx[:, 0], idx[:, 1]]], dim=1).contiguous()
-        n = torch.tensor([rec.shape[0]], device="cuda", dtype=torch.int64)
-        counts = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(counts, n)
-        mx = int(max(c.item() for c in counts))
-        pad = torch.zeros((mx, 3), device="cuda", dtype=torch.float64)
-        pad[: rec.shape[0]] = rec
-        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)
+        rec = ldist.hit_packets(res.unique_pix, digit, res.adc_ticks_list, digit.min())
+        ldist.gather_packets(rec, dst=0)
 
     def sync():
         if world > 1:

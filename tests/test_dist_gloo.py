@@ -1,0 +1,61 @@
+"""Host-side multi-rank logic on CPU: world size 2, gloo backend."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from larndsim_b200 import dist as ldist
+
+
+def test_assign_units_lpt():
+    sizes = [900, 10, 500, 400, 30, 20]
+    a = ldist.assign_units(sizes, 2)
+    assert sorted(a[0] + a[1]) == list(range(6))
+    loads = [sum(sizes[i] for i in r) for r in a]
+    assert abs(loads[0] - loads[1]) <= 100
+    assert ldist.assign_units(sizes, 2) == a                      # deterministic
+    assert ldist.assign_units([5, 5, 5], 4)[3] == []
+
+
+def test_hit_packets_compaction():
+    uniq = torch.tensor([7, 9, 11], dtype=torch.int32)
+    digit = torch.tensor([[74., 90.], [74., 74.], [101., 74.]], dtype=torch.float64)
+    ticks = torch.tensor([[0., 12.5], [0., 0.], [3.25, 0.]], dtype=torch.float64)
+    rec = ldist.hit_packets(uniq, digit, ticks, 74.0)
+    assert rec.tolist() == [[7.0, 90.0, 12.5], [11.0, 101.0, 3.25]]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 3 if rank == 0 else 5                                     # ragged
+    rec = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3) + 100 * rank
+    out = ldist.gather_packets(rec, dst=0)
+    if rank == 0:
+        q.put([o.tolist() for o in out])
+    else:
+        assert out is None
+    empty = ldist.gather_packets(torch.zeros((0, 3), dtype=torch.float64), dst=0)     # no hits anywhere
+    if rank == 0:
+        q.put([tuple(e.shape) for e in empty])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_packets_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    shapes = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(got) == 2 and len(got[0]) == 3 and len(got[1]) == 5
+    assert got[1][0] == [100.0, 101.0, 102.0] and got[0][2] == [6.0, 7.0, 8.0]
+    assert shapes == [(0, 3), (0, 3)]
