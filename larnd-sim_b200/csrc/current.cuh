@@ -243,37 +243,62 @@ __global__ void k_mc_sampler(McParams p, PairRec* __restrict__ pairs, SampleRec*
 }
 
 // ---------------------------------------------------------------------------------------
-#define ACC_TPB 256
+#define ACC_TPB 128
 #define ACC_RMAX 8
 #define ACC_CHUNK 256      // samples staged per smem chunk
 
 // Samples are summed in float32 in groups of ACC_GROUP and the group sums are added in float64: samples
 // that hit the same LUT row with the same tick shift contribute identical values, so a plain float32
 // running sum would round in the same direction every time (error growing linearly with the count).
+// The loop is written for memory-level parallelism: the offsets of 4 samples are fetched with one uniform
+// LDS.128, their 4 x NFULL independent LDGs are issued back to back, and only then added.
 #define ACC_GROUP 8
-template <typename TL, int STRIDE, int NFULL>
-__device__ __forceinline__ void acc_interior(const TL* __restrict__ lut, const int* s_off, int ns, int base_tick, bool rem_ok,
+template <typename TL, int STRIDE, int NFULL, bool CHECK>
+__device__ __forceinline__ void acc_interior(const TL* __restrict__ lut, const int* s_off, int ns, int tick0, bool rem_ok,
                                              double (&dacc)[ACC_RMAX]) {
-    // signal[base_tick + tid + TPB*r] += LUT[off + STRIDE*(base_tick + tid + TPB*r)]
-    const TL* pbase = lut + (long long)STRIDE * (base_tick + (int)threadIdx.x);
-    for (int s0 = 0; s0 < ns; s0 += ACC_GROUP) {
+    // signal[tick0 + TPB*r] += LUT[off + STRIDE*(tick0 + TPB*r)], tick0 = base_tick + tid
+    constexpr int NL = NFULL < ACC_RMAX ? NFULL + 1 : NFULL;      // loads per sample incl. the partial row
+    const int t0 = STRIDE * tick0;
+    int s0 = 0;
+    for (; s0 + ACC_GROUP <= ns; s0 += ACC_GROUP) {
         float acc[ACC_RMAX];
 #pragma unroll
         for (int r = 0; r < ACC_RMAX; r++) acc[r] = 0.f;
 #pragma unroll
-        for (int u = 0; u < ACC_GROUP; u++) {
-            int s = s0 + u;
-            int off = s < ns ? s_off[s] : OFF_IRREGULAR;
-            if (off == OFF_IRREGULAR) continue;    // irregular sample: handled by the exact path
-            const TL* p = pbase + off;
+        for (int h = 0; h < ACC_GROUP; h += 4) {
+            const int4 o = *reinterpret_cast<const int4*>(s_off + s0 + h);
+            const int off[4] = {o.x, o.y, o.z, o.w};
+            float v[4][NL];
 #pragma unroll
-            for (int r = 0; r < NFULL; r++) acc[r] += (float)__ldg(p + r * ACC_TPB * STRIDE);
-            if (NFULL < ACC_RMAX) {
-                if (rem_ok) acc[NFULL] += (float)__ldg(p + NFULL * ACC_TPB * STRIDE);
+            for (int u = 0; u < 4; u++) {
+                const bool ok = !CHECK || off[u] != OFF_IRREGULAR;
+                const TL* p = lut + (ok ? off[u] + t0 : 0);
+#pragma unroll
+                for (int r = 0; r < NL; r++) {
+                    const bool ld = ok && (r < NFULL || rem_ok);
+                    v[u][r] = ld ? (float)__ldg(p + r * ACC_TPB * STRIDE) : 0.f;
+                }
             }
+#pragma unroll
+            for (int r = 0; r < NL; r++) acc[r] += (v[0][r] + v[1][r]) + (v[2][r] + v[3][r]);
         }
 #pragma unroll
-        for (int r = 0; r < ACC_RMAX; r++) if (r <= NFULL) dacc[r] += (double)acc[r];
+        for (int r = 0; r < NL; r++) dacc[r] += (double)acc[r];
+    }
+    if (s0 < ns) {
+        float acc[ACC_RMAX];
+#pragma unroll
+        for (int r = 0; r < ACC_RMAX; r++) acc[r] = 0.f;
+        for (int s = s0; s < ns; s++) {
+            const int off = s_off[s];
+            if (CHECK && off == OFF_IRREGULAR) continue;
+            const TL* p = lut + off + t0;
+#pragma unroll
+            for (int r = 0; r < NL; r++)
+                if (r < NFULL || rem_ok) acc[r] += (float)__ldg(p + r * ACC_TPB * STRIDE);
+        }
+#pragma unroll
+        for (int r = 0; r < NL; r++) dacc[r] += (double)acc[r];
     }
 }
 
@@ -285,8 +310,8 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
     long long pr = blockIdx.x;
     const PairRec* gp = pairs + pr;
     if (!gp->valid) return;
-    __shared__ int s_off[ACC_CHUNK];
-    __shared__ SampleRec s_rec[ACC_CHUNK];
+    __shared__ __align__(16) int s_off[ACC_CHUNK];
+    __shared__ SampleRec s_rec[ACC_TPB];
     const int tid = threadIdx.x;
     const int T = p.T;
     const int it_first = gp->it_first, n_live = gp->n_live;
@@ -312,19 +337,20 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
             for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
                 int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
                 __syncthreads();
-                if (tid < ns) s_off[tid] = offs32[soff + c0 + tid];
+                for (int q = tid; q < ns; q += ACC_TPB) s_off[q] = offs32[soff + c0 + q];
                 __syncthreads();
+#define ACC_CASE(N)                                                                                                   \
+    case N:                                                                                                           \
+        if (n_irr) acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), N, true>(lut, s_off, ns, base + tid, rem_ok, dacc);   \
+        else acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), N, false>(lut, s_off, ns, base + tid, rem_ok, dacc);        \
+        break;
                 switch (nfull) {
-                    case 0: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 0>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 1: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 1>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 2: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 2>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 3: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 3>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 4: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 4>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 5: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 5>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 6: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 6>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    case 7: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 7>(lut, s_off, ns, base, rem_ok, dacc); break;
-                    default: acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 8>(lut, s_off, ns, base, rem_ok, dacc); break;
+                    ACC_CASE(0) ACC_CASE(1) ACC_CASE(2) ACC_CASE(3) ACC_CASE(4) ACC_CASE(5) ACC_CASE(6) ACC_CASE(7)
+                    default:
+                        if (n_irr) acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 8, true>(lut, s_off, ns, base + tid, rem_ok, dacc);
+                        else acc_interior<TL, (STRIDE > 0 ? STRIDE : 1), 8, false>(lut, s_off, ns, base + tid, rem_ok, dacc);
                 }
+#undef ACC_CASE
             }
             // irregular samples (off < 0) contribute to interior ticks through the exact path below,
             // so interior results are written with "+=" semantics into a zeroed output: store now,
@@ -353,8 +379,8 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
             bool active = e < n_edge;
             int it = e < n_left ? uni_lo + e : right0 + (e - n_left);
             double sum = 0.0;
-            for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
-                int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
+            for (int c0 = 0; c0 < n_live; c0 += ACC_TPB) {
+                int ns = n_live - c0 < ACC_TPB ? n_live - c0 : ACC_TPB;
                 __syncthreads();
                 if (tid < ns) s_rec[tid] = samples[soff + c0 + tid];
                 __syncthreads();
@@ -379,8 +405,8 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
             bool active = it < T;
             double sum = 0.0;
             bool any = false;
-            for (int c0 = 0; c0 < n_live; c0 += ACC_CHUNK) {
-                int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
+            for (int c0 = 0; c0 < n_live; c0 += ACC_TPB) {
+                int ns = n_live - c0 < ACC_TPB ? n_live - c0 : ACC_TPB;
                 __syncthreads();
                 if (tid < ns) s_rec[tid] = samples[soff + c0 + tid];
                 __syncthreads();

@@ -213,29 +213,35 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
 #pragma unroll
             for (int r = 0; r < FEE_RING; r++) ring[r] = 0.0;
             for (long long ic0 = w.ic0; ic0 <= w.ic1; ic0 += FEE_RING) {
+                // the FEE_RING loads of this block are independent: issue them before the dependent adds
+                double x[FEE_RING];
 #pragma unroll
                 for (int r = 0; r < FEE_RING; r++) {
                     const long long ic = ic0 + r;
-                    if (ic <= w.ic1) {
-                        double v = 0.0;
-                        if (ic < Tt) {
-                            long long it = ic - start;
-                            if (it >= 0 && it < T) v = (double)__ldg(row + it);
-                            if (n_same) {
-                                for (int q = me + 1; q < n; q++)
-                                    if (L[q].slot == slot) {
-                                        long long it2 = ic - L[q].start_tick;
-                                        if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
-                                    }
-                            }
+                    double v = 0.0;
+                    if (ic <= w.ic1 && ic < Tt) {
+                        long long it = ic - start;
+                        if (it >= 0 && it < T) v = (double)__ldg(row + it);
+                        if (n_same) {
+                            for (int q = me + 1; q < n; q++)
+                                if (L[q].slot == slot) {
+                                    long long it2 = ic - L[q].start_tick;
+                                    if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
+                                }
                         }
-                        ring[r] = v * fp.TS;
+                    }
+                    x[r] = v * fp.TS;
+                }
+#pragma unroll
+                for (int r = 0; r < FEE_RING; r++) {
+                    if (ic0 + r <= w.ic1) {
+                        ring[r] = x[r];
                         // taps jc = ic-10 .. ic (ascending): ring slot of jc = (r - (ic - jc)) mod FEE_RING
 #pragma unroll
                         for (int d = FEE_RING - 1; d >= 0; d--) {
                             if (d < fp.n_taps) {
-                                const double x = ring[(r - d + 2 * FEE_RING) % FEE_RING];
-                                acc += x * d_fee_w[d];
+                                const double xv = ring[(r - d + 2 * FEE_RING) % FEE_RING];
+                                acc += xv * d_fee_w[d];
                             }
                         }
                     }
