@@ -65,7 +65,64 @@ __device__ __forceinline__ double fee_noise(Rng& r, double sigma, double e) {
     return (double)rng_normal_f32(r) * sigma * e;
 }
 
-__global__ void __launch_bounds__(128) k_fee_trigger(FeeParams fp, const double* __restrict__ pixels_signals, long long U, int Tt,
+// ---- pre-computed inputs of the state machine (parallel, off the serial path) -------------------
+// q_pre[ip][ic] = the CSA FIR of fee.py:566-573 with conv_start = max(0, floor(ic - back)), i.e. the value
+// the state machine needs whenever no reset lies inside the tap window (same taps, same order).
+__global__ void k_fee_fir_pre(FeeParams fp, const double* __restrict__ pixels_signals, long long U, int Tt, int Tq,
+                              double* __restrict__ q_pre) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= U * Tq) return;
+    long long ip = idx / Tq;
+    long long ic = idx - ip * Tq;
+    q_pre[idx] = fee_fir(pixels_signals + ip * Tt, ic, 0, Tt, fp);
+}
+// xoroshiro128+ is sequential per pixel but cheap; the Box-Muller transcendentals are not.  Step every
+// pixel's stream NMAX normals ahead, store the float32 uniform pairs ([i][pixel]: coalesced) and a state
+// snapshot every 64 normals, then turn the pairs into normals with one thread per value.
+#define FEE_SNAP 64
+__global__ void k_fee_rng_uniforms(const unsigned long long* __restrict__ rng_states, long long U, int NMAX,
+                                   float2* __restrict__ uu, ulonglong2* __restrict__ snaps) {
+    long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (ip >= U) return;
+    Rng r; r.s0 = rng_states[2 * ip]; r.s1 = rng_states[2 * ip + 1];
+    for (int i = 0; i < NMAX; i++) {
+        if ((i % FEE_SNAP) == 0) snaps[(long long)(i / FEE_SNAP) * U + ip] = make_ulonglong2(r.s0, r.s1);
+        float u1 = rng_uniform_f32(r);
+        float u2 = rng_uniform_f32(r);
+        uu[(long long)i * U + ip] = make_float2(u1, u2);
+    }
+    snaps[(long long)(NMAX / FEE_SNAP) * U + ip] = make_ulonglong2(r.s0, r.s1);
+}
+__global__ void k_fee_rng_normals(const float2* __restrict__ uu, float* __restrict__ nrm, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 u = uu[i];
+    float a = sqrtf(__fmul_rn(-2.0f, logf(u.x)));              // == rng_normal_f32
+    float b = cosf(__fmul_rn(6.283185307179586f, u.y));
+    nrm[i] = __fmul_rn(a, b);
+}
+
+struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2* snaps; int NMAX; };
+
+// noise source of one pixel: either the inline generator or the pre-computed normals (same values)
+template <bool PRE>
+struct FeeNoise {
+    Rng r; long long idx; long long U, ip; const FeePre* pre; bool inl;
+    __device__ __forceinline__ double draw(double sigma) {
+        if (!PRE) return fee_noise(r, sigma, 1.0);
+        if (!inl && idx >= pre->NMAX) {            // more draws than provisioned: continue inline from the last snapshot
+            ulonglong2 s = pre->snaps[(long long)(pre->NMAX / FEE_SNAP) * U + ip];
+            r.s0 = s.x; r.s1 = s.y; inl = true;
+        }
+        if (inl) { idx++; return fee_noise(r, sigma, 1.0); }
+        long long i = idx++;
+        if (sigma == 0.0) return 0.0;
+        return (double)__ldg(pre->nrm + i * U + ip) * sigma;
+    }
+};
+
+template <bool PRE>
+__global__ void __launch_bounds__(128) k_fee_trigger(FeeParams fp, FeePre pre, const double* __restrict__ pixels_signals, long long U, int Tt,
                                                       const double* __restrict__ time_ticks, int n_tt,
                                                       double* __restrict__ adc_list, double* __restrict__ adc_ticks_list, int A,
                                                       double time_padding, unsigned long long* __restrict__ rng_states,
@@ -74,33 +131,45 @@ __global__ void __launch_bounds__(128) k_fee_trigger(FeeParams fp, const double*
     long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (ip >= U) return;
     const double* curre = pixels_signals + ip * Tt;
-    Rng rng; rng.s0 = rng_states[2 * ip]; rng.s1 = rng_states[2 * ip + 1];
+    const double* qrow = PRE ? pre.q_pre + ip * pre.Tq : nullptr;
+    const long long cs_back = (long long)ceil(fp.back);          // floor(ic - back) = ic - ceil(back) for integer ic
+    FeeNoise<PRE> nz;
+    nz.idx = 0; nz.U = U; nz.ip = ip; nz.pre = &pre; nz.inl = false;
+    if (!PRE) { nz.r.s0 = rng_states[2 * ip]; nz.r.s1 = rng_states[2 * ip + 1]; }
+    auto fir = [&](long long ic, long long last_reset) -> double {
+        if (PRE && fp.BR > 0) {
+            long long cs = ic - cs_back;
+            if (cs < 0) cs = 0;
+            if (last_reset <= cs) return ic < pre.Tq ? qrow[ic] : 0.0;
+        }
+        return fee_fir(curre, ic, last_reset, Tt, fp);
+    };
     const double thr = thresholds[ip];
     long long ic = 0, adc_busy = 0, last_reset = 0;
     int iadc = 0, cleared = 0;
     double true_q = 0.0;
-    double q_sum = fee_noise(rng, fp.reset_noise, 1.0) * fp.e;
+    double q_sum = nz.draw(fp.reset_noise) * fp.e;
     FeeWindow* win = windows + ip * (A + 1);
     bool broke = false;
     while (ic < Tt || adc_busy > 0) {
         if (iadc >= fp.max_adc || iadc >= A) { broke = true; break; }
-        double q = fee_fir(curre, ic, last_reset, Tt, fp);
+        double q = fir(ic, last_reset);
         q_sum += q; true_q += q;
-        double q_noise = fee_noise(rng, fp.unc_noise, 1.0) * fp.e;
-        double disc_noise = fee_noise(rng, fp.disc_noise, 1.0) * fp.e;
+        double q_noise = nz.draw(fp.unc_noise) * fp.e;
+        double disc_noise = nz.draw(fp.disc_noise) * fp.e;
         if (adc_busy > 0) adc_busy--;
         if (q_sum + q_noise >= thr + disc_noise && adc_busy == 0) {
             long long integrate_end = ic + fp.interval;
             ic++;
             while (ic <= integrate_end) {
-                q = fee_fir(curre, ic, last_reset, Tt, fp);
+                q = fir(ic, last_reset);
                 q_sum += q; true_q += q; ic++;
             }
-            double adc = q_sum + fee_noise(rng, fp.unc_noise, 1.0) * fp.e;
-            disc_noise = fee_noise(rng, fp.disc_noise, 1.0) * fp.e;
+            double adc = q_sum + nz.draw(fp.unc_noise) * fp.e;
+            disc_noise = nz.draw(fp.disc_noise) * fp.e;
             if (adc < thr + disc_noise) {
                 ic += fp.reset_ticks;
-                q_sum = fee_noise(rng, fp.reset_noise, 1.0) * fp.e;
+                q_sum = nz.draw(fp.reset_noise) * fp.e;
                 true_q = 0.0;
                 cleared = 1;
                 last_reset = ic;
@@ -116,7 +185,7 @@ __global__ void __launch_bounds__(128) k_fee_trigger(FeeParams fp, const double*
             ic += fp.reset_ticks;
             last_reset = ic;
             adc_busy = fp.busy_ticks;
-            q_sum = fee_noise(rng, fp.reset_noise, 1.0) * fp.e;
+            q_sum = nz.draw(fp.reset_noise) * fp.e;
             true_q = 0.0;
             cleared = 0;
             iadc++;
@@ -132,7 +201,14 @@ __global__ void __launch_bounds__(128) k_fee_trigger(FeeParams fp, const double*
         nw = iadc + 1;
     }
     n_windows[ip] = nw;
-    rng_states[2 * ip] = rng.s0; rng_states[2 * ip + 1] = rng.s1;
+    if (PRE && !nz.inl) {
+        // the stream position after nz.idx normals: nearest snapshot + the remaining steps
+        long long snap = nz.idx / FEE_SNAP;
+        ulonglong2 s = pre.snaps[snap * U + ip];
+        nz.r.s0 = s.x; nz.r.s1 = s.y;
+        for (long long k = snap * FEE_SNAP; k < nz.idx; k++) { rng_next(nz.r); rng_next(nz.r); }
+    }
+    rng_states[2 * ip] = nz.r.s0; rng_states[2 * ip + 1] = nz.r.s1;
 }
 
 // warp per pixel; lane = segment slot (K > 32: several passes)
@@ -204,65 +280,80 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
     const long long start = L[me].start_tick;
     const int nw = n_windows[p];
     const FeeWindow* W = windows + (long long)p * (A + 1);
-    for (int iw = 0; iw < nw; iw++) {
-        const FeeWindow w = W[iw];
-        double* out = cf + ((long long)p * A + iw) * K + slot;
-        double acc = (w.flags & 2) ? 0.0 : *out;
-        if (fp.BR > 0) {
-            double ring[FEE_RING];
-#pragma unroll
-            for (int r = 0; r < FEE_RING; r++) ring[r] = 0.0;
-            for (long long ic0 = w.ic0; ic0 <= w.ic1; ic0 += FEE_RING) {
-                // the FEE_RING loads of this block are independent: issue them before the dependent adds
-                double x[FEE_RING];
-#pragma unroll
-                for (int r = 0; r < FEE_RING; r++) {
-                    const long long ic = ic0 + r;
-                    double v = 0.0;
-                    if (ic <= w.ic1 && ic < Tt) {
-                        long long it = ic - start;
-                        if (it >= 0 && it < T) v = (double)__ldg(row + it);
-                        if (n_same) {
-                            for (int q = me + 1; q < n; q++)
-                                if (L[q].slot == slot) {
-                                    long long it2 = ic - L[q].start_tick;
-                                    if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
-                                }
-                        }
-                    }
-                    x[r] = v * fp.TS;
-                }
-#pragma unroll
-                for (int r = 0; r < FEE_RING; r++) {
-                    if (ic0 + r <= w.ic1) {
-                        ring[r] = x[r];
-                        // taps jc = ic-10 .. ic (ascending): ring slot of jc = (r - (ic - jc)) mod FEE_RING
-#pragma unroll
-                        for (int d = FEE_RING - 1; d >= 0; d--) {
-                            if (d < fp.n_taps) {
-                                const double xv = ring[(r - d + 2 * FEE_RING) % FEE_RING];
-                                acc += xv * d_fee_w[d];
-                            }
-                        }
-                    }
-                }
-            }
-        } else {
-            long long hi = w.ic1 < Tt - 1 ? w.ic1 : Tt - 1;
-            for (long long ic = w.ic0; ic <= hi; ic++) {
-                double v = 0.0;
-                long long it = ic - start;
-                if (it >= 0 && it < T) v = (double)__ldg(row + it);
-                for (int q = me + 1; n_same && q < n; q++)
+    if (nw == 0) return;
+    // value of this (pixel, slot) waveform at pixel tick ic, as the dense tensor would hold it
+    auto sample = [&](long long ic) -> double {
+        double v = 0.0;
+        if (ic < Tt) {
+            long long it = ic - start;
+            if (it >= 0 && it < T) v = (double)__ldg(row + it);
+            if (n_same) {
+                for (int q = me + 1; q < n; q++)
                     if (L[q].slot == slot) {
                         long long it2 = ic - L[q].start_tick;
                         if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
                     }
-                acc += v * fp.TS;
             }
         }
-        if (w.flags & 1) acc /= w.true_q;
-        *out = acc;
+        return v;
+    };
+    double* out = cf + ((long long)p * A) * K + slot;
+    int iw = 0;
+    FeeWindow w = W[0];
+    double acc = 0.0;
+    if (fp.BR > 0) {
+        // one tick loop for the whole waveform, identical for every lane of the warp (ring position = ic mod
+        // FEE_RING); window starts / ends are rare per-lane events
+        double ring[FEE_RING];
+#pragma unroll
+        for (int r = 0; r < FEE_RING; r++) ring[r] = 0.0;
+        const long long last = W[nw - 1].ic1;
+        for (long long ic0 = 0; ic0 <= last && iw < nw; ic0 += FEE_RING) {
+            double x[FEE_RING];                      // independent loads first
+#pragma unroll
+            for (int r = 0; r < FEE_RING; r++) x[r] = sample(ic0 + r) * fp.TS;
+#pragma unroll
+            for (int r = 0; r < FEE_RING; r++) {
+                const long long ic = ic0 + r;
+                if (iw < nw && ic == w.ic0) {
+#pragma unroll
+                    for (int k = 0; k < FEE_RING; k++) ring[k] = 0.0;
+                    acc = (w.flags & 2) ? 0.0 : *out;
+                }
+                ring[r] = x[r];
+                if (iw < nw && ic >= w.ic0 && ic <= w.ic1) {
+                    // taps jc = ic-10 .. ic (ascending): ring slot of jc = (r - (ic - jc)) mod FEE_RING
+#pragma unroll
+                    for (int d = FEE_RING - 1; d >= 0; d--) {
+                        if (d < fp.n_taps) {
+                            const double xv = ring[(r - d + 2 * FEE_RING) % FEE_RING];
+                            acc += xv * d_fee_w[d];
+                        }
+                    }
+                    if (ic == w.ic1) {
+                        if (w.flags & 1) acc /= w.true_q;
+                        *out = acc;
+                        iw++; out += K;
+                        if (iw < nw) w = W[iw];
+                    }
+                }
+            }
+        }
+    } else {
+        for (; iw < nw; iw++, out += K) {
+            w = W[iw];
+            acc = (w.flags & 2) ? 0.0 : *out;
+            long long hi = w.ic1 < Tt - 1 ? w.ic1 : Tt - 1;
+            for (long long ic = w.ic0; ic <= hi; ic++) acc += sample(ic) * fp.TS;
+            if (w.flags & 1) acc /= w.true_q;
+            *out = acc;
+        }
+    }
+    // windows without a single FIR evaluation (a failed trigger cleared the row at the very end)
+    for (; iw < nw; iw++, out += K) {
+        w = W[iw];
+        if (w.ic1 >= w.ic0) continue;               // cannot happen: evaluated windows are closed in the loop above
+        if (w.flags & 2) *out = 0.0;
     }
 }
 __global__ void k_entry_pixel(const long long* __restrict__ offs, const int* __restrict__ counts, long long U, int* __restrict__ entry_pixel) {
@@ -305,9 +396,37 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
     FeeWindow* windows; int* n_windows;
     LSB_CUDA(tp.get(&windows, U * (long long)(A + 1)));
     LSB_CUDA(tp.get(&n_windows, U));
-    k_fee_trigger<<<lsb_blocks(U, 128), 128, 0, st>>>(fp, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list, adc_ticks_list, A,
-                                                     time_padding, (unsigned long long*)rng_states, pixel_thresholds, windows, n_windows);
-    LSB_LAUNCH_CHECK("k_fee_trigger");
+    {
+        // provision of pre-computed noise / FIR values per pixel (see k_fee_rng_uniforms)
+        const long long iters = (long long)Tt + fp.busy_ticks + 2;
+        long long nmax = 1 + 2 * iters + 3 * (iters / (fp.interval + 1) + A + 2) + 8;
+        nmax = (nmax + FEE_SNAP - 1) / FEE_SNAP * FEE_SNAP;
+        const int Tq = Tt + fp.n_taps;
+        const double pre_bytes = (double)U * ((double)nmax * 12.0 + (double)Tq * 8.0);
+        FeePre pre; pre.q_pre = nullptr; pre.Tq = Tq; pre.nrm = nullptr; pre.snaps = nullptr; pre.NMAX = (int)nmax;
+        if (pre_bytes < 12e9 && nmax < 2000000) {
+            double* q_pre; float2* uu; float* nrm; ulonglong2* snaps;
+            LSB_CUDA(tp.get(&q_pre, U * (long long)Tq));
+            LSB_CUDA(tp.get(&uu, U * nmax));
+            LSB_CUDA(tp.get(&nrm, U * nmax));
+            LSB_CUDA(tp.get(&snaps, U * (nmax / FEE_SNAP + 1)));
+            k_fee_fir_pre<<<lsb_blocks(U * (long long)Tq, 256), 256, 0, st>>>(fp, pixels_signals, U, Tt, Tq, q_pre);
+            LSB_LAUNCH_CHECK("k_fee_fir_pre");
+            k_fee_rng_uniforms<<<lsb_blocks(U, 64), 64, 0, st>>>((const unsigned long long*)rng_states, U, (int)nmax, uu, snaps);
+            LSB_LAUNCH_CHECK("k_fee_rng_uniforms");
+            k_fee_rng_normals<<<lsb_blocks(U * nmax, 256), 256, 0, st>>>(uu, nrm, U * nmax);
+            LSB_LAUNCH_CHECK("k_fee_rng_normals");
+            pre.q_pre = q_pre; pre.nrm = nrm; pre.snaps = snaps;
+            k_fee_trigger<true><<<lsb_blocks(U, 64), 64, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
+                                                                 adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,
+                                                                 pixel_thresholds, windows, n_windows);
+        } else {
+            k_fee_trigger<false><<<lsb_blocks(U, 128), 128, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
+                                                                    adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,
+                                                                    pixel_thresholds, windows, n_windows);
+        }
+        LSB_LAUNCH_CHECK("k_fee_trigger");
+    }
     if (K > 0 && A > 0) {
         const bool ring_ok = fp.BR <= 0 || fp.n_taps <= FEE_RING;
         if (sp && ring_ok) {
