@@ -104,111 +104,152 @@ __global__ void k_fee_rng_normals(const float2* __restrict__ uu, float* __restri
 
 struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2* snaps; int NMAX; };
 
-// noise source of one pixel: either the inline generator or the pre-computed normals (same values)
-template <bool PRE>
-struct FeeNoise {
-    Rng r; long long idx; long long U, ip; const FeePre* pre; bool inl;
-    __device__ __forceinline__ double draw(double sigma) {
-        if (!PRE) return fee_noise(r, sigma, 1.0);
-        if (!inl && idx >= pre->NMAX) {            // more draws than provisioned: continue inline from the last snapshot
-            ulonglong2 s = pre->snaps[(long long)(pre->NMAX / FEE_SNAP) * U + ip];
-            r.s0 = s.x; r.s1 = s.y; inl = true;
-        }
-        if (inl) { idx++; return fee_noise(r, sigma, 1.0); }
-        long long i = idx++;
-        if (sigma == 0.0) return 0.0;
-        return (double)__ldg(pre->nrm + i * U + ip) * sigma;
-    }
-};
+// The state machine is a serial, data-dependent loop: a global load per draw would expose the full memory
+// latency every tick.  Each thread therefore keeps small windows of its inputs in shared memory
+// ([slot][thread], conflict-free) and refills them with FEE_NBUF / FEE_QBUF independent loads at a time.
+#define FEE_TRIG_TPB 64
+#define FEE_NBUF 32
+#define FEE_QBUF 16
 
+// fee.py:548-655 as ONE flat loop: every iteration evaluates the CSA FIR at the pixel's current tick and
+// then does the work of the state it is in (watching for a threshold crossing, or integrating after one),
+// so the lanes of a warp -- pixels that trigger at different times -- run the same instructions.  Tick and
+// draw counters are 32-bit.  The order of FIR evaluations and of noise draws is the reference's.
 template <bool PRE>
-__global__ void __launch_bounds__(128) k_fee_trigger(FeeParams fp, FeePre pre, const double* __restrict__ pixels_signals, long long U, int Tt,
+__global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeePre pre, const double* __restrict__ pixels_signals, long long U, int Tt,
                                                       const double* __restrict__ time_ticks, int n_tt,
                                                       double* __restrict__ adc_list, double* __restrict__ adc_ticks_list, int A,
                                                       double time_padding, unsigned long long* __restrict__ rng_states,
                                                       const double* __restrict__ thresholds, FeeWindow* __restrict__ windows,
                                                       int* __restrict__ n_windows) {
-    long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    __shared__ float s_n[PRE ? FEE_NBUF * FEE_TRIG_TPB : 1];
+    __shared__ double s_q[PRE ? FEE_QBUF * FEE_TRIG_TPB : 1];
+    const long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (ip >= U) return;
     const double* curre = pixels_signals + ip * Tt;
     const double* qrow = PRE ? pre.q_pre + ip * pre.Tq : nullptr;
-    const long long cs_back = (long long)ceil(fp.back);          // floor(ic - back) = ic - ceil(back) for integer ic
-    FeeNoise<PRE> nz;
-    nz.idx = 0; nz.U = U; nz.ip = ip; nz.pre = &pre; nz.inl = false;
-    if (!PRE) { nz.r.s0 = rng_states[2 * ip]; nz.r.s1 = rng_states[2 * ip + 1]; }
-    auto fir = [&](long long ic, long long last_reset) -> double {
+    const float* ncol = PRE ? pre.nrm + ip : nullptr;
+    float* nbuf = s_n + (PRE ? threadIdx.x : 0);
+    double* qbuf = s_q + (PRE ? threadIdx.x : 0);
+    const int cs_back = (int)ceil(fp.back);          // floor(ic - back) = ic - ceil(back) for integer ic
+    const int NMAX = pre.NMAX, Tq = pre.Tq;
+    const int interval = (int)fp.interval, reset_ticks = (int)fp.reset_ticks, busy_ticks = (int)fp.busy_ticks;
+    const int max_hits = fp.max_adc < A ? fp.max_adc : A;
+    Rng rng;
+    bool inl = !PRE;
+    if (!PRE) { rng.s0 = rng_states[2 * ip]; rng.s1 = rng_states[2 * ip + 1]; }
+    int idx = 0, nbase = -FEE_NBUF - 1, qbase = -FEE_QBUF - 1;
+
+    auto refill_n = [&](int i) {
+        nbase = i;
+#pragma unroll
+        for (int k = 0; k < FEE_NBUF; k++) nbuf[k * FEE_TRIG_TPB] = (i + k < NMAX) ? __ldg(ncol + (long long)(i + k) * U) : 0.f;
+    };
+    auto refill_q = [&](int ic) {
+        qbase = ic;
+#pragma unroll
+        for (int k = 0; k < FEE_QBUF; k++) qbuf[k * FEE_TRIG_TPB] = (ic + k < Tq) ? __ldg(qrow + ic + k) : 0.0;
+    };
+    auto draw = [&](double sigma) -> double {
+        if (PRE && !inl && idx >= NMAX) {            // more draws than provisioned: continue inline from the last snapshot
+            ulonglong2 sn = pre.snaps[(long long)(NMAX / FEE_SNAP) * U + ip];
+            rng.s0 = sn.x; rng.s1 = sn.y; inl = true;
+        }
+        if (inl) { idx++; return fee_noise(rng, sigma, 1.0); }
+        const int i = idx++;
+        if (sigma == 0.0) return 0.0;
+        if (i >= nbase + FEE_NBUF) refill_n(i);
+        return (double)nbuf[(i - nbase) * FEE_TRIG_TPB] * sigma;
+    };
+    auto fir = [&](int ic, int last_reset) -> double {
         if (PRE && fp.BR > 0) {
-            long long cs = ic - cs_back;
+            int cs = ic - cs_back;
             if (cs < 0) cs = 0;
-            if (last_reset <= cs) return ic < pre.Tq ? qrow[ic] : 0.0;
+            if (last_reset <= cs) {
+                if (ic >= Tq) return 0.0;
+                if (ic < qbase || ic >= qbase + FEE_QBUF) refill_q(ic);
+                return qbuf[(ic - qbase) * FEE_TRIG_TPB];
+            }
         }
         return fee_fir(curre, ic, last_reset, Tt, fp);
     };
+
     const double thr = thresholds[ip];
-    long long ic = 0, adc_busy = 0, last_reset = 0;
-    int iadc = 0, cleared = 0;
+    int ic = 0, adc_busy = 0, last_reset = 0, iadc = 0, cleared = 0, integrate_end = 0;
+    bool integrating = false, broke = false;
     double true_q = 0.0;
-    double q_sum = nz.draw(fp.reset_noise) * fp.e;
+    double q_sum = draw(fp.reset_noise) * fp.e;                          // fee.py:557
     FeeWindow* win = windows + ip * (A + 1);
-    bool broke = false;
-    while (ic < Tt || adc_busy > 0) {
-        if (iadc >= fp.max_adc || iadc >= A) { broke = true; break; }
-        double q = fir(ic, last_reset);
+    for (;;) {
+        if (PRE) {
+            // refill the staging windows for the whole warp at once: lanes drift apart by a tick or two per hit,
+            // and per-lane refills would expose one memory latency per lane instead of one per warp
+            const bool need = !inl && ((idx + 6 > nbase + FEE_NBUF) || (fp.BR > 0 && (ic < qbase || ic >= qbase + FEE_QBUF)));
+            if (__any_sync(__activemask(), need) && !inl) { refill_n(idx); if (fp.BR > 0) refill_q(ic); }
+        }
+        if (!integrating) {
+            if (!(ic < Tt || adc_busy > 0)) break;                       // :559
+            if (iadc >= max_hits) { broke = true; break; }               // :561-563 (and the rows of the outputs)
+        }
+        const double q = fir(ic, last_reset);                            // :565-578 / :597-610
         q_sum += q; true_q += q;
-        double q_noise = nz.draw(fp.unc_noise) * fp.e;
-        double disc_noise = nz.draw(fp.disc_noise) * fp.e;
-        if (adc_busy > 0) adc_busy--;
-        if (q_sum + q_noise >= thr + disc_noise && adc_busy == 0) {
-            long long integrate_end = ic + fp.interval;
+        if (!integrating) {
+            const double q_noise = draw(fp.unc_noise) * fp.e;            // :583-584
+            const double disc_noise = draw(fp.disc_noise) * fp.e;
+            if (adc_busy > 0) adc_busy--;
+            if (q_sum + q_noise >= thr + disc_noise && adc_busy == 0) {  // :589
+                integrate_end = ic + interval;
+                integrating = true;
+            }
             ic++;
-            while (ic <= integrate_end) {
-                q = fir(ic, last_reset);
-                q_sum += q; true_q += q; ic++;
-            }
-            double adc = q_sum + nz.draw(fp.unc_noise) * fp.e;
-            disc_noise = nz.draw(fp.disc_noise) * fp.e;
-            if (adc < thr + disc_noise) {
-                ic += fp.reset_ticks;
-                q_sum = nz.draw(fp.reset_noise) * fp.e;
-                true_q = 0.0;
-                cleared = 1;
-                last_reset = ic;
-                continue;
-            }
-            FeeWindow w; w.ic0 = (int)last_reset; w.ic1 = (int)(ic - 1); w.flags = (true_q > 0 ? 1 : 0) | (cleared ? 2 : 0);
-            w.pad = 0; w.true_q = true_q;
-            win[iadc] = w;
-            adc_list[ip * A + iadc] = adc;
-            long long crossing = ic < n_tt - 1 ? ic : n_tt - 1;
-            long long post = ic - crossing > 0 ? ic - crossing : 0;
-            adc_ticks_list[ip * A + iadc] = time_ticks[crossing] + time_padding - 2 + (double)post;
-            ic += fp.reset_ticks;
-            last_reset = ic;
-            adc_busy = fp.busy_ticks;
-            q_sum = nz.draw(fp.reset_noise) * fp.e;
+            if (!integrating || ic <= integrate_end) continue;           // interval == 0: fall through to the read-out
+        } else {
+            ic++;
+            if (ic <= integrate_end) continue;
+        }
+        // ---- end of the integration window (:615-652) ----
+        integrating = false;
+        const double adc = q_sum + draw(fp.unc_noise) * fp.e;
+        const double disc_noise = draw(fp.disc_noise) * fp.e;
+        if (adc < thr + disc_noise) {                                    // :619-627
+            ic += reset_ticks;
+            q_sum = draw(fp.reset_noise) * fp.e;
             true_q = 0.0;
-            cleared = 0;
-            iadc++;
+            cleared = 1;
+            last_reset = ic;
             continue;
         }
-        ic++;
+        FeeWindow w; w.ic0 = last_reset; w.ic1 = ic - 1; w.flags = (true_q > 0 ? 1 : 0) | (cleared ? 2 : 0);
+        w.pad = 0; w.true_q = true_q;
+        win[iadc] = w;
+        adc_list[ip * A + iadc] = adc;
+        const int crossing = ic < n_tt - 1 ? ic : n_tt - 1;              // :639-643
+        const int post = ic - crossing > 0 ? ic - crossing : 0;
+        adc_ticks_list[ip * A + iadc] = time_ticks[crossing] + time_padding - 2 + (double)post;
+        ic += reset_ticks;
+        last_reset = ic;
+        adc_busy = busy_ticks;
+        q_sum = draw(fp.reset_noise) * fp.e;
+        true_q = 0.0;
+        cleared = 0;
+        iadc++;
     }
     int nw = iadc;
     if (!broke && iadc < A && (ic - 1 >= last_reset || cleared)) {
         // trailing window: accumulated but never normalised (the reference leaves it in the row)
-        FeeWindow w; w.ic0 = (int)last_reset; w.ic1 = (int)(ic - 1); w.flags = (cleared ? 2 : 0); w.pad = 0; w.true_q = 0.0;
+        FeeWindow w; w.ic0 = last_reset; w.ic1 = ic - 1; w.flags = (cleared ? 2 : 0); w.pad = 0; w.true_q = 0.0;
         win[iadc] = w;
         nw = iadc + 1;
     }
     n_windows[ip] = nw;
-    if (PRE && !nz.inl) {
-        // the stream position after nz.idx normals: nearest snapshot + the remaining steps
-        long long snap = nz.idx / FEE_SNAP;
-        ulonglong2 s = pre.snaps[snap * U + ip];
-        nz.r.s0 = s.x; nz.r.s1 = s.y;
-        for (long long k = snap * FEE_SNAP; k < nz.idx; k++) { rng_next(nz.r); rng_next(nz.r); }
+    if (PRE && !inl) {
+        // the stream position after idx normals: nearest snapshot + the remaining steps
+        const int snap = idx / FEE_SNAP;
+        ulonglong2 sn = pre.snaps[(long long)snap * U + ip];
+        rng.s0 = sn.x; rng.s1 = sn.y;
+        for (int k = snap * FEE_SNAP; k < idx; k++) { rng_next(rng); rng_next(rng); }
     }
-    rng_states[2 * ip] = nz.r.s0; rng_states[2 * ip + 1] = nz.r.s1;
+    rng_states[2 * ip] = rng.s0; rng_states[2 * ip + 1] = rng.s1;
 }
 
 // warp per pixel; lane = segment slot (K > 32: several passes)
@@ -259,6 +300,7 @@ __global__ void __launch_bounds__(128) k_fee_fractions(FeeParams fp, const doubl
 // reset, beyond the waveform) enter as +0.0, which leaves a float64 sum unchanged.  Values are the
 // float32 samples the dense tensor would hold, so the fractions are bit-identical to the dense path.
 #define FEE_RING 11
+template <int NTAPS>
 __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, const float* __restrict__ signals, int T, long long U,
                                                               int Tt, int K, const long long* __restrict__ offs,
                                                               const int* __restrict__ counts, const SumEntry* __restrict__ sorted,
@@ -282,18 +324,19 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
     const FeeWindow* W = windows + (long long)p * (A + 1);
     if (nw == 0) return;
     // value of this (pixel, slot) waveform at pixel tick ic, as the dense tensor would hold it
-    auto sample = [&](long long ic) -> double {
-        double v = 0.0;
-        if (ic < Tt) {
-            long long it = ic - start;
-            if (it >= 0 && it < T) v = (double)__ldg(row + it);
-            if (n_same) {
-                for (int q = me + 1; q < n; q++)
-                    if (L[q].slot == slot) {
-                        long long it2 = ic - L[q].start_tick;
-                        if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
-                    }
-            }
+    const int start32 = (int)(start < -2000000000LL ? -2000000000LL : (start > 2000000000LL ? 2000000000LL : start));
+    auto sample = [&](int ic) -> double {
+        // branch-free so that the FEE_RING loads of a block are issued back to back
+        const unsigned it = (unsigned)(ic - start32);
+        const bool ok = (ic < Tt) && (it < (unsigned)T);
+        const float f = __ldg(row + (ok ? it : 0u));
+        double v = ok ? (double)f : 0.0;
+        if (n_same && ic < Tt) {                     // several row entries of one segment on this pixel (not produced by get_pixels)
+            for (int q = me + 1; q < n; q++)
+                if (L[q].slot == slot) {
+                    long long it2 = ic - L[q].start_tick;
+                    if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
+                }
         }
         return v;
     };
@@ -303,38 +346,34 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
     double acc = 0.0;
     if (fp.BR > 0) {
         // one tick loop for the whole waveform, identical for every lane of the warp (ring position = ic mod
-        // FEE_RING); window starts / ends are rare per-lane events
+        // FEE_RING); window starts / ends are rare per-lane events.  NTAPS = taps of the FIR (<= FEE_RING).
         double ring[FEE_RING];
 #pragma unroll
         for (int r = 0; r < FEE_RING; r++) ring[r] = 0.0;
-        const long long last = W[nw - 1].ic1;
-        for (long long ic0 = 0; ic0 <= last && iw < nw; ic0 += FEE_RING) {
+        const int last = W[nw - 1].ic1;
+        int w0 = w.ic0, w1 = w.ic1;
+        for (int ic0 = 0; ic0 <= last && iw < nw; ic0 += FEE_RING) {
             double x[FEE_RING];                      // independent loads first
 #pragma unroll
             for (int r = 0; r < FEE_RING; r++) x[r] = sample(ic0 + r) * fp.TS;
 #pragma unroll
             for (int r = 0; r < FEE_RING; r++) {
-                const long long ic = ic0 + r;
-                if (iw < nw && ic == w.ic0) {
+                const int ic = ic0 + r;
+                if (ic == w0) {
 #pragma unroll
                     for (int k = 0; k < FEE_RING; k++) ring[k] = 0.0;
                     acc = (w.flags & 2) ? 0.0 : *out;
                 }
                 ring[r] = x[r];
-                if (iw < nw && ic >= w.ic0 && ic <= w.ic1) {
-                    // taps jc = ic-10 .. ic (ascending): ring slot of jc = (r - (ic - jc)) mod FEE_RING
+                if (ic >= w0 && ic <= w1) {
+                    // taps jc = ic-(NTAPS-1) .. ic (ascending): ring slot of jc = (r - (ic - jc)) mod FEE_RING
 #pragma unroll
-                    for (int d = FEE_RING - 1; d >= 0; d--) {
-                        if (d < fp.n_taps) {
-                            const double xv = ring[(r - d + 2 * FEE_RING) % FEE_RING];
-                            acc += xv * d_fee_w[d];
-                        }
-                    }
-                    if (ic == w.ic1) {
+                    for (int d = NTAPS - 1; d >= 0; d--) acc += ring[(r - d + 2 * FEE_RING) % FEE_RING] * d_fee_w[d];
+                    if (ic == w1) {
                         if (w.flags & 1) acc /= w.true_q;
                         *out = acc;
                         iw++; out += K;
-                        if (iw < nw) w = W[iw];
+                        if (iw < nw) { w = W[iw]; w0 = w.ic0; w1 = w.ic1; } else { w0 = 2147483647; w1 = -1; }
                     }
                 }
             }
@@ -344,7 +383,7 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
             w = W[iw];
             acc = (w.flags & 2) ? 0.0 : *out;
             long long hi = w.ic1 < Tt - 1 ? w.ic1 : Tt - 1;
-            for (long long ic = w.ic0; ic <= hi; ic++) acc += sample(ic) * fp.TS;
+            for (long long ic = w.ic0; ic <= hi; ic++) acc += sample((int)ic) * fp.TS;
             if (w.flags & 1) acc /= w.true_q;
             *out = acc;
         }
@@ -417,11 +456,11 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
             k_fee_rng_normals<<<lsb_blocks(U * nmax, 256), 256, 0, st>>>(uu, nrm, U * nmax);
             LSB_LAUNCH_CHECK("k_fee_rng_normals");
             pre.q_pre = q_pre; pre.nrm = nrm; pre.snaps = snaps;
-            k_fee_trigger<true><<<lsb_blocks(U, 64), 64, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
+            k_fee_trigger<true><<<lsb_blocks(U, FEE_TRIG_TPB), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
                                                                  adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,
                                                                  pixel_thresholds, windows, n_windows);
         } else {
-            k_fee_trigger<false><<<lsb_blocks(U, 128), 128, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
+            k_fee_trigger<false><<<lsb_blocks(U, FEE_TRIG_TPB), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
                                                                     adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,
                                                                     pixel_thresholds, windows, n_windows);
         }
@@ -436,9 +475,16 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
             k_entry_pixel<<<lsb_blocks(U, 256), 256, 0, st>>>(sp->offs, sp->counts, U, entry_pixel);
             LSB_LAUNCH_CHECK("k_entry_pixel");
             // entries are packed at the front of `sorted` (exclusive scan of the bucket sizes); unused tail has pixel -1
-            k_fee_fractions_sparse<<<lsb_blocks(sp->n_entries_cap, 128), 128, 0, st>>>(
-                fp, sp->signals, sp->T, U, Tt, K, sp->offs, sp->counts, sp->sorted, sp->n_entries_cap, entry_pixel, windows,
-                n_windows, A, current_fractions);
+#define FEE_FRAC_LAUNCH(N) k_fee_fractions_sparse<N><<<lsb_blocks(sp->n_entries_cap, 128), 128, 0, st>>>(                       \
+                fp, sp->signals, sp->T, U, Tt, K, sp->offs, sp->counts, sp->sorted, sp->n_entries_cap, entry_pixel, windows,       \
+                n_windows, A, current_fractions)
+            switch (fp.BR > 0 ? fp.n_taps : 1) {
+                case 1: FEE_FRAC_LAUNCH(1); break;   case 2: FEE_FRAC_LAUNCH(2); break;   case 3: FEE_FRAC_LAUNCH(3); break;
+                case 4: FEE_FRAC_LAUNCH(4); break;   case 5: FEE_FRAC_LAUNCH(5); break;   case 6: FEE_FRAC_LAUNCH(6); break;
+                case 7: FEE_FRAC_LAUNCH(7); break;   case 8: FEE_FRAC_LAUNCH(8); break;   case 9: FEE_FRAC_LAUNCH(9); break;
+                case 10: FEE_FRAC_LAUNCH(10); break; default: FEE_FRAC_LAUNCH(11); break;
+            }
+#undef FEE_FRAC_LAUNCH
             LSB_LAUNCH_CHECK("k_fee_fractions_sparse");
         } else {
             if (!pst) return lsb_fail_arg("get_adc_values: dense per-segment waveforms required for this rise time");
