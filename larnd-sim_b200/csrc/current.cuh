@@ -374,10 +374,17 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
         if (int_lo <= int_hi) { n_left = int_lo - uni_lo; right0 = int_hi + 1; }
         else { n_left = uni_hi - uni_lo + 1; right0 = uni_hi + 1; }
         int n_edge = n_left + (uni_hi - right0 + 1);
-        for (int e0 = 0; e0 < n_edge; e0 += ACC_TPB) {
-            int e = e0 + tid;
-            bool active = e < n_edge;
-            int it = e < n_left ? uni_lo + e : right0 + (e - n_left);
+        // 32 edge ticks per pass (lane = tick); the ACC_TPB/32 warps split the samples and their float64
+        // partial sums are combined in a fixed order.  Loads are branch-free (masked to offset 0) so the
+        // four of an unrolled step are in flight together.
+        constexpr int NG = ACC_TPB / 32;
+        __shared__ double s_part[NG][32];
+        const int lane = tid & 31, grp = tid >> 5;
+        for (int e0 = 0; e0 < n_edge; e0 += 32) {
+            const int e = e0 + lane;
+            const bool active = e < n_edge;
+            const int it = e < n_left ? uni_lo + e : right0 + (e - n_left);
+            const int tpos = STRIDE * it;
             double sum = 0.0;
             for (int c0 = 0; c0 < n_live; c0 += ACC_TPB) {
                 int ns = n_live - c0 < ACC_TPB ? n_live - c0 : ACC_TPB;
@@ -385,13 +392,32 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
                 if (tid < ns) s_rec[tid] = samples[soff + c0 + tid];
                 __syncthreads();
                 if (!active) continue;
-                for (int s = 0; s < ns; s++) {
-                    const SampleRec& r = s_rec[s];
+                int sidx = grp;
+                for (; sidx + 3 * NG < ns; sidx += 4 * NG) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const SampleRec& r = s_rec[sidx + u * NG];
+                        const bool ok = r.shift != SHIFT_IRREGULAR && it >= r.lo && it <= r.hi;
+                        const float x = (float)__ldg(lut + (ok ? r.rowoff + tpos + r.shift : 0));
+                        v[u] = ok ? x : 0.f;
+                    }
+                    sum += ((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3]);
+                }
+                for (; sidx < ns; sidx += NG) {
+                    const SampleRec& r = s_rec[sidx];
                     if (r.shift == SHIFT_IRREGULAR || it < r.lo || it > r.hi) continue;
-                    sum += (double)lut[(long long)r.rowoff + (long long)STRIDE * it + r.shift];
+                    sum += (double)lut[r.rowoff + tpos + r.shift];
                 }
             }
-            if (active) out[it] = __double2float_rn(charge * sum);
+            s_part[grp][lane] = sum;
+            __syncthreads();
+            if (grp == 0 && active) {
+                double tot = s_part[0][lane];
+#pragma unroll
+                for (int g = 1; g < NG; g++) tot += s_part[g][lane];
+                out[it] = __double2float_rn(charge * tot);
+            }
         }
     }
 
