@@ -211,15 +211,27 @@ __global__ void k_mc_sampler(McParams p, PairRec* __restrict__ pairs, SampleRec*
             double tl = t0 > 0 ? t0 : 0;
             double e = floor((tl - g.t_start) / TS);
             int lo = e < 0 ? 0 : (e > (double)p.T ? p.T : (int)e);
-#define LOW_OK(it) (tick_time(g.t_start, (it)) >= 0 && t0 < tick_time(g.t_start, (it)) && resp_k(tick_time(g.t_start, (it)), t0) >= 0)
+            // tick > t0 already implies k = round((tick - t0)/rs) >= 0: no division in the lower search
+#define LOW_OK(it) (tick_time(g.t_start, (it)) >= 0 && t0 < tick_time(g.t_start, (it)))
             while (lo > 0 && LOW_OK(lo - 1)) lo--;
             while (lo < p.T && !LOW_OK(lo)) lo++;
-            // upper bound: last tick with tick < t0+W and k < Rt
+            // upper bound: last tick with tick < t0+W and k < Rt.  The window test needs no division; k < Rt only
+            // bites when the table is shorter than the window, and k is monotone in the tick index.
             e = ceil((t0W - g.t_start) / TS);
             int hi = e < -1 ? -1 : (e > (double)(p.T - 1) ? p.T - 1 : (int)e);
-#define HIGH_OK(it) (tick_time(g.t_start, (it)) < t0W && resp_k(tick_time(g.t_start, (it)), t0) < p.Rt)
-            while (hi < p.T - 1 && HIGH_OK(hi + 1)) hi++;
-            while (hi >= 0 && !HIGH_OK(hi)) hi--;
+#define HIGH_T(it) (tick_time(g.t_start, (it)) < t0W)
+#define K_OK(it) (resp_k(tick_time(g.t_start, (it)), t0) < p.Rt)
+            while (hi < p.T - 1 && HIGH_T(hi + 1)) hi++;
+            while (hi >= 0 && !HIGH_T(hi)) hi--;
+            if (hi >= 0 && !K_OK(hi)) {
+                double e2 = floor((t0 + ((double)p.Rt - 0.5) * d_c.response_sampling - g.t_start) / TS) + 1.0;
+                int h2 = e2 < -1 ? -1 : (e2 > (double)hi ? hi : (int)e2);
+                while (h2 < hi && K_OK(h2 + 1)) h2++;          // safety: the estimate must not undershoot
+                hi = h2;
+                while (hi >= 0 && !K_OK(hi)) hi--;
+            }
+#undef HIGH_T
+#undef K_OK
             if (lo > hi) continue;
             int shift = SHIFT_IRREGULAR;
             if (p.stride > 0) {
@@ -236,7 +248,6 @@ __global__ void k_mc_sampler(McParams p, PairRec* __restrict__ pairs, SampleRec*
             uni_lo = lo < uni_lo ? lo : uni_lo; uni_hi = hi > uni_hi ? hi : uni_hi;
         }
 #undef LOW_OK
-#undef HIGH_OK
     sp[0] = rng.s0; sp[1] = rng.s1;
     PairRec* gp = pairs + pr;
     gp->n_live = n_live; gp->n_irregular = n_irr; gp->int_lo = int_lo; gp->int_hi = int_hi; gp->uni_lo = uni_lo; gp->uni_hi = uni_hi;
