@@ -1,0 +1,105 @@
+"""Size-independent properties of the CUDA chain at the benchmark size (BASELINE.json configs[1]: module0,
+1e4 synthetic cosmic segments) where the oracle is too slow to run in full, plus the statistical agreement
+of the production ("cloud") RNG discipline with the reference's draw pattern ("replay")."""
+import numpy as np
+import pytest
+
+import helpers as h
+from larndsim_b200 import consts as lc, synth
+from larndsim_b200 import _launch as ll
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_chain(n, seed, dense=False, rng_seed=1, config="module0", kind="cosmic"):
+    import torch
+    from larndsim_b200 import chain as lchain
+    tracks = h.production_tracks(n, config, seed, kind)
+    mod = lc.load_snapshot(config)
+    resp = synth.response_lut(mod.detector)
+    ch = lchain.Chain(tracks.dtype, resp, dense=dense)
+    dtr = ll.DeviceRecords(host=tracks)
+    res = ch.run(dtr, rng_seed=rng_seed)
+    torch.cuda.synchronize()
+    out = dict(S=res.n_segments, U=res.n_unique_pixels, T=res.n_ticks, P=res.max_neighbors, hits=res.n_hits,
+               uniq=res.unique_pix.cpu().numpy(), tpm=res.track_pixel_map.cpu().numpy(), adc=res.adc_list.cpu().numpy(),
+               digit=res.adc_digit.cpu().numpy(), ticks=res.adc_ticks_list.cpu().numpy(), cf=res.current_fractions.cpu().numpy(),
+               ps_sum=res.pixels_signals.sum(dim=1).cpu().numpy(), tracks=dtr.copy_to_host(), mod=mod,
+               sig_sum=float(res.signals.double().sum().item()))
+    ch.close()
+    return out
+
+
+def test_full_size_chain_properties(cuda):
+    a = _run_chain(10000, 12345)
+    mod = a["mod"]
+    assert a["S"] == 10000 and a["U"] > 5000 and a["hits"] > 1000
+    # sorted unique pixel list, every id a valid pixel of an existing TPC
+    assert np.all(np.diff(a["uniq"]) > 0) and a["uniq"][0] >= 0
+    assert a["uniq"][-1] < mod.detector.N_PIXELS[0] * mod.detector.N_PIXELS[1] * len(mod.detector.TPC_BORDERS)
+    # track-pixel map: rows are filled from the left, entries are distinct segment indices
+    tpm = a["tpm"]
+    filled = tpm >= 0
+    assert np.all(filled[:, :-1] >= filled[:, 1:]) and tpm.max() < a["S"] and filled[:, 0].all()
+    rows = np.sort(np.where(filled, tpm, -np.arange(1, tpm.shape[1] + 1)), axis=1)
+    assert np.all(np.diff(rows, axis=1) != 0)
+    # charge conservation: sum(I dt) over all pixels ~ drifted electrons (synthetic LUT integrates to ~1 on the pad)
+    q_tot = a["ps_sum"].sum() * mod.detector.TIME_SAMPLING
+    n_e = a["tracks"]["n_electrons"].astype(np.float64).sum()
+    assert 0.8 * n_e < q_tot < 1.3 * n_e
+    # nothing dropped by the K=50 slot limit; the per-segment total also holds what the reference computes for the -1
+    # padding ids (detsim.py:277-288, pixel (Nx-1,Ny-1) of the last TPC) and ticks beyond the readout window
+    assert abs(a["sig_sum"] - a["ps_sum"].sum()) <= 1e-4 * abs(a["sig_sum"])
+    # hits: ADC codes within range, timestamps increasing per pixel, fractions of a hit sum to 1
+    ped = h.Oracle().digitize(np.zeros(1))[0]
+    hit = a["digit"] > ped
+    assert a["digit"].min() >= 0 and a["digit"].max() <= 255 and hit.sum() == a["hits"]
+    t = np.where(hit, a["ticks"], np.inf)
+    assert np.all(np.diff(np.where(np.isfinite(t), t, 1e30), axis=1) >= 0)
+    fsum = a["cf"].sum(axis=2)[hit]
+    assert np.allclose(fsum, 1.0, atol=1e-9)
+    # reproducibility: same inputs, same seed -> identical bytes (deterministic summation order, no float atomics)
+    b = _run_chain(10000, 12345)
+    for k in ("uniq", "tpm", "adc", "digit", "ticks", "cf", "ps_sum"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["sig_sum"] == b["sig_sum"]
+
+
+def test_sparse_and_dense_paths_identical(cuda):
+    """The fused chain never materialises pixels_tracks_signals; dense=1 does (the reference's buffers).
+    Same hits, timestamps and fractions, bit for bit."""
+    a = _run_chain(1500, 99, dense=False, config="2x2", kind="beam")
+    b = _run_chain(1500, 99, dense=True, config="2x2", kind="beam")
+    for k in ("uniq", "tpm", "adc", "digit", "ticks", "cf", "ps_sum"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_cloud_vs_replay_ks(cuda):
+    """KS agreement of per-(segment,pixel) integrated charge between the production RNG discipline and the
+    reference's per-tick draw pattern (north_star parity level 3), plus agreement of the totals."""
+    from scipy.stats import ks_2samp
+    import torch
+    from larndsim_b200 import detsim, rng
+    mod = lc.load_snapshot("module0")
+    tr = h.production_tracks(160, "module0", 5)
+    orc = h.Oracle()
+    front = h.oracle_front(tr, orc)
+    resp = synth.response_lut(mod.detector)
+    S, P_ = front["neigh"].shape
+    T = front["T"]
+    q = {}
+    for mode, seed in (("cloud", 11), ("replay", 12)):
+        detsim.MC_MODE = mode
+        try:
+            sig = torch.zeros((S, P_, T), dtype=torch.float32, device="cuda")
+            detsim.tracks_current_mc[(S, P_, 31), (1, 1, 64)](sig, front["neigh"], tr, resp, rng.create_xoroshiro128p_states(S * P_, seed))
+        finally:
+            detsim.MC_MODE = "cloud"
+        q[mode] = sig.double().sum(dim=2).cpu().numpy().reshape(-1) * mod.detector.TIME_SAMPLING
+    valid = front["neigh"].reshape(-1) >= 0
+    a, b = q["cloud"][valid], q["replay"][valid]
+    assert abs(a.sum() / b.sum() - 1) < 5e-3
+    assert ks_2samp(a, b).pvalue > 0.05
+    # per pair the two estimators agree within MC noise (a few % for ~200 sample points)
+    big = np.abs(b) > 0.05 * np.abs(b).max()
+    assert np.median(np.abs(a[big] / b[big] - 1)) < 0.05
