@@ -293,6 +293,17 @@ int lsb_chain_run_host(lsb_chain* h, void* tracks_host, int64_t S, int32_t quenc
                        int32_t n_events, int32_t* unique_pix_host, double* adc_digit_host,
                        double* adc_ticks_host, int64_t U_cap, lsb_chain_result* out, void* stream);
 
+/* Pipelined form.  The handle owns a high-priority stream (front + FEE stages) and a low-priority stream
+ * (MC stage).  lsb_chain_run_async queues one batch behind the work already on `stream` and returns;
+ * lsb_chain_wait blocks until that batch is complete and fills `out` (stage_ms is not filled).  Alternate two
+ * handles to run the latency-bound FEE kernels of one batch under the MC kernels of the next. */
+int lsb_chain_run_async(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                        int32_t n_events, void* stream);
+int lsb_chain_run_host_async(lsb_chain* h, void* tracks_host, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                             int32_t n_events, int32_t* unique_pix_host, double* adc_digit_host,
+                             double* adc_ticks_host, int64_t U_cap);
+int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,51 @@ class ChainResult:
         return self._view(self._r.pixels_signals, (self.n_unique_pixels, self._Tt), np.float64)
 
 
+class Pipeline:
+    """Round-robin over `depth` chains: batch i+1 is queued while batch i is still in flight, so the
+    latency-bound FEE stage of one batch runs under the MC stage of the next (each chain has a
+    high-priority stream for front/FEE work and a low-priority one for the MC kernels)."""
+
+    def __init__(self, track_dtype, response, depth=2, **kw):
+        self.chains = [Chain(track_dtype, response, **kw) for _ in range(depth)]
+        self._inflight = []          # chains with a pending batch, oldest first
+        self._next = 0
+
+    def full(self):
+        return len(self._inflight) == len(self.chains)
+
+    def collect(self):
+        """Wait for the oldest batch in flight and return its result.  The device views of a result stay valid
+        until the chain that produced it is reused, i.e. until `depth` further submits."""
+        ch = self._inflight.pop(0)
+        return ch.wait()
+
+    def _slot(self):
+        if self.full():
+            raise RuntimeError("pipeline full: collect() a result before submitting another batch")
+        ch = self.chains[self._next]
+        self._next = (self._next + 1) % len(self.chains)
+        self._inflight.append(ch)
+        return ch
+
+    def submit(self, tracks_dev, **kw):
+        self._slot().run_async(tracks_dev, **kw)
+
+    def submit_host(self, tracks_host, unique_pix_out, adc_out, ticks_out, **kw):
+        self._slot().run_host_async(tracks_host, unique_pix_out, adc_out, ticks_out, **kw)
+
+    def drain(self):
+        out = []
+        while self._inflight:
+            out.append(self.collect())
+        return out
+
+    def close(self):
+        self.drain()
+        for ch in self.chains:
+            ch.close()
+
+
 class Chain:
     """``Chain(track_dtype, response)``; ``run(tracks_dev)`` on device records, ``run_host(tracks)``
     on a (pinned) host structured array with H2D/D2H inside the call."""
@@ -92,7 +137,7 @@ class Chain:
         self._K, self._A, self._Tt = int(self._c.max_tracks_per_pixel), int(self._c.max_adc_values), int(self._c.n_time_ticks)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _l is not None:          # `_l` is None during interpreter shutdown
             _l.lib().lsb_chain_destroy(C.c_void_p(self._h))
             self._h = None
 
@@ -106,6 +151,33 @@ class Chain:
         qm = int(self._c.mode_birks if quench_mode is None else quench_mode)
         _l.check(_l.lib().lsb_chain_run(C.c_void_p(self._h), t.c, C.c_int64(t.shape[0]), C.c_int32(qm),
                                         C.c_uint64(int(rng_seed)), C.c_int32(int(n_events)), C.byref(r), _l.stream()), "chain_run")
+        return ChainResult(r, self._K, self._A, self._Tt)
+
+    def run_async(self, tracks_dev, quench_mode=None, rng_seed=0, n_events=1):
+        """Queue one batch on this chain's own streams and return immediately; collect with :meth:`wait`."""
+        t = _l.dev(tracks_dev, name="tracks", records=True)
+        if t.dtype != self.dtype:
+            raise TypeError("tracks dtype differs from the dtype this chain was created for")
+        qm = int(self._c.mode_birks if quench_mode is None else quench_mode)
+        self._keep = t
+        _l.check(_l.lib().lsb_chain_run_async(C.c_void_p(self._h), t.c, C.c_int64(t.shape[0]), C.c_int32(qm),
+                                              C.c_uint64(int(rng_seed)), C.c_int32(int(n_events)), _l.stream()), "chain_run_async")
+
+    def run_host_async(self, tracks_host, unique_pix_out, adc_out, ticks_out, quench_mode=None, rng_seed=0, n_events=1):
+        qm = int(self._c.mode_birks if quench_mode is None else quench_mode)
+
+        def p(a):
+            return C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        n = tracks_host.shape[0] if not isinstance(tracks_host, torch.Tensor) else tracks_host.numel() // self.dtype.itemsize
+        self._keep = (tracks_host, unique_pix_out, adc_out, ticks_out)
+        _l.check(_l.lib().lsb_chain_run_host_async(C.c_void_p(self._h), p(tracks_host), C.c_int64(n), C.c_int32(qm),
+                                                   C.c_uint64(int(rng_seed)), C.c_int32(int(n_events)), p(unique_pix_out),
+                                                   p(adc_out), p(ticks_out), C.c_int64(unique_pix_out.shape[0])), "chain_run_host_async")
+
+    def wait(self):
+        r = _abi.ChainResult()
+        _l.check(_l.lib().lsb_chain_wait(C.c_void_p(self._h), C.byref(r)), "chain_wait")
+        self._keep = None
         return ChainResult(r, self._K, self._A, self._Tt)
 
     def run_host(self, tracks_host, unique_pix_out, adc_out, ticks_out, quench_mode=None, rng_seed=0, n_events=1):

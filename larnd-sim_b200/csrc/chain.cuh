@@ -30,19 +30,29 @@ struct DevBuf {
 enum { ST_QUENCH_DRIFT = 0, ST_GET_PIXELS, ST_UNIQUE, ST_TIME_INTERVALS, ST_TRACKS_CURRENT, ST_INDEX_MAPS, ST_SUM_PIXELS,
        ST_GET_ADC, ST_DIGITIZE, ST_COUNT };
 
+struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int pad; long long n_hits; };
+
 struct lsb_chain {
     lsb_consts c;
     lsb_track_layout L;
     const void* response; int Rx, Ry, Rt, f64, rng_mode, timing;
     DevBuf tracks, scal, active, neigh, nrad, npl, uniq, uniq_ws, starts, signals, mc_ws, pim, tpm, psig, pts, oflow, tticks,
            integral, adc_digit, adc_ticks, cf, thr, rng, nhits, sx_slot, sx_counts, sx_cursor, sx_raw, sx_offs, sx_bsums, sx_sorted;
+    DevBuf arena_buf; TmpArena arena;
     int dense;                // 1: materialise pixels_tracks_signals like the reference (parity / debugging)
     long long n_rng;
     int tticks_n; long long tticks_events;
     cudaEvent_t ev[ST_COUNT + 1];
+    // pipelined (asynchronous) operation: front + FEE stages on a high-priority stream, the MC stage on a
+    // low-priority one, so the latency-bound FEE kernels of one batch run under the L1-bound MC kernels of the
+    // next batch (issued through a second chain handle)
+    cudaStream_t hp, lp;
+    cudaEvent_t ev_in, ev_front, ev_mc, ev_done;
+    ChainScalars* hs_pinned;
+    lsb_chain_result pending;
+    int pending_valid;
 };
 
-struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int pad; long long n_hits; };
 
 __global__ void k_chain_max_tran(Layout L, const char* __restrict__ tracks, long long n, unsigned long long* __restrict__ out) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -75,6 +85,19 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     h->c = *c; h->L = *L; h->response = response; h->Rx = Rx; h->Ry = Ry; h->Rt = Rt; h->f64 = response_f64;
     h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->dense = 0; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // non-blocking: no implicit synchronisation with the legacy default stream (torch / numba / cupy work there)
+    cudaStreamCreateWithPriority(&h->hp, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&h->lp, cudaStreamNonBlocking, prio_lo);
+    cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_mc, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+    h->hs_pinned = nullptr;
+    cudaMallocHost((void**)&h->hs_pinned, sizeof(ChainScalars));
+    h->pending_valid = 0;
+    h->arena.base = nullptr; h->arena.cap = h->arena.off = h->arena.high_water = h->arena.overflow = 0;
     return h;
 }
 LSB_EXPORT int lsb_chain_set_dense(lsb_chain* h, int32_t dense) {
@@ -87,9 +110,13 @@ LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
     DevBuf* all[] = {&h->tracks, &h->scal, &h->active, &h->neigh, &h->nrad, &h->npl, &h->uniq, &h->uniq_ws, &h->starts, &h->signals,
                      &h->mc_ws, &h->pim, &h->tpm, &h->psig, &h->pts, &h->oflow, &h->tticks, &h->integral, &h->adc_digit,
                      &h->adc_ticks, &h->cf, &h->thr, &h->rng, &h->nhits, &h->sx_slot, &h->sx_counts, &h->sx_cursor, &h->sx_raw,
-                     &h->sx_offs, &h->sx_bsums, &h->sx_sorted};
+                     &h->sx_offs, &h->sx_bsums, &h->sx_sorted, &h->arena_buf};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamSynchronize(h->hp); cudaStreamSynchronize(h->lp);
+    cudaStreamDestroy(h->hp); cudaStreamDestroy(h->lp);
+    cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_front); cudaEventDestroy(h->ev_mc); cudaEventDestroy(h->ev_done);
+    if (h->hs_pinned) cudaFreeHost(h->hs_pinned);
     delete h;
 }
 
@@ -117,10 +144,11 @@ static int chain_grow_rng(lsb_chain* h, long long n, uint64_t seed, cudaStream_t
 
 #define CH_STAGE(i) do { if (h->timing) cudaEventRecord(h->ev[i], st); } while (0)
 
-LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
-                             int32_t n_events, lsb_chain_result* out, void* stream) {
+// Enqueue one batch.  `st` = stream of the front and FEE stages, `st_mc` = stream of the MC stage (may be the
+// same).  Returns with everything queued; the hit count arrives in h->hs_pinned once `st` has drained.
+static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                         int32_t n_events, lsb_chain_result* out, cudaStream_t st, cudaStream_t st_mc) {
     LSB_REQUIRE(h && out && (tracks_dev || S == 0), "chain_run: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
     const lsb_consts* c = &h->c;
     const lsb_track_layout* L = &h->L;
     memset(out, 0, sizeof(*out));
@@ -180,11 +208,13 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
     CH_STAGE(4);
     // ---- tracks_current_mc (:1007-1016) -------------------------------------------------
     if ((rc = h->signals.need((size_t)S * P * T * 4))) return rc;
-    LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
     long long need_rng = S * P;
     long long need_rng2 = 128LL * ((U + 127) / 128);
     if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
+    if (st_mc != st) { LSB_CUDA(cudaEventRecord(h->ev_front, st)); LSB_CUDA(cudaStreamWaitEvent(st_mc, h->ev_front, 0)); }
     {
+        cudaStream_t st = st_mc;                                   // MC stage
+        LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
         // sample workspace: MIN_STEP_SIZE bounds the samples of a (segment,pixel); start from a typical
         // figure and let the kernel split the batch if it does not fit
         long long guess = S * 4000LL;
@@ -195,7 +225,23 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
                                         h->mc_ws.p, (int64_t)h->mc_ws.cap, st))) return rc;
         out->n_samples = lsb_tracks_current_mc_last_samples();
     }
-    CH_STAGE(5);
+    if (st_mc != st) LSB_CUDA(cudaEventRecord(h->ev_mc, st_mc));
+    else CH_STAGE(5);
+    // temporaries of the remaining stages (all queued on `st`) come from this handle's arena
+    struct ArenaScope {
+        lsb_chain* h; TmpArena* prev;
+        ArenaScope(lsb_chain* hh, size_t want_bytes) : h(hh), prev(g_lsb_arena) {
+            if (h->arena.overflow) {                        // last batch did not fit: grow (synchronises, warm-up only)
+                size_t want = h->arena.high_water + h->arena.overflow + (64u << 20);
+                h->arena_buf.need(want);
+                h->arena.overflow = 0;
+            }
+            if (want_bytes > h->arena_buf.cap) h->arena_buf.need(want_bytes);
+            h->arena.base = (char*)h->arena_buf.p; h->arena.cap = h->arena_buf.cap; h->arena.off = 0;
+            g_lsb_arena = h->arena.base ? &h->arena : nullptr;
+        }
+        ~ArenaScope() { g_lsb_arena = prev; }
+    } arena_scope(h, fee_scratch_bytes(c, U, Tt, A, S * P) + (size_t)S * P * 24 + (size_t)U * 32 + (16u << 20));
     // ---- pixel_index_map (:1021-1025), track_pixel_map (:1031-1042) ---------------------
     if ((rc = h->pim.need((size_t)S * P * 8)) || (rc = h->tpm.need((size_t)U * K * 8))) return rc;
     if ((rc = lsb_pixel_index_map((const int32_t*)h->neigh.p, S * P, max_id, h->uniq_ws.p, (int64_t*)h->pim.p, st))) return rc;
@@ -223,6 +269,7 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
         if ((rc = lsb_upload_consts(c, st))) return rc;
         if ((rc = sum_build_entries(sx, U, S, (int)P, (const double*)h->starts.p, (const long long*)h->pim.p, (const long long*)h->tpm.p, K,
                                     (double*)h->oflow.p, st))) return rc;
+        if (st_mc != st) LSB_CUDA(cudaStreamWaitEvent(st, h->ev_mc, 0));
         if ((rc = sum_run(sx, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, (int)T, K, h->dense ? (double*)h->pts.p : nullptr, st))) return rc;
     }
     CH_STAGE(7);
@@ -269,15 +316,57 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
         LSB_LAUNCH_CHECK("k_count_hits");
     }
     CH_STAGE(9);
-    LSB_CUDA(cudaMemcpyAsync(&hs, d_s, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    LSB_CUDA(cudaStreamSynchronize(st));
-    out->n_hits = hs.n_hits;
+    LSB_CUDA(cudaMemcpyAsync(h->hs_pinned, d_s, sizeof(ChainScalars), cudaMemcpyDeviceToHost, st));
     out->unique_pix = (const int32_t*)h->uniq.p; out->track_pixel_map = (const int64_t*)h->tpm.p;
     out->adc_list = (const double*)h->integral.p; out->adc_digit = (const double*)h->adc_digit.p;
     out->adc_ticks_list = (const double*)h->adc_ticks.p; out->current_fractions = (const double*)h->cf.p;
     out->signals = (const float*)h->signals.p; out->pixels_signals = (const double*)h->psig.p;
-    if (h->timing)
+    return 0;
+}
+// after `st` has drained: hit count, stage times
+static void chain_finish(lsb_chain* h, lsb_chain_result* out, bool with_timing) {
+    if (out->unique_pix) out->n_hits = h->hs_pinned->n_hits;
+    if (h->timing && with_timing && out->unique_pix)
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) out->stage_ms[i] = ms; }
+}
+
+LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                             int32_t n_events, lsb_chain_result* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = chain_enqueue(h, tracks_dev, S, quench_mode, rng_seed, n_events, out, st, st);
+    if (rc) return rc;
+    LSB_CUDA(cudaStreamSynchronize(st));
+    chain_finish(h, out, true);
+    return 0;
+}
+
+// Pipelined form: returns as soon as the batch is queued on the handle's own streams (ordered after the work
+// already queued on `stream`); lsb_chain_wait blocks until it is complete and returns the result.  Use two
+// handles alternately to overlap the FEE stage of one batch with the MC stage of the next.
+LSB_EXPORT int lsb_chain_run_async(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                                   int32_t n_events, void* stream) {
+    LSB_REQUIRE(h, "chain_run_async: null handle");
+    LSB_REQUIRE(!h->pending_valid, "chain_run_async: previous batch not collected (call lsb_chain_wait)");
+    // order this batch after the work already queued on the caller's stream (e.g. the upload of `tracks_dev`);
+    // an idle caller stream needs no dependency
+    if (cudaStreamQuery((cudaStream_t)stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        LSB_CUDA(cudaEventRecord(h->ev_in, (cudaStream_t)stream));
+        LSB_CUDA(cudaStreamWaitEvent(h->hp, h->ev_in, 0));
+    }
+    int rc = chain_enqueue(h, tracks_dev, S, quench_mode, rng_seed, n_events, &h->pending, h->hp, h->lp);
+    if (rc) return rc;
+    LSB_CUDA(cudaEventRecord(h->ev_done, h->hp));
+    h->pending_valid = 1;
+    return 0;
+}
+LSB_EXPORT int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out) {
+    LSB_REQUIRE(h && out, "chain_wait: null pointer");
+    LSB_REQUIRE(h->pending_valid, "chain_wait: nothing pending");
+    LSB_CUDA(cudaEventSynchronize(h->ev_done));
+    chain_finish(h, &h->pending, false);
+    *out = h->pending;
+    h->pending_valid = 0;
     return 0;
 }
 
@@ -301,5 +390,31 @@ LSB_EXPORT int lsb_chain_run_host(lsb_chain* h, void* tracks_host, int64_t S, in
         if (adc_ticks_host) LSB_CUDA(cudaMemcpyAsync(adc_ticks_host, out->adc_ticks_list, (size_t)U * A * 8, cudaMemcpyDeviceToHost, st));
     }
     LSB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// pipelined host-buffer form: H2D, chain and D2H are queued on the handle's streams; collect with lsb_chain_wait
+LSB_EXPORT int lsb_chain_run_host_async(lsb_chain* h, void* tracks_host, int64_t S, int32_t quench_mode, uint64_t rng_seed,
+                                        int32_t n_events, int32_t* unique_pix_host, double* adc_digit_host,
+                                        double* adc_ticks_host, int64_t U_cap) {
+    LSB_REQUIRE(h && (tracks_host || S == 0), "chain_run_host_async: null pointer");
+    LSB_REQUIRE(!h->pending_valid, "chain_run_host_async: previous batch not collected (call lsb_chain_wait)");
+    cudaStream_t st = h->hp;
+    size_t bytes = (size_t)S * h->L.itemsize;
+    int rc;
+    if ((rc = h->tracks.need(bytes ? bytes : 1))) return rc;
+    if (S) LSB_CUDA(cudaMemcpyAsync(h->tracks.p, tracks_host, bytes, cudaMemcpyHostToDevice, st));
+    lsb_chain_result* out = &h->pending;
+    if ((rc = chain_enqueue(h, h->tracks.p, S, quench_mode, rng_seed, n_events, out, st, h->lp))) return rc;
+    if (S) LSB_CUDA(cudaMemcpyAsync(tracks_host, h->tracks.p, bytes, cudaMemcpyDeviceToHost, st));
+    const long long U = out->n_unique_pixels, A = h->c.max_adc_values;
+    if (U > 0 && out->unique_pix) {
+        LSB_REQUIRE(U <= U_cap, "chain_run_host_async: U_cap too small");
+        if (unique_pix_host) LSB_CUDA(cudaMemcpyAsync(unique_pix_host, out->unique_pix, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+        if (adc_digit_host) LSB_CUDA(cudaMemcpyAsync(adc_digit_host, out->adc_digit, (size_t)U * A * 8, cudaMemcpyDeviceToHost, st));
+        if (adc_ticks_host) LSB_CUDA(cudaMemcpyAsync(adc_ticks_host, out->adc_ticks_list, (size_t)U * A * 8, cudaMemcpyDeviceToHost, st));
+    }
+    LSB_CUDA(cudaEventRecord(h->ev_done, st));
+    h->pending_valid = 1;
     return 0;
 }

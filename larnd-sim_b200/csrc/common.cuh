@@ -168,19 +168,40 @@ __device__ __forceinline__ float rng_normal_f32(Rng& r) {
 // so steady-state calls do not reach the driver).  Freed when the guard leaves scope.
 // ---------------------------------------------------------------------------------------
 void lsb_pool_init_once();
+// A caller (the fused chain) may lend a pre-allocated device arena: temporaries are then carved from it with
+// stack discipline (all users of one arena queue their work on ONE stream, so reuse is stream-ordered) and
+// no allocator is involved at all; requests that do not fit fall back to the pool and are remembered so the
+// owner can grow the arena for the next batch.
+struct TmpArena { char* base; size_t cap, off, high_water, overflow; };
+extern TmpArena* g_lsb_arena;
 struct TmpPool {
     cudaStream_t st;
     void* ptrs[24];
     int n;
-    explicit TmpPool(cudaStream_t s) : st(s), n(0) { lsb_pool_init_once(); }
+    TmpArena* arena;
+    size_t arena_mark;
+    explicit TmpPool(cudaStream_t s) : st(s), n(0), arena(g_lsb_arena), arena_mark(g_lsb_arena ? g_lsb_arena->off : 0) { lsb_pool_init_once(); }
     template <typename T>
     cudaError_t get(T** p, long long count) {
         *p = nullptr;
-        if (n >= 24) return cudaErrorMemoryAllocation;
         size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+        if (arena) {
+            size_t need = (bytes + 255) & ~(size_t)255;
+            if (arena->off + need <= arena->cap) {
+                *p = (T*)(arena->base + arena->off);
+                arena->off += need;
+                if (arena->off > arena->high_water) arena->high_water = arena->off;
+                return cudaSuccess;
+            }
+            arena->overflow += need;
+        }
+        if (n >= 24) return cudaErrorMemoryAllocation;
         cudaError_t e = cudaMallocAsync((void**)p, bytes, st);
         if (e == cudaSuccess) ptrs[n++] = (void*)*p;
         return e;
     }
-    ~TmpPool() { for (int i = n - 1; i >= 0; i--) cudaFreeAsync(ptrs[i], st); }
+    ~TmpPool() {
+        for (int i = n - 1; i >= 0; i--) cudaFreeAsync(ptrs[i], st);
+        if (arena) arena->off = arena_mark;
+    }
 };

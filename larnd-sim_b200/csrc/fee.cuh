@@ -420,6 +420,20 @@ static int fee_params(const lsb_consts* c, FeeParams& fp, double* w_host) {
     return 0;
 }
 
+// provision of normals per pixel for one call (see k_fee_rng_uniforms) and the bytes of temporaries fee_run needs
+static long long fee_nmax(const FeeParams& fp, int Tt, int A) {
+    const long long iters = (long long)Tt + fp.busy_ticks + 2;
+    long long nmax = 1 + 2 * iters + 3 * (iters / (fp.interval + 1) + A + 2) + 8;
+    return (nmax + FEE_SNAP - 1) / FEE_SNAP * FEE_SNAP;
+}
+static size_t fee_scratch_bytes(const lsb_consts* c, long long U, int Tt, int A, long long n_entries) {
+    FeeParams fp; double w[FEE_MAX_TAPS];
+    if (fee_params(c, fp, w)) return 0;
+    const long long nmax = fee_nmax(fp, Tt, A);
+    return (size_t)U * ((size_t)nmax * 12 + (size_t)(Tt + fp.n_taps) * 8 + (size_t)(A + 1) * sizeof(FeeWindow) + 4 +
+                        16 * (size_t)(nmax / FEE_SNAP + 1)) + (size_t)n_entries * 4 + 16 * 256;
+}
+
 // sparse context: the (pixel, slot) entries of sum_pixel_signals and the per-segment waveforms
 struct FeeSparse { const float* signals; int T; const long long* offs; const int* counts; const SumEntry* sorted; long long n_entries_cap; };
 
@@ -437,9 +451,7 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
     LSB_CUDA(tp.get(&n_windows, U));
     {
         // provision of pre-computed noise / FIR values per pixel (see k_fee_rng_uniforms)
-        const long long iters = (long long)Tt + fp.busy_ticks + 2;
-        long long nmax = 1 + 2 * iters + 3 * (iters / (fp.interval + 1) + A + 2) + 8;
-        nmax = (nmax + FEE_SNAP - 1) / FEE_SNAP * FEE_SNAP;
+        const long long nmax = fee_nmax(fp, Tt, A);
         const int Tq = Tt + fp.n_taps;
         const double pre_bytes = (double)U * ((double)nmax * 12.0 + (double)Tq * 8.0);
         FeePre pre; pre.q_pre = nullptr; pre.Tq = Tq; pre.nrm = nullptr; pre.snaps = nullptr; pre.NMAX = (int)nmax;

@@ -23,6 +23,8 @@ int lsb_upload_consts(const lsb_consts* c, cudaStream_t st) {
     return 0;
 }
 
+TmpArena* g_lsb_arena = nullptr;
+
 void lsb_pool_init_once() {
     static bool done = false;
     if (done) return;

@@ -291,3 +291,56 @@ def test_chain_vs_oracle(cuda, config, kind, n):
         assert r["adc_list_equal"] if not noise else r["adc_list_relerr"] < 1e-7
         assert r["adc_mismatch"] == 0 and r["n_hits"] == r["n_hits_oracle"] and r["n_hits"] > 0
         assert r["launches"] > 10
+
+
+def test_light_chain_medium_vs_oracle(cuda):
+    """Light chain on 300 cosmic segments, 24 channels, ~1.2k ticks, 9000-tap windows shortened to 400 taps so the
+    single-threaded oracle finishes in seconds: bit-exact float32 waveforms (reference add order)."""
+    from larndsim_b200 import quenching, drifting, lightLUT, light_sim, rng
+    mod = lc.load_snapshot("module0")
+    li = mod.light
+    li.ENABLE_LUT_SMEARING = True
+    li.LIGHT_WINDOW = (0.1, 0.5)
+    li.LIGHT_TICK_SIZE = 0.001
+    tr = _tracks(300, "module0", seed=8)
+    tr["t0"] = np.random.default_rng(3).uniform(0, 0.4, len(tr))
+    tr["t0_start"] = tr["t0"]; tr["t0_end"] = tr["t0"]
+    orc = h.Oracle()
+    orc.quench(tr, 2); orc.drift(tr)
+    lut = synth.light_lut((14, 26, 8, 48), 16)
+    ol = h.OracleLight()
+    ndet = int(li.N_OP_CHANNEL)
+    eff = np.asarray(li.OP_CHANNEL_EFFICIENCY, dtype=np.float64)
+    tpc = np.asarray(li.OP_CHANNEL_TO_TPC, dtype=np.int64)
+    linc_ref, vox_ref = ol.light_incidence(tr, lut, ndet, eff, tpc)
+    linc = np.zeros_like(linc_ref); vox = np.zeros_like(vox_ref)
+    lightLUT.calculate_light_incidence[2, 256](tr, lut, linc, vox)
+    assert np.array_equal(vox, vox_ref) and np.array_equal(linc["n_photons_det"], linc_ref["n_photons_det"])
+    assert np.array_equal(linc["t0_det"], linc_ref["t0_det"])
+    op_channel = np.arange(0, 96, 4, dtype=np.int32)
+    nd, nticks = len(op_channel), 1200
+    sorted_idx = np.stack([np.argsort(linc["n_photons_det"][:, ch], kind="stable")[::-1] for ch in op_channel]).astype(np.int64)
+    seg_ids = np.arange(len(tr), dtype=np.int64)
+    empty_i = np.zeros((nd, nticks, 0), dtype=np.int64); empty_f = np.zeros((nd, nticks, 0))
+    ref_inc, _, _ = ol.sum_light_signals(tr, vox, seg_ids, linc, op_channel, lut, -0.1, nticks, 0, sorted_idx, 16)
+    inc = np.zeros((nd, nticks), dtype=np.float32)
+    light_sim.sum_light_signals[(nd, 19), (1, 64)](tr, vox, seg_ids, linc, op_channel, lut, -0.1, inc, empty_i, empty_f, sorted_idx, 16.0)
+    assert (ref_inc != 0).sum() > 500 and np.array_equal(inc, ref_inc)
+    ref_sc, _, _ = ol.scintillation(ref_inc, empty_i, empty_f)
+    sc = np.zeros_like(inc)
+    light_sim.calc_scintillation_effect[(nd, 19), (1, 64)](inc, empty_i, empty_f, sc, empty_i.copy(), empty_f.copy())
+    assert np.array_equal(sc, ref_sc)
+    st = h.rng_states(nd * nticks, 5)
+    ref_disc = ol.stat_fluctuations(ref_sc, st)
+    disc = np.zeros_like(inc)
+    states = rng.create_xoroshiro128p_states(nd * nticks, 5)
+    light_sim.calc_stat_fluctuations[(nd, 19), (1, 64)](sc, disc, states)
+    # Poisson counts are integers: identical unless the float32 uniform lands within an ulp of a CDF step,
+    # or (mean >= 30) the Gaussian branch truncates a float32 normal that differs in the last bit
+    assert (disc != ref_disc).mean() < 1e-4
+    assert np.array_equal(states.copy_to_host().view(np.uint64).reshape(-1, 2), st)
+    gain = np.asarray(li.LIGHT_GAIN, dtype=np.float64).reshape(-1)
+    ref_resp, _, _ = ol.detector_response(ref_disc, empty_i, empty_f, gain, np.asarray(li.IMPULSE_MODEL, dtype=np.float64))
+    resp = np.zeros_like(inc)
+    light_sim.calc_light_detector_response[(nd, 19), (1, 64)](ref_disc, empty_i, empty_f, resp, empty_i.copy(), empty_f.copy())
+    assert np.array_equal(resp, ref_resp)
