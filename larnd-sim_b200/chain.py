@@ -21,6 +21,8 @@ class ChainResult:
         self.max_active, self.max_neighbors, self.n_ticks = int(r.max_active), int(r.max_neighbors), int(r.n_ticks)
         self.n_hits, self.n_samples = int(r.n_hits), int(r.n_samples)
         self.stage_ms = {STAGES[i]: float(r.stage_ms[i]) for i in range(len(STAGES))}
+        #: async batches: ms since the library's reference event of (front begin, front end, MC begin, MC end, FEE begin, done)
+        self.timeline = [float(r.stage_ms[i]) for i in range(6)]
         self._r, self._K, self._A, self._Tt = r, K, A, Tt
 
     def _view(self, ptr, shape, np_dtype):

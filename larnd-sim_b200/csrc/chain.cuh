@@ -30,7 +30,8 @@ struct DevBuf {
 enum { ST_QUENCH_DRIFT = 0, ST_GET_PIXELS, ST_UNIQUE, ST_TIME_INTERVALS, ST_TRACKS_CURRENT, ST_INDEX_MAPS, ST_SUM_PIXELS,
        ST_GET_ADC, ST_DIGITIZE, ST_COUNT };
 
-struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int pad; long long n_hits; };
+struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int mc_overflow;
+                      long long n_hits; double sum_len; long long mc_total; };
 
 struct lsb_chain {
     lsb_consts c;
@@ -48,19 +49,34 @@ struct lsb_chain {
     // next batch (issued through a second chain handle)
     cudaStream_t hp, lp;
     cudaEvent_t ev_in, ev_front, ev_mc, ev_done;
+    cudaEvent_t tl[6];        // timeline of the last async batch: front begin/end, MC begin/end, FEE begin, done
     ChainScalars* hs_pinned;
     lsb_chain_result pending;
     int pending_valid;
 };
 
 
-__global__ void k_chain_max_tran(Layout L, const char* __restrict__ tracks, long long n, unsigned long long* __restrict__ out) {
+// max(tran_diff) (-> neighbour radius) and the summed 3-D segment length (-> upper bound of the MC sample count:
+// every (segment,pixel) takes at most len/MIN_STEP_SIZE + 1 steps, detsim.py:319)
+__global__ void k_chain_max_tran(Layout L, const char* __restrict__ tracks, long long n, unsigned long long* __restrict__ out,
+                                 double* __restrict__ sum_len) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    double v = 0.0;
-    if (i < n) { double t = fld_get(L, tracks + i * L.itemsize, LSB_F_TRAN_DIFF); if (t > v) v = t; }   // NaN/negatives ignored
+    double v = 0.0, len = 0.0;
+    if (i < n) {
+        const char* t = tracks + i * L.itemsize;
+        double td = fld_get(L, t, LSB_F_TRAN_DIFF); if (td > v) v = td;   // NaN/negatives ignored
+        double dx = fld_get(L, t, LSB_F_X_END) - fld_get(L, t, LSB_F_X_START);
+        double dy = fld_get(L, t, LSB_F_Y_END) - fld_get(L, t, LSB_F_Y_START);
+        double dz = fld_get(L, t, LSB_F_Z_END) - fld_get(L, t, LSB_F_Z_START);
+        len = sqrt(dx * dx + dy * dy + dz * dz);
+        if (!(len >= 0.0) || len > 1e30) len = 1e30;                     // NaN / inf: force the synchronous path
+    }
     unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, b, o); b = w > b ? w : b; }
-    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, b, o); b = w > b ? w : b;
+        len += __shfl_xor_sync(0xffffffffu, len, o);
+    }
+    if ((threadIdx.x & 31) == 0) { if (b) atomicMax(out, b); atomicAdd(sum_len, len); }
 }
 __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 __global__ void k_fill_i64(long long* p, long long n, long long v) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
@@ -89,11 +105,16 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     // non-blocking: no implicit synchronisation with the legacy default stream (torch / numba / cupy work there)
     cudaStreamCreateWithPriority(&h->hp, cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&h->lp, cudaStreamNonBlocking, prio_lo);
+    // ONE low-priority stream for the MC stage of every handle: MC stages of different batches must run back to
+    // back, not interleaved (they are L1/L2-bound and would evict each other's LUT lines)
+    static cudaStream_t s_mc_stream = nullptr;
+    if (!s_mc_stream) cudaStreamCreateWithPriority(&s_mc_stream, cudaStreamNonBlocking, prio_lo);
+    h->lp = s_mc_stream;
     cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_mc, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+    for (int i = 0; i < 6; i++) cudaEventCreate(&h->tl[i]);
     h->hs_pinned = nullptr;
     cudaMallocHost((void**)&h->hs_pinned, sizeof(ChainScalars));
     h->pending_valid = 0;
@@ -114,13 +135,15 @@ LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
     for (DevBuf* b : all) b->release();
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamSynchronize(h->hp); cudaStreamSynchronize(h->lp);
-    cudaStreamDestroy(h->hp); cudaStreamDestroy(h->lp);
+    cudaStreamDestroy(h->hp);          // h->lp is shared by all handles
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_front); cudaEventDestroy(h->ev_mc); cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < 6; i++) cudaEventDestroy(h->tl[i]);
     if (h->hs_pinned) cudaFreeHost(h->hs_pinned);
     delete h;
 }
 
 int lsb_rng_create_states_host_impl(uint64_t* states, int64_t n, uint64_t seed, uint64_t subsequence_start);
+cudaEvent_t lsb_reference_event();
 
 // cli/simulate_pixels.py:92-104 maybe_create_rng_states: keep evolved states, append fresh ones
 static int chain_grow_rng(lsb_chain* h, long long n, uint64_t seed, cudaStream_t st) {
@@ -161,17 +184,20 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     ChainScalars hs;
     LSB_CUDA(cudaMemsetAsync(d_s, 0, sizeof(ChainScalars), st));
     CH_STAGE(0);
+    if (st_mc != st) cudaEventRecord(h->tl[0], st);
     // ---- quench, drift (simulate_pixels.py:732,742) -------------------------------------
     if ((rc = lsb_quench(c, L, tracks_dev, S, quench_mode, st))) return rc;
     if ((rc = lsb_drift(c, L, tracks_dev, S, st))) return rc;
     CH_STAGE(1);
     // ---- max_radius, max_pixels (:918-928) ----------------------------------------------
-    k_chain_max_tran<<<lsb_blocks(S, 256), 256, 0, st>>>(make_layout(L), (const char*)tracks_dev, S, &d_s->max_tran_bits);
+    k_chain_max_tran<<<lsb_blocks(S, 256), 256, 0, st>>>(make_layout(L), (const char*)tracks_dev, S, &d_s->max_tran_bits, &d_s->sum_len);
     LSB_LAUNCH_CHECK("k_chain_max_tran");
     if ((rc = lsb_max_pixels(c, L, tracks_dev, S, (int64_t*)&d_s->max_pixels, st))) return rc;
     LSB_CUDA(cudaMemcpyAsync(&hs, d_s, sizeof(hs), cudaMemcpyDeviceToHost, st));
     LSB_CUDA(cudaStreamSynchronize(st));
     double max_tran; memcpy(&max_tran, &hs.max_tran_bits, 8);
+    const double sum_len = hs.sum_len;
+    long long mc_total_host = -1;
     const int radius = (int)ceil(max_tran * 5 / c->pixel_pitch);
     const long long maxpix = hs.max_pixels;
     const long long P = (2LL * radius + 1) * maxpix + (1 + 2LL * radius) * radius * 2;
@@ -211,21 +237,56 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     long long need_rng = S * P;
     long long need_rng2 = 128LL * ((U + 127) / 128);
     if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
-    if (st_mc != st) { LSB_CUDA(cudaEventRecord(h->ev_front, st)); LSB_CUDA(cudaStreamWaitEvent(st_mc, h->ev_front, 0)); }
+    if (st_mc != st) { LSB_CUDA(cudaEventRecord(h->ev_front, st)); LSB_CUDA(cudaStreamWaitEvent(st_mc, h->ev_front, 0)); cudaEventRecord(h->tl[1], st); cudaEventRecord(h->tl[2], st_mc); }
+    if (st_mc != st) {
+        // The MC kernels re-read the response table (15.8 MB) ~2000 times per batch and need it L2-resident,
+        // while the FEE stage of the previous batch streams GBs through L2 at the same time: pin the table
+        // with a persisting access-policy window on the MC stream.
+        static size_t persist_max = (size_t)-1;
+        if (persist_max == (size_t)-1) {
+            int dev = 0; cudaGetDevice(&dev);
+            cudaDeviceProp prop; persist_max = 0;
+            if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) persist_max = (size_t)prop.persistingL2CacheMaxSize;
+            if (persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_max);
+            (void)cudaGetLastError();
+        }
+        const size_t lut_bytes = (size_t)h->Rx * h->Ry * h->Rt * (h->f64 ? 8 : 4);
+        if (persist_max) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = const_cast<void*>(h->response);
+            attr.accessPolicyWindow.num_bytes = lut_bytes;
+            attr.accessPolicyWindow.hitRatio = lut_bytes <= persist_max ? 1.0f : (float)((double)persist_max / (double)lut_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(st_mc, cudaStreamAttributeAccessPolicyWindow, &attr);
+            (void)cudaGetLastError();
+        }
+    }
     {
         cudaStream_t st = st_mc;                                   // MC stage
         LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
-        // sample workspace: MIN_STEP_SIZE bounds the samples of a (segment,pixel); start from a typical
-        // figure and let the kernel split the batch if it does not fit
-        long long guess = S * 4000LL;
-        long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, guess);
-        if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
-        if ((rc = lsb_tracks_current_mc(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
-                                        h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, h->n_rng, S, h->rng_mode,
-                                        h->mc_ws.p, (int64_t)h->mc_ws.cap, st))) return rc;
-        out->n_samples = lsb_tracks_current_mc_last_samples();
+        // sample workspace from an upper bound of the sample count (no host round trip inside the MC stage):
+        // every (segment,pixel) takes at most len/MIN_STEP_SIZE + 1 steps
+        const double bound_d = (sum_len / c->min_step_size + (double)S) * (double)P * (double)c->mc_sample_multiplier * 1.001 + 1024.0;
+        if (h->rng_mode == 0 && bound_d < 4e9) {
+            long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, (long long)bound_d);
+            if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
+            if ((rc = mc_run_nosync(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
+                                    h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, S, h->mc_ws.p,
+                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, st))) return rc;
+        } else {
+            long long guess = S * 4000LL;
+            long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, guess);
+            if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
+            if ((rc = lsb_tracks_current_mc(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
+                                            h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, h->n_rng, S, h->rng_mode,
+                                            h->mc_ws.p, (int64_t)h->mc_ws.cap, st))) return rc;
+            mc_total_host = lsb_tracks_current_mc_last_samples();
+        }
+        out->n_samples = mc_total_host;
     }
-    if (st_mc != st) LSB_CUDA(cudaEventRecord(h->ev_mc, st_mc));
+    if (st_mc != st) { LSB_CUDA(cudaEventRecord(h->ev_mc, st_mc)); cudaEventRecord(h->tl[3], st_mc); }
     else CH_STAGE(5);
     // temporaries of the remaining stages (all queued on `st`) come from this handle's arena
     struct ArenaScope {
@@ -269,7 +330,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
         if ((rc = lsb_upload_consts(c, st))) return rc;
         if ((rc = sum_build_entries(sx, U, S, (int)P, (const double*)h->starts.p, (const long long*)h->pim.p, (const long long*)h->tpm.p, K,
                                     (double*)h->oflow.p, st))) return rc;
-        if (st_mc != st) LSB_CUDA(cudaStreamWaitEvent(st, h->ev_mc, 0));
+        if (st_mc != st) { LSB_CUDA(cudaStreamWaitEvent(st, h->ev_mc, 0)); cudaEventRecord(h->tl[4], st); }
         if ((rc = sum_run(sx, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, (int)T, K, h->dense ? (double*)h->pts.p : nullptr, st))) return rc;
     }
     CH_STAGE(7);
@@ -317,6 +378,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     }
     CH_STAGE(9);
     LSB_CUDA(cudaMemcpyAsync(h->hs_pinned, d_s, sizeof(ChainScalars), cudaMemcpyDeviceToHost, st));
+    if (st_mc != st) cudaEventRecord(h->tl[5], st);
     out->unique_pix = (const int32_t*)h->uniq.p; out->track_pixel_map = (const int64_t*)h->tpm.p;
     out->adc_list = (const double*)h->integral.p; out->adc_digit = (const double*)h->adc_digit.p;
     out->adc_ticks_list = (const double*)h->adc_ticks.p; out->current_fractions = (const double*)h->cf.p;
@@ -325,7 +387,10 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
 }
 // after `st` has drained: hit count, stage times
 static void chain_finish(lsb_chain* h, lsb_chain_result* out, bool with_timing) {
-    if (out->unique_pix) out->n_hits = h->hs_pinned->n_hits;
+    if (out->unique_pix) {
+        out->n_hits = h->hs_pinned->n_hits;
+        if (out->n_samples < 0) out->n_samples = h->hs_pinned->mc_total;
+    }
     if (h->timing && with_timing && out->unique_pix)
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) out->stage_ms[i] = ms; }
 }
@@ -337,6 +402,7 @@ LSB_EXPORT int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t 
     if (rc) return rc;
     LSB_CUDA(cudaStreamSynchronize(st));
     chain_finish(h, out, true);
+    LSB_REQUIRE(!(out->unique_pix && h->hs_pinned->mc_overflow), "chain_run: MC sample bound exceeded (internal error)");
     return 0;
 }
 
@@ -365,8 +431,13 @@ LSB_EXPORT int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out) {
     LSB_REQUIRE(h->pending_valid, "chain_wait: nothing pending");
     LSB_CUDA(cudaEventSynchronize(h->ev_done));
     chain_finish(h, &h->pending, false);
+    if (h->pending.unique_pix) {
+        // timeline of this batch in ms since the library's reference event: front begin/end, MC begin/end, FEE begin, done
+        for (int i = 0; i < 6; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, lsb_reference_event(), h->tl[i]) == cudaSuccess) h->pending.stage_ms[i] = ms; }
+    }
     *out = h->pending;
     h->pending_valid = 0;
+    LSB_REQUIRE(!(out->unique_pix && h->hs_pinned->mc_overflow), "chain_wait: MC sample bound exceeded (internal error)");
     return 0;
 }
 

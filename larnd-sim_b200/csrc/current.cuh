@@ -46,7 +46,11 @@ struct McParams {
     long long rng_stride;     // ntrk of detsim.py:324
     int P, T, Rx, Ry, Rt;
     int stride;               // TIME_SAMPLING / RESPONSE_SAMPLING if integral, else 0
+    // sync-free operation (fused chain): the sample total stays on the device; every kernel after the scan
+    // returns at once if it exceeds the capacity the caller provisioned (and *overflow is raised)
+    const long long* total_dev; long long cap; int* overflow;
 };
+#define MC_GUARD(p) do { if ((p).total_dev && *(p).total_dev > (p).cap) return; } while (0)
 
 __device__ __forceinline__ double tick_time(double t_start, int it) { return t_start + (double)it * d_c.time_sampling; }
 
@@ -154,8 +158,9 @@ __global__ void k_mc_pairs(Layout L, const char* __restrict__ tracks, const int3
     pairs[pr] = g;
 }
 
-__global__ void k_mc_set_offsets(PairRec* __restrict__ pairs, const long long* __restrict__ offs, long long n) {
+__global__ void k_mc_set_offsets(McParams p, PairRec* __restrict__ pairs, const long long* __restrict__ offs, long long n) {
     long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p.total_dev && *p.total_dev > p.cap) { if (pr == 0 && p.overflow) *p.overflow = 1; return; }
     if (pr < n) pairs[pr].sample_off = offs[pr];
 }
 
@@ -184,73 +189,167 @@ __device__ __forceinline__ SampleGeom mc_sample(const PairRec& g, long long iste
 }
 __device__ __forceinline__ long long resp_k(double tick, double t0) { return __double2ll_rn((tick - t0) / d_c.response_sampling); }
 
-__global__ void k_mc_sampler(McParams p, PairRec* __restrict__ pairs, SampleRec* __restrict__ samples,
-                             int* __restrict__ offs32, unsigned long long* __restrict__ rng_states) {
-    long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+// The sampler is split so that the only sequential part -- stepping each pair's xoroshiro128+ stream -- is a
+// short integer chain, and the expensive part (3 Box-Muller normals, FP64 geometry with exact divisions, the
+// tick-range search) runs one SAMPLE per lane with balanced warps:
+//   k_mc_uniforms  thread per (segment,pixel): 6 float32 uniforms per sample -> uu[sample][6]; state written back
+//   k_mc_sampler   warp per (segment,pixel): lane = sample; live samples are compacted in order (ballot prefix)
+struct SampleU { float u[6]; };
+
+#define UNI_TPB 64
+#define UNI_CHUNK 16         // samples generated per thread between two cooperative write-outs (16*6 floats = 3 warp rows)
+__global__ void __launch_bounds__(UNI_TPB) k_mc_uniforms(McParams p, const PairRec* __restrict__ pairs, SampleU* __restrict__ uu,
+                                                        unsigned long long* __restrict__ rng_states) {
+    // thread = (segment,pixel).  Each thread's samples are contiguous in `uu`, so direct stores would scatter
+    // 24-byte pieces over 32 different places per warp; the values go through shared memory and leave as
+    // contiguous 192-byte runs per pair instead.
+    MC_GUARD(p);
+    __shared__ float s_u[UNI_TPB][UNI_CHUNK * 6 + 1];
+    __shared__ long long s_base[UNI_TPB];
+    __shared__ long long s_n[UNI_TPB];
+    __shared__ long long s_max;
+    const int tid = threadIdx.x;
+    const long long pr = blockIdx.x * (long long)UNI_TPB + tid;
+    const bool valid = pr < p.S * p.P && pairs[pr].valid;
+    const long long n = valid ? pairs[pr].nstep * d_c.mc_sample_multiplier : 0;
+    Rng rng; rng.s0 = 0; rng.s1 = 0;
+    unsigned long long* sp = nullptr;
+    if (valid) {
+        long long itrk = p.seg0 + pr / p.P;
+        int ipix = (int)(pr % p.P);
+        sp = rng_states + 2 * (itrk + p.rng_stride * ipix);
+        rng.s0 = sp[0]; rng.s1 = sp[1];
+    }
+    s_base[tid] = valid ? pairs[pr].sample_off : 0;
+    s_n[tid] = n;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    if (n > 0) atomicMax((unsigned long long*)&s_max, (unsigned long long)n);
+    __syncthreads();
+    const long long nmax = s_max;
+    float* dst = reinterpret_cast<float*>(uu);
+    for (long long i0 = 0; i0 < nmax; i0 += UNI_CHUNK) {
+#pragma unroll
+        for (int j = 0; j < UNI_CHUNK; j++) {
+            if (i0 + j < n) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) s_u[tid][j * 6 + k] = rng_uniform_f32(rng);
+            }
+        }
+        __syncthreads();
+        // warp w writes the runs of pairs w, w + nwarps, ...: 96 contiguous floats each = 3 coalesced rows
+        for (int t = tid >> 5; t < UNI_TPB; t += UNI_TPB / 32) {
+            const long long left = (s_n[t] - i0) * 6;              // floats still owed to this pair
+            if (left <= 0) continue;
+            float* row = dst + (s_base[t] + i0) * 6;
+#pragma unroll
+            for (int j = 0; j < UNI_CHUNK * 6 / 32; j++) {
+                const int o = (tid & 31) + 32 * j;
+                if (o < left) row[o] = s_u[t][o];
+            }
+        }
+        __syncthreads();
+    }
+    if (valid) { sp[0] = rng.s0; sp[1] = rng.s1; }
+}
+__device__ __forceinline__ float normal_from_uniforms(float u1, float u2) {     // == rng_normal_f32
+    float a = sqrtf(__fmul_rn(-2.0f, logf(u1)));
+    float b = cosf(__fmul_rn(6.283185307179586f, u2));
+    return __fmul_rn(a, b);
+}
+
+#define SMP_WARPS 4
+__global__ void __launch_bounds__(32 * SMP_WARPS) k_mc_sampler(McParams p, PairRec* __restrict__ pairs,
+                                                               const SampleU* __restrict__ uu, SampleRec* __restrict__ samples,
+                                                               int* __restrict__ offs32) {
+    MC_GUARD(p);
+    const int lane = threadIdx.x & 31;
+    const long long pr = blockIdx.x * (long long)SMP_WARPS + (threadIdx.x >> 5);
     if (pr >= p.S * p.P) return;
-    PairRec g = pairs[pr];
+    const PairRec g = pairs[pr];
     if (!g.valid) return;
-    long long itrk = p.seg0 + pr / p.P;
-    int ipix = (int)(pr % p.P);
-    unsigned long long* sp = rng_states + 2 * (itrk + p.rng_stride * ipix);
-    Rng rng; rng.s0 = sp[0]; rng.s1 = sp[1];
     SampleRec* out = samples + g.sample_off;
     int* out32 = offs32 + g.sample_off;
+    const SampleU* in = uu + g.sample_off;
     int n_live = 0, n_irr = 0, int_lo = 0, int_hi = p.T - 1, uni_lo = p.T, uni_hi = -1;
     const int M = d_c.mc_sample_multiplier;
     const double W = d_c.time_window, TS = d_c.time_sampling;
-    for (long long istep = 0; istep < g.nstep; istep++)
-        for (int m = 0; m < M; m++) {
-            float nz = rng_normal_f32(rng);
-            float nx = rng_normal_f32(rng);
-            float ny = rng_normal_f32(rng);
+    const long long n = g.nstep * M;
+    for (long long i0 = 0; i0 < n; i0 += 32) {
+        const long long i = i0 + lane;
+        bool keep = false;
+        SampleRec r; r.t0 = 0; r.rowoff = 0; r.shift = SHIFT_IRREGULAR; r.lo = 0; r.hi = -1;
+        if (i < n) {
+            const SampleU v = in[i];
+            const float nz = normal_from_uniforms(v.u[0], v.u[1]);
+            const float nx = normal_from_uniforms(v.u[2], v.u[3]);
+            const float ny = normal_from_uniforms(v.u[4], v.u[5]);
+            const long long istep = i / M;
             SampleGeom s = mc_sample(g, istep, nz, nx, ny, p.Rx, p.Ry, p.Rt);
-            if (!s.live) continue;
-            double t0 = s.t0, t0W = t0 + W;
-            // lower bound: first tick with tick>=0, tick>t0, k>=0 (all monotone in the tick index)
-            double tl = t0 > 0 ? t0 : 0;
-            double e = floor((tl - g.t_start) / TS);
-            int lo = e < 0 ? 0 : (e > (double)p.T ? p.T : (int)e);
-            // tick > t0 already implies k = round((tick - t0)/rs) >= 0: no division in the lower search
+            if (s.live) {
+                double t0 = s.t0, t0W = t0 + W;
+                // lower bound: first tick with tick>=0, tick>t0 (tick > t0 already implies k = round((tick-t0)/rs) >= 0)
+                double tl = t0 > 0 ? t0 : 0;
+                double e = floor((tl - g.t_start) / TS);
+                int lo = e < 0 ? 0 : (e > (double)p.T ? p.T : (int)e);
 #define LOW_OK(it) (tick_time(g.t_start, (it)) >= 0 && t0 < tick_time(g.t_start, (it)))
-            while (lo > 0 && LOW_OK(lo - 1)) lo--;
-            while (lo < p.T && !LOW_OK(lo)) lo++;
-            // upper bound: last tick with tick < t0+W and k < Rt.  The window test needs no division; k < Rt only
-            // bites when the table is shorter than the window, and k is monotone in the tick index.
-            e = ceil((t0W - g.t_start) / TS);
-            int hi = e < -1 ? -1 : (e > (double)(p.T - 1) ? p.T - 1 : (int)e);
+                while (lo > 0 && LOW_OK(lo - 1)) lo--;
+                while (lo < p.T && !LOW_OK(lo)) lo++;
+#undef LOW_OK
+                // upper bound: last tick with tick < t0+W and k < Rt.  The window test needs no division; k < Rt only
+                // bites when the table is shorter than the window, and k is monotone in the tick index.
+                e = ceil((t0W - g.t_start) / TS);
+                int hi = e < -1 ? -1 : (e > (double)(p.T - 1) ? p.T - 1 : (int)e);
 #define HIGH_T(it) (tick_time(g.t_start, (it)) < t0W)
 #define K_OK(it) (resp_k(tick_time(g.t_start, (it)), t0) < p.Rt)
-            while (hi < p.T - 1 && HIGH_T(hi + 1)) hi++;
-            while (hi >= 0 && !HIGH_T(hi)) hi--;
-            if (hi >= 0 && !K_OK(hi)) {
-                double e2 = floor((t0 + ((double)p.Rt - 0.5) * d_c.response_sampling - g.t_start) / TS) + 1.0;
-                int h2 = e2 < -1 ? -1 : (e2 > (double)hi ? hi : (int)e2);
-                while (h2 < hi && K_OK(h2 + 1)) h2++;          // safety: the estimate must not undershoot
-                hi = h2;
-                while (hi >= 0 && !K_OK(hi)) hi--;
-            }
+                while (hi < p.T - 1 && HIGH_T(hi + 1)) hi++;
+                while (hi >= 0 && !HIGH_T(hi)) hi--;
+                if (hi >= 0 && !K_OK(hi)) {
+                    double e2 = floor((t0 + ((double)p.Rt - 0.5) * d_c.response_sampling - g.t_start) / TS) + 1.0;
+                    int h2 = e2 < -1 ? -1 : (e2 > (double)hi ? hi : (int)e2);
+                    while (h2 < hi && K_OK(h2 + 1)) h2++;          // safety: the estimate must not undershoot
+                    hi = h2;
+                    while (hi >= 0 && !K_OK(hi)) hi--;
+                }
 #undef HIGH_T
 #undef K_OK
-            if (lo > hi) continue;
-            int shift = SHIFT_IRREGULAR;
-            if (p.stride > 0) {
-                long long klo = resp_k(tick_time(g.t_start, lo), t0), khi = resp_k(tick_time(g.t_start, hi), t0);
-                long long sh = klo - (long long)p.stride * lo;
-                if (khi == (long long)p.stride * hi + sh) shift = (int)sh;
+                if (lo <= hi) {
+                    int shift = SHIFT_IRREGULAR;
+                    if (p.stride > 0) {
+                        long long klo = resp_k(tick_time(g.t_start, lo), t0), khi = resp_k(tick_time(g.t_start, hi), t0);
+                        long long sh = klo - (long long)p.stride * lo;
+                        if (khi == (long long)p.stride * hi + sh) shift = (int)sh;
+                    }
+                    r.t0 = t0; r.rowoff = s.rowoff; r.shift = shift; r.lo = lo; r.hi = hi;
+                    keep = true;
+                }
             }
-            SampleRec r; r.t0 = t0; r.rowoff = s.rowoff; r.shift = shift; r.lo = lo; r.hi = hi;
-            out[n_live] = r;
-            out32[n_live] = (shift == SHIFT_IRREGULAR) ? OFF_IRREGULAR : s.rowoff + shift;
-            n_live++;
-            if (shift != SHIFT_IRREGULAR) { int_lo = lo > int_lo ? lo : int_lo; int_hi = hi < int_hi ? hi : int_hi; }
-            else n_irr++;
-            uni_lo = lo < uni_lo ? lo : uni_lo; uni_hi = hi > uni_hi ? hi : uni_hi;
         }
-#undef LOW_OK
-    sp[0] = rng.s0; sp[1] = rng.s1;
-    PairRec* gp = pairs + pr;
-    gp->n_live = n_live; gp->n_irregular = n_irr; gp->int_lo = int_lo; gp->int_hi = int_hi; gp->uni_lo = uni_lo; gp->uni_hi = uni_hi;
+        // ordered compaction of the live samples of this chunk
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = n_live + __popc(m & ((1u << lane) - 1));
+            out[pos] = r;
+            out32[pos] = (r.shift == SHIFT_IRREGULAR) ? OFF_IRREGULAR : r.rowoff + r.shift;
+            if (r.shift != SHIFT_IRREGULAR) { int_lo = r.lo > int_lo ? r.lo : int_lo; int_hi = r.hi < int_hi ? r.hi : int_hi; }
+            else n_irr++;
+            uni_lo = r.lo < uni_lo ? r.lo : uni_lo; uni_hi = r.hi > uni_hi ? r.hi : uni_hi;
+        }
+        n_live += __popc(m);
+    }
+    // per-pair reductions over the lanes
+    for (int o = 16; o > 0; o >>= 1) {
+        int v;
+        v = __shfl_xor_sync(0xffffffffu, int_lo, o); int_lo = v > int_lo ? v : int_lo;
+        v = __shfl_xor_sync(0xffffffffu, int_hi, o); int_hi = v < int_hi ? v : int_hi;
+        v = __shfl_xor_sync(0xffffffffu, uni_lo, o); uni_lo = v < uni_lo ? v : uni_lo;
+        v = __shfl_xor_sync(0xffffffffu, uni_hi, o); uni_hi = v > uni_hi ? v : uni_hi;
+        n_irr += __shfl_xor_sync(0xffffffffu, n_irr, o);
+    }
+    if (lane == 0) {
+        PairRec* gp = pairs + pr;
+        gp->n_live = n_live; gp->n_irregular = n_irr; gp->int_lo = int_lo; gp->int_hi = int_hi; gp->uni_lo = uni_lo; gp->uni_hi = uni_hi;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -318,6 +417,7 @@ __global__ void __launch_bounds__(ACC_TPB) k_mc_accumulate(McParams p, const Pai
                                                            const SampleRec* __restrict__ samples,
                                                            const int* __restrict__ offs32, const TL* __restrict__ lut,
                                                            float* __restrict__ signals) {
+    MC_GUARD(p);
     long long pr = blockIdx.x;
     const PairRec* gp = pairs + pr;
     if (!gp->valid) return;
@@ -511,8 +611,9 @@ __global__ void k_mc_replay(McParams p, const PairRec* __restrict__ pairs, const
 // ---------------------------------------------------------------------------------------
 struct McWs {
     PairRec* pairs; uint32_t* nsamp; long long* offs; long long* block_sums; long long* total;
-    SampleRec* samples; int* offs32; long long sample_cap;
+    SampleRec* samples; int* offs32; SampleU* uu; long long sample_cap;
 };
+#define MC_BYTES_PER_SAMPLE ((long long)(sizeof(SampleRec) + 4 + sizeof(SampleU)))
 static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 static inline long long mc_fixed_bytes(long long npair) {
     return align_up(npair * (long long)sizeof(PairRec), 256) + align_up(npair * 4, 256) + align_up(npair * 8, 256) +
@@ -520,21 +621,22 @@ static inline long long mc_fixed_bytes(long long npair) {
 }
 LSB_EXPORT int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total) {
     return mc_fixed_bytes(S * (long long)P) + align_up(max_steps_total * (long long)sizeof(SampleRec), 256) +
-           align_up(max_steps_total * 4, 256);
+           align_up(max_steps_total * 4, 256) + align_up(max_steps_total * (long long)sizeof(SampleU), 256) + 1024;
 }
 static inline bool mc_carve(void* ws, long long bytes, long long npair, McWs& w) {
     char* p = (char*)ws;
     long long fixed = mc_fixed_bytes(npair);
-    if (bytes < fixed + 28 * 64) return false;
+    if (bytes < fixed + MC_BYTES_PER_SAMPLE * 64 + 1024) return false;
     w.pairs = (PairRec*)p; p += align_up(npair * (long long)sizeof(PairRec), 256);
     w.nsamp = (uint32_t*)p; p += align_up(npair * 4, 256);
     w.offs = (long long*)p; p += align_up(npair * 8, 256);
     w.block_sums = (long long*)p; p += align_up((scan_num_blocks(npair) + 1) * 8, 256);
     w.total = (long long*)p; p += 256;
     long long rest = bytes - fixed;
-    w.sample_cap = (rest - 512) / 28;
+    w.sample_cap = (rest - 1024) / MC_BYTES_PER_SAMPLE;
     w.samples = (SampleRec*)p; p += align_up(w.sample_cap * (long long)sizeof(SampleRec), 256);
-    w.offs32 = (int*)p;
+    w.offs32 = (int*)p; p += align_up(w.sample_cap * 4, 256);
+    w.uu = (SampleU*)p;
     return w.sample_cap > 0;
 }
 
@@ -567,23 +669,30 @@ static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixe
     }
     int rc = exclusive_scan<uint32_t, long long>(w.nsamp, npair, w.offs, w.block_sums, w.total, st);
     if (rc) return rc;
-    long long total = 0;
-    LSB_CUDA(cudaMemcpyAsync(&total, w.total, 8, cudaMemcpyDeviceToHost, st));
-    LSB_CUDA(cudaStreamSynchronize(st));
-    if (total > w.sample_cap) {
-        if (p.S <= 1) return lsb_fail_arg("tracks_current_mc: workspace too small for a single segment");
-        if (depth > 40) return lsb_fail_arg("tracks_current_mc: workspace split too deep");
-        McParams a = p, b = p;
-        a.S = p.S / 2; b.S = p.S - a.S; b.seg0 = p.seg0 + a.S;
-        rc = mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, a, ws, ws_bytes, st, depth + 1);
-        if (rc) return rc;
-        return mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, b, ws, ws_bytes, st, depth + 1);
+    if (p.overflow) {
+        // sync-free: the caller provisioned the workspace from an upper bound; the kernels check it on the device
+        p.total_dev = w.total; p.cap = w.sample_cap;
+    } else {
+        long long total = 0;
+        LSB_CUDA(cudaMemcpyAsync(&total, w.total, 8, cudaMemcpyDeviceToHost, st));
+        LSB_CUDA(cudaStreamSynchronize(st));
+        if (total > w.sample_cap) {
+            if (p.S <= 1) return lsb_fail_arg("tracks_current_mc: workspace too small for a single segment");
+            if (depth > 40) return lsb_fail_arg("tracks_current_mc: workspace split too deep");
+            McParams a = p, b = p;
+            a.S = p.S / 2; b.S = p.S - a.S; b.seg0 = p.seg0 + a.S;
+            rc = mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, a, ws, ws_bytes, st, depth + 1);
+            if (rc) return rc;
+            return mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, b, ws, ws_bytes, st, depth + 1);
+        }
+        g_mc_last_samples += total;
+        if (total == 0) return 0;
     }
-    g_mc_last_samples += total;
-    if (total == 0) return 0;
-    k_mc_set_offsets<<<lsb_blocks(npair, 256), 256, 0, st>>>(w.pairs, w.offs, npair);
+    k_mc_set_offsets<<<lsb_blocks(npair, 256), 256, 0, st>>>(p, w.pairs, w.offs, npair);
     LSB_LAUNCH_CHECK("k_mc_set_offsets");
-    k_mc_sampler<<<lsb_blocks(npair, 64), 64, 0, st>>>(p, w.pairs, w.samples, w.offs32, rng);
+    k_mc_uniforms<<<lsb_blocks(npair, UNI_TPB), UNI_TPB, 0, st>>>(p, w.pairs, w.uu, rng);
+    LSB_LAUNCH_CHECK("k_mc_uniforms");
+    k_mc_sampler<<<lsb_blocks(npair, SMP_WARPS), 32 * SMP_WARPS, 0, st>>>(p, w.pairs, w.uu, w.samples, w.offs32);
     LSB_LAUNCH_CHECK("k_mc_sampler");
     if (f64) return mc_launch_accumulate<double>(p, w, (const double*)response, signals, st);
     return mc_launch_accumulate<float>(p, w, (const float*)response, signals, st);
@@ -620,8 +729,33 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
     g_mc_last_samples = 0;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr;
     return mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states,
                         rng_mode, p, workspace, workspace_bytes, st, 0);
+}
+
+// Fused-chain entry without host synchronisation: `workspace` must hold `lsb_tracks_current_mc_workspace_bytes`
+// of an UPPER BOUND of the sample count; *total_out (device) receives the actual count, *overflow (device)
+// is raised -- and nothing is written -- if the bound was wrong.  Cloud mode only.
+static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S, const int32_t* pixels,
+                         int32_t P, float* signals, int32_t T, const void* response, int32_t Rx, int32_t Ry, int32_t Rt,
+                         int32_t response_f64, uint64_t* rng_states, int64_t rng_stride, void* workspace,
+                         int64_t workspace_bytes, long long* total_out, int* overflow, cudaStream_t st) {
+    if (S == 0 || P == 0 || T == 0) return 0;
+    if (require_current_fields(L, true)) return -1;
+    int rc = lsb_upload_consts(c, st); if (rc) return rc;
+    McParams p;
+    p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
+    double ratio = c->time_sampling / c->response_sampling;
+    p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
+    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow;
+    rc = mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states, 0, p,
+                      workspace, workspace_bytes, st, 0);
+    if (rc) return rc;
+    McWs w;
+    mc_carve(workspace, workspace_bytes, S * (long long)P, w);
+    LSB_CUDA(cudaMemcpyAsync(total_out, w.total, 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
 }
 
 // =======================================================================================

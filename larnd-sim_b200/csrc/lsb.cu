@@ -25,6 +25,13 @@ int lsb_upload_consts(const lsb_consts* c, cudaStream_t st) {
 
 TmpArena* g_lsb_arena = nullptr;
 
+// a process-wide time origin for pipeline timelines (recorded on first use)
+cudaEvent_t lsb_reference_event() {
+    static cudaEvent_t ev = nullptr;
+    if (!ev) { cudaEventCreate(&ev); cudaEventRecord(ev, 0); cudaEventSynchronize(ev); }
+    return ev;
+}
+
 void lsb_pool_init_once() {
     static bool done = false;
     if (done) return;

@@ -47,3 +47,36 @@ def gather_packets(rec, dst=0, group=None):
     if rank != dst:
         return None
     return [b[:c] for b, c in zip(bufs, counts)]
+
+
+class HitTableGather:
+    """Sync-free gather of the per-batch hit table to `dst`: every rank sends ONE fixed-size buffer
+    [cap + 1, 1 + 2A] of float64 -- row 0 holds the number of valid rows, rows 1..U hold
+    (pixel id | ADC codes[A] | timestamps[A]) -- so no count exchange and no host synchronisation is needed
+    (the pixel count U is already known to the host from the chain result).  `dst` compacts it into packets
+    with :func:`hit_packets` whenever it wants to."""
+
+    def __init__(self, cap, n_adc, device, dst=0, group=None):
+        self.cap, self.A, self.dst, self.group = int(cap), int(n_adc), dst, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.send = torch.zeros((self.cap + 1, 1 + 2 * self.A), dtype=torch.float64, device=device)
+        self.recv = ([torch.empty_like(self.send) for _ in range(self.world)] if self.rank == dst else None)
+
+    def gather(self, unique_pix, adc_digit, adc_ticks):
+        U = int(unique_pix.shape[0])
+        if U > self.cap:
+            raise ValueError("hit table larger than the gather buffer (%d > %d)" % (U, self.cap))
+        b = self.send
+        b[0, 0] = float(U)
+        b[1:U + 1, 0] = unique_pix.to(torch.float64)
+        b[1:U + 1, 1:1 + self.A] = adc_digit
+        b[1:U + 1, 1 + self.A:] = adc_ticks
+        if self.world == 1:
+            return [b]
+        dist.gather(b, self.recv, dst=self.dst, group=self.group)
+        return self.recv
+
+    def unpack(self, buf):
+        U = int(buf[0, 0].item())
+        return buf[1:U + 1, 0].to(torch.int32), buf[1:U + 1, 1:1 + self.A], buf[1:U + 1, 1 + self.A:]

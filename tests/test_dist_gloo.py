@@ -37,6 +37,15 @@ def _worker(rank, world, port, q):
         q.put([o.tolist() for o in out])
     else:
         assert out is None
+    g = ldist.HitTableGather(cap=6, n_adc=2, device="cpu")
+    U = 2 + rank
+    uniq = torch.arange(U, dtype=torch.int32) + 10 * rank
+    digit = torch.full((U, 2), 80.0 + rank, dtype=torch.float64)
+    ticks = torch.full((U, 2), 1.5 * (rank + 1), dtype=torch.float64)
+    tabs = g.gather(uniq, digit, ticks)
+    if rank == 0:
+        u1, d1, t1 = g.unpack(tabs[1])
+        q.put((u1.tolist(), d1.tolist(), t1.tolist(), [int(t[0, 0].item()) for t in tabs]))
     empty = ldist.gather_packets(torch.zeros((0, 3), dtype=torch.float64), dst=0)     # no hits anywhere
     if rank == 0:
         q.put([tuple(e.shape) for e in empty])
@@ -52,6 +61,7 @@ def test_gather_packets_world2_gloo():
     for p in procs:
         p.start()
     got = q.get(timeout=120)
+    table = q.get(timeout=120)
     shapes = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
@@ -59,3 +69,4 @@ def test_gather_packets_world2_gloo():
     assert len(got) == 2 and len(got[0]) == 3 and len(got[1]) == 5
     assert got[1][0] == [100.0, 101.0, 102.0] and got[0][2] == [6.0, 7.0, 8.0]
     assert shapes == [(0, 3), (0, 3)]
+    assert table[0] == [10, 11, 12] and table[1] == [[81.0, 81.0]] * 3 and table[2] == [[3.0, 3.0]] * 3 and table[3] == [2, 3]
