@@ -284,6 +284,10 @@ void       lsb_chain_destroy(lsb_chain* h);
  * run get_adc_values on it; dense=0 (default): read the per-segment waveforms from `signals` through the
  * (pixel, slot) entry list -- same numbers, no 0.8 MB/pixel tensor. */
 int        lsb_chain_set_dense(lsb_chain* h, int32_t dense);
+/* current_fractions (fee.py:568-573, the per-segment share of each hit): exact=1 replays the reference's tick-major
+ * summation order (bit-identical float64), exact=0 (default) evaluates the same double sum as order-free weighted
+ * sums over each hit window (agrees to ~1e-15 relative; hits, timestamps and charges do not depend on it). */
+int        lsb_chain_set_exact_fractions(lsb_chain* h, int32_t exact);
 /* tracks on the device, modified in place by quench/drift like the reference */
 int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
                   int32_t n_events, lsb_chain_result* out, void* stream);

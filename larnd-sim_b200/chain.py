@@ -120,7 +120,7 @@ class Chain:
     """``Chain(track_dtype, response)``; ``run(tracks_dev)`` on device records, ``run_host(tracks)``
     on a (pinned) host structured array with H2D/D2H inside the call."""
 
-    def __init__(self, track_dtype, response, rng_mode="cloud", stage_timing=False, dense=False):
+    def __init__(self, track_dtype, response, rng_mode="cloud", stage_timing=False, dense=False, exact_fractions=False):
         self._c = _consts.snapshot()
         self._L = _abi.track_layout(track_dtype)
         self.dtype = np.dtype(track_dtype)
@@ -136,6 +136,8 @@ class Chain:
             raise _abi.LsbError("lsb_chain_create failed: %s" % lib.lsb_last_error().decode())
         if dense:
             _l.check(lib.lsb_chain_set_dense(C.c_void_p(self._h), C.c_int32(1)), "chain_set_dense")
+        if exact_fractions:
+            _l.check(lib.lsb_chain_set_exact_fractions(C.c_void_p(self._h), C.c_int32(1)), "chain_set_exact_fractions")
         self._K, self._A, self._Tt = int(self._c.max_tracks_per_pixel), int(self._c.max_adc_values), int(self._c.n_time_ticks)
 
     def close(self):

@@ -40,6 +40,7 @@ struct lsb_chain {
     DevBuf tracks, scal, active, neigh, nrad, npl, uniq, uniq_ws, starts, signals, mc_ws, pim, tpm, psig, pts, oflow, tticks,
            integral, adc_digit, adc_ticks, cf, thr, rng, nhits, sx_slot, sx_counts, sx_cursor, sx_raw, sx_offs, sx_bsums, sx_sorted;
     DevBuf arena_buf; TmpArena arena;
+    int exact_fractions;      // 1: current_fractions in the reference's summation order (bit-identical), 0: order-free weighted sums
     int dense;                // 1: materialise pixels_tracks_signals like the reference (parity / debugging)
     long long n_rng;
     int tticks_n; long long tticks_events;
@@ -99,7 +100,7 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     if (!c || !L || !response || Rx <= 0 || Ry <= 0 || Rt <= 0) { lsb_fail_arg("chain_create: bad arguments"); return nullptr; }
     lsb_chain* h = new lsb_chain();
     h->c = *c; h->L = *L; h->response = response; h->Rx = Rx; h->Ry = Ry; h->Rt = Rt; h->f64 = response_f64;
-    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->dense = 0; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
+    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->dense = 0; h->exact_fractions = 0; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -124,6 +125,11 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
 LSB_EXPORT int lsb_chain_set_dense(lsb_chain* h, int32_t dense) {
     LSB_REQUIRE(h, "chain_set_dense: null handle");
     h->dense = dense ? 1 : 0;
+    return 0;
+}
+LSB_EXPORT int lsb_chain_set_exact_fractions(lsb_chain* h, int32_t exact) {
+    LSB_REQUIRE(h, "chain_set_exact_fractions: null handle");
+    h->exact_fractions = exact ? 1 : 0;
     return 0;
 }
 LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
@@ -359,7 +365,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     if ((rc = chain_grow_rng(h, need_rng2, rng_seed, st))) return rc;
     {
         FeeSparse sp; sp.signals = (const float*)h->signals.p; sp.T = (int)T; sp.offs = sx.offs; sp.counts = sx.counts;
-        sp.sorted = sx.sorted; sp.n_entries_cap = S * P;
+        sp.sorted = sx.sorted; sp.n_entries_cap = S * P; sp.exact = h->exact_fractions;
         LSB_REQUIRE(h->n_rng >= U, "chain_run: rng_states shorter than the number of pixels");
         if ((rc = fee_run(c, (const double*)h->psig.p, h->dense ? (const double*)h->pts.p : nullptr, h->dense ? nullptr : &sp, U, Tt, K,
                           (const double*)h->tticks.p, Tt + 1, (double*)h->integral.p, (double*)h->adc_ticks.p, A, 0.0,

@@ -30,6 +30,7 @@ struct FeeParams {
     int n_taps;                  // ceil(back)+1 taps jc = floor(ic-back) .. ic
 };
 __constant__ double d_fee_w[FEE_MAX_TAPS];
+__constant__ double d_fee_wp[FEE_MAX_TAPS];      // d_fee_wp[m] = w[0] + ... + w[m]
 
 struct FeeWindow {
     int ic0, ic1;                // FIR evaluated at every ic in [ic0, ic1]; last_reset == ic0
@@ -395,6 +396,57 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
         if (w.flags & 2) *out = 0.0;
     }
 }
+// Order-free variant (default of the fused chain): the double sum of fee.py:566-573 over a window [ic0, ic1],
+//     sum_{ic=ic0}^{ic1} sum_{jc=max(ic0,ic-(n-1))}^{min(ic,Tt-1)} I[jc]*dt*w[ic-jc]
+//   = dt * sum_{jc=ic0}^{min(ic1,Tt-1)} I[jc] * Wp[min(n-1, ic1-jc)],        Wp = prefix sums of w,
+// is a weighted sum of the waveform, evaluated by one warp per (pixel, slot) with coalesced row reads and a
+// shuffle reduction.  Mathematically identical to the replay above; the float64 rounding differs (1e-15).
+__global__ void __launch_bounds__(128) k_fee_fractions_fast(FeeParams fp, const float* __restrict__ signals, int T, long long U,
+                                                            int Tt, int K, const long long* __restrict__ offs,
+                                                            const int* __restrict__ counts, const SumEntry* __restrict__ sorted,
+                                                            long long n_sorted_total, const int* __restrict__ entry_pixel,
+                                                            const FeeWindow* __restrict__ windows,
+                                                            const int* __restrict__ n_windows, int A, double* __restrict__ cf) {
+    const int lane = threadIdx.x & 31;
+    const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;      // one warp per sorted entry
+    if (i >= n_sorted_total) return;
+    const int p = entry_pixel[i];
+    if (p < 0) return;
+    const SumEntry* L = sorted + offs[p];
+    const int n = counts[p];
+    const int me = (int)(i - offs[p]);
+    const int slot = L[me].slot;
+    for (int q = 0; q < me; q++) if (L[q].slot == slot) return;          // an earlier entry owns this (pixel, slot)
+    const int nw = n_windows[p];
+    const FeeWindow* W = windows + (long long)p * (A + 1);
+    const int ntap = fp.BR > 0 ? fp.n_taps : 1;
+    for (int iw = 0; iw < nw; iw++) {
+        const FeeWindow w = W[iw];
+        double acc = 0.0;
+        const int hi = w.ic1 < Tt - 1 ? w.ic1 : Tt - 1;
+        for (int q = me; q < n; q++) {                                    // normally exactly one entry per (pixel, slot)
+            if (L[q].slot != slot) continue;
+            const float* row = signals + (long long)L[q].e * T;
+            const long long start = L[q].start_tick;
+            long long lo = w.ic0 > start ? w.ic0 : start;                 // ticks where this row has samples
+            long long up = hi < start + T - 1 ? hi : start + T - 1;
+            for (long long jc = lo + lane; jc <= up; jc += 32) {
+                const double v = (double)__ldg(row + (jc - start));
+                const int m = (int)(w.ic1 - jc);
+                const double wt = fp.BR > 0 ? d_fee_wp[m < ntap - 1 ? m : ntap - 1] : 1.0;
+                acc += v * wt;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            double* out = cf + ((long long)p * A + iw) * K + slot;
+            double r = acc * fp.TS + ((w.flags & 2) ? 0.0 : *out);
+            if (w.flags & 1) r /= w.true_q;
+            *out = r;
+        }
+    }
+}
+
 __global__ void k_entry_pixel(const long long* __restrict__ offs, const int* __restrict__ counts, long long U, int* __restrict__ entry_pixel) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= U) return;
@@ -435,7 +487,8 @@ static size_t fee_scratch_bytes(const lsb_consts* c, long long U, int Tt, int A,
 }
 
 // sparse context: the (pixel, slot) entries of sum_pixel_signals and the per-segment waveforms
-struct FeeSparse { const float* signals; int T; const long long* offs; const int* counts; const SumEntry* sorted; long long n_entries_cap; };
+struct FeeSparse { const float* signals; int T; const long long* offs; const int* counts; const SumEntry* sorted; long long n_entries_cap;
+                   int exact; /* 1: replay the reference's summation order (bit-identical fractions) */ };
 
 static int fee_run(const lsb_consts* c, const double* pixels_signals, const double* pst, const FeeSparse* sp, long long U, int Tt,
                    int K, const double* time_ticks, int n_time_ticks, double* adc_list, double* adc_ticks_list, int A,
@@ -444,7 +497,13 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
     FeeParams fp;
     double w_host[FEE_MAX_TAPS];
     if (fee_params(c, fp, w_host)) return -1;
-    if (fp.n_w > 0) LSB_CUDA(cudaMemcpyToSymbolAsync(d_fee_w, w_host, sizeof(double) * fp.n_w, 0, cudaMemcpyHostToDevice, st));
+    if (fp.n_w > 0) {
+        LSB_CUDA(cudaMemcpyToSymbolAsync(d_fee_w, w_host, sizeof(double) * fp.n_w, 0, cudaMemcpyHostToDevice, st));
+        double wp_host[FEE_MAX_TAPS];
+        double run = 0.0;
+        for (int d = 0; d < fp.n_w; d++) { run += w_host[d]; wp_host[d] = run; }
+        LSB_CUDA(cudaMemcpyToSymbolAsync(d_fee_wp, wp_host, sizeof(double) * fp.n_w, 0, cudaMemcpyHostToDevice, st));
+    }
     TmpPool tp(st);
     FeeWindow* windows; int* n_windows;
     LSB_CUDA(tp.get(&windows, U * (long long)(A + 1)));
@@ -480,13 +539,20 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
     }
     if (K > 0 && A > 0) {
         const bool ring_ok = fp.BR <= 0 || fp.n_taps <= FEE_RING;
-        if (sp && ring_ok) {
+        if (sp && (ring_ok || !sp->exact)) {
             int* entry_pixel;
             LSB_CUDA(tp.get(&entry_pixel, sp->n_entries_cap));
             LSB_CUDA(cudaMemsetAsync(entry_pixel, 0xff, sp->n_entries_cap * 4, st));
             k_entry_pixel<<<lsb_blocks(U, 256), 256, 0, st>>>(sp->offs, sp->counts, U, entry_pixel);
             LSB_LAUNCH_CHECK("k_entry_pixel");
             // entries are packed at the front of `sorted` (exclusive scan of the bucket sizes); unused tail has pixel -1
+            if (!sp->exact) {
+                k_fee_fractions_fast<<<lsb_blocks(sp->n_entries_cap * 32, 128), 128, 0, st>>>(
+                    fp, sp->signals, sp->T, U, Tt, K, sp->offs, sp->counts, sp->sorted, sp->n_entries_cap, entry_pixel, windows,
+                    n_windows, A, current_fractions);
+                LSB_LAUNCH_CHECK("k_fee_fractions_fast");
+                return 0;
+            }
 #define FEE_FRAC_LAUNCH(N) k_fee_fractions_sparse<N><<<lsb_blocks(sp->n_entries_cap, 128), 128, 0, st>>>(                       \
                 fp, sp->signals, sp->T, U, Tt, K, sp->offs, sp->counts, sp->sorted, sp->n_entries_cap, entry_pixel, windows,       \
                 n_windows, A, current_fractions)

@@ -283,11 +283,13 @@ def test_adc_noise_off_and_low_threshold(cuda):
 
 @pytest.mark.parametrize("config,kind,n", [("module0", "cosmic", 200), ("2x2", "beam", 300), ("ndlar", "beam", 200)])
 def test_chain_vs_oracle(cuda, config, kind, n):
-    for noise, dense in ((True, False), (False, False), (True, True)):
-        r = h.chain_vs_oracle(n_segments=n, config=config, seed=17, noise=noise, kind=kind, dense=dense)
+    # (noise, dense buffers, fractions in the reference's summation order)
+    for noise, dense, exact in ((True, False, True), (False, False, True), (True, True, True), (True, False, False)):
+        r = h.chain_vs_oracle(n_segments=n, config=config, seed=17, noise=noise, kind=kind, dense=dense, exact_fractions=exact)
         assert r["tracks_equal"] and r["shape_equal"] and r["unique_equal"] and r["tpm_equal"]
         assert r["signals_relerr"] < 1e-5
-        assert r["pixels_signals_equal"] and r["ticks_equal"] and r["cf_equal"] and r["adc_pattern_equal"]
+        assert r["pixels_signals_equal"] and r["ticks_equal"] and r["adc_pattern_equal"]
+        assert r["cf_equal"] if exact else r["cf_close"]        # order-free fraction sums: 1e-12, everything else identical
         assert r["adc_list_equal"] if not noise else r["adc_list_relerr"] < 1e-7
         assert r["adc_mismatch"] == 0 and r["n_hits"] == r["n_hits_oracle"] and r["n_hits"] > 0
         assert r["launches"] > 10
