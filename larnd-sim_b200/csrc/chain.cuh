@@ -253,6 +253,8 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
             int dev = 0; cudaGetDevice(&dev);
             cudaDeviceProp prop; persist_max = 0;
             if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) persist_max = (size_t)prop.persistingL2CacheMaxSize;
+            if (getenv("LSB_NO_L2_PERSIST")) persist_max = 0;        // tuning / A-B switch
+            if (persist_max > (64u << 20)) persist_max = 64u << 20;   // the table needs 16-32 MB; leave the rest of L2 alone
             if (persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_max);
             (void)cudaGetLastError();
         }
