@@ -304,28 +304,43 @@ def run_ours(args, rank, world, local_rank):
     total_kernel_ms = sum(v[1] for _, v in kern)
     top_name, (top_cnt, top_ms) = max(kern, key=lambda kv: kv[1][1])
     per_launch_ms = top_ms / max(top_cnt, 1)
-    # algorithmic HBM bytes per launch of each candidate (DESIGN.md "kernels and their rooflines")
-    alg = {
-        "k_mc_accumulate": 4.0 * S * P_ * T + 4.0 * n_samples + 152.0 * S * P_,
-        "k_fee_fractions": 8.0 * U * Tt * K + 8.0 * U * A * K,
-        "k_sum_pixel_signals": 4.0 * S * P_ * T + 2 * 8.0 * U * Tt + 2 * 8.0 * (S * P_ * 0.61) * T,
-        "memset_pts": 8.0 * U * Tt * K,
-        "k_fee_trigger": 8.0 * U * Tt + 2 * 8.0 * U * A,
-    }
     launches_per_step = top_cnt / args.steps
-    bytes_per_launch = alg.get(top_name, 0.0) / max(launches_per_step, 1e-9) if top_name in alg else None
-    roofline = {"kernel": top_name, "bound": "hbm", "timed": "CUDA events on the launching stream, same K steps run one batch at a time", "share_of_kernel_time": top_ms / total_kernel_ms,
-                "ms_per_launch": per_launch_ms, "launches_per_step": launches_per_step,
+    # algorithmic HBM bytes per launch.  n_valid = (segment,pixel) pairs with a pixel,
+    # T_act = ticks with time >= 0 actually written (about half of T for uniformly distributed drift times)
+    n_valid = 0.61 * S * P_
+    alg = {
+        # out: written waveform ticks; in: per-sample offset (4 B) + sample record for the edge ticks (24 B) + pair records
+        "k_mc_accumulate": 4.0 * n_valid * T * 0.5 + 28.0 * n_samples + 152.0 * S * P_,
+        "k_fee_trigger": 8.0 * U * Tt + 4.0 * U * 4480 + 2 * 8.0 * U * A,
+        "k_sum_pixel_signals": 4.0 * n_valid * T + 2 * 8.0 * U * Tt,
+        "k_mc_sampler": 24.0 * n_samples + 28.0 * n_samples,
+        "k_mc_uniforms": 24.0 * n_samples,
+    }
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj.get(top_name, {}).get("dram_bytes")
+    bytes_per_launch = alg.get(top_name)
+    roofline = {"kernel": top_name, "bound": "hbm", "timed": "CUDA events on the launching stream, same K steps run one batch at a time",
+                "share_of_kernel_time": top_ms / total_kernel_ms, "ms_per_launch": per_launch_ms, "launches_per_step": launches_per_step,
                 "achieved": (bytes_per_launch / (per_launch_ms * 1e-3) / 1e9) if bytes_per_launch else None,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": traffic,
+                "traffic_source": "ncu --set full, profiles/r01_top_kernels_final.md" if traffic else None}
     roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
     if top_name == "k_mc_accumulate":
-        # not an HBM-bound kernel: its limiter is the L1/LSU gather rate (one LUT word per FADD).  Report the
-        # FP32 figure of SURVEY 8(d) beside the HBM one.
-        n_fma = float(n_samples) * T * 0.98
-        roofline["fp32"] = {"achieved_tflops": 2.0 * n_fma / (top_ms / args.steps * 1e-3) / 1e12,
-                            "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz (spec arithmetic)",
-                            "lut_reads_per_s": n_fma / (top_ms / args.steps * 1e-3)}
+        # This kernel is not HBM-bound (the LUT is L2/L1-resident): its limiter is the L1 data pipe, one 4-byte LUT word
+        # per FADD.  The HBM figures above are reported because the contract asks for them; these explain the kernel.
+        n_fma = 32.0 * 9.19e8 * (S * P_ / 180000.0)      # LUT words read per launch (ncu: 9.19e8 warp-level loads at this shape)
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        roofline["limiter"] = {"what": "L1TEX data pipe (LUT gather, table L2-resident)",
+                               "lut_words_per_s": n_fma / (per_launch_ms * 1e-3),
+                               "l1_wavefront_peak_per_s": 148 * sm_clk * 1e6,
+                               "l1_requests_per_s": n_fma / 32.0 / (per_launch_ms * 1e-3),
+                               "ncu_l1tex_throughput_pct": 88.95,
+                               "fp32_tflops_lut_adds_only": n_fma / (per_launch_ms * 1e-3) / 1e12,
+                               "fp32_peak_tflops": 148 * 128 * 2 * sm_clk * 1e6 / 1e12}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
                sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
 
