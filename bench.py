@@ -346,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- CPU baseline (bounded sample) ----------------
     cpu = None
-    if world == 1:
+    if world == 1 and not os.environ.get("LSB_BENCH_NO_CPU"):     # (the switch is for kernel A/B runs, tools/ab_variants.sh)
         n_cpu = 4096
         cpu_chain(tracks, response, 16)
         cpu_s, _ = cpu_chain(tracks, response, n_cpu)

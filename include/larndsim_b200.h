@@ -184,6 +184,11 @@ int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout* L, const 
 int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total);
 /* sample points drawn by the last lsb_tracks_current_mc call (roofline accounting) */
 int64_t lsb_tracks_current_mc_last_samples(void);
+/* interior-tick strategy of tracks_current_mc for float32 tables at unit sampling ratio: 1 = grouped path
+ * (default: offsets sorted per pair, aligned 4-word register windows shared by the samples of a group),
+ * 0 = generic gather stream.  Same results to 1e-5; the default can also be set with LSB_MC_GROUPED=0/1. */
+void lsb_mc_set_grouped(int32_t on);
+int32_t lsb_mc_get_grouped(void);
 /* larndsim/detsim.py:351-453  tracks_current(signals, pixels, tracks, response) */
 int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
                        const int32_t* pixels, int32_t P, float* signals, int32_t T,

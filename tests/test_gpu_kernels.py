@@ -295,6 +295,25 @@ def test_chain_vs_oracle(cuda, config, kind, n):
         assert r["launches"] > 10
 
 
+def test_chain_generic_mc_path_vs_oracle(cuda):
+    """The generic interior of tracks_current_mc (one table word per add; what float64 tables and non-unit sampling
+    ratios always use) on the production shape: same waveforms to 1e-5, everything downstream identical."""
+    from larndsim_b200 import _launch as ll
+    lib = ll.lib()
+    was = lib.lsb_mc_get_grouped()
+    lib.lsb_mc_set_grouped(0)
+    try:
+        assert lib.lsb_mc_get_grouped() == 0
+        for config, kind, n in (("module0", "cosmic", 200), ("2x2", "beam", 300)):
+            r = h.chain_vs_oracle(n_segments=n, config=config, seed=17, noise=True, kind=kind, exact_fractions=True)
+            assert r["tracks_equal"] and r["shape_equal"] and r["unique_equal"] and r["tpm_equal"]
+            assert r["signals_relerr"] < 1e-5
+            assert r["pixels_signals_equal"] and r["ticks_equal"] and r["adc_pattern_equal"] and r["cf_equal"]
+            assert r["adc_mismatch"] == 0 and r["n_hits"] == r["n_hits_oracle"] and r["n_hits"] > 0
+    finally:
+        lib.lsb_mc_set_grouped(was)
+
+
 def test_light_chain_medium_vs_oracle(cuda):
     """Light chain on 300 cosmic segments, 24 channels, ~1.2k ticks, 9000-tap windows shortened to 400 taps so the
     single-threaded oracle finishes in seconds: bit-exact float32 waveforms (reference add order)."""
