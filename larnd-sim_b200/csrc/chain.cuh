@@ -273,7 +273,6 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     }
     {
         cudaStream_t st = st_mc;                                   // MC stage
-        LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
         // sample workspace from an upper bound of the sample count (no host round trip inside the MC stage):
         // every (segment,pixel) takes at most len/MIN_STEP_SIZE + 1 steps
         const double bound_d = (sum_len / c->min_step_size + (double)S) * (double)P * (double)c->mc_sample_multiplier * 1.001 + 1024.0;
@@ -284,6 +283,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
                                     h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, S, h->mc_ws.p,
                                     (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, st))) return rc;
         } else {
+            LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
             long long guess = S * 4000LL;
             long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, guess);
             if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }

@@ -58,6 +58,7 @@ struct McParams {
     // sync-free operation (fused chain): the sample total stays on the device; every kernel after the scan
     // returns at once if it exceeds the capacity the caller provisioned (and *overflow is raised)
     const long long* total_dev; long long cap; int* overflow;
+    int zero_fill;            // k_mc_accumulate also stores the zeros the caller would otherwise have to pre-fill (fused chain)
 };
 #define MC_GUARD(p) do { if ((p).total_dev && *(p).total_dev > (p).cap) return; } while (0)
 
@@ -416,29 +417,59 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
 #pragma unroll
     for (int r = 0; r < NR; r++) { const int pos = lane * NR + r; s_buf[pos + (pos >> 5)] = v[r]; }
     __syncwarp();
-    // group heads: position whose 4-word block differs from its predecessor's; the head lane counts its run
+    // group heads: position whose 4-word block differs from its predecessor's.  Runs are measured with ballots (32
+    // positions at a time); the last run of a row stays "pending" (warp-uniform registers) because it may continue
+    // in the next row.
     int ng = 0;
+    int pq = 0, pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0;
+    bool pending = false;
 #pragma unroll
     for (int r = 0; r < NR; r++) {
         const int pos = r * 32 + lane;
         const int key = s_buf[pos + (pos >> 5)];                       // padding keys (INT_MAX) sort last
         const int prev = pos > 0 ? s_buf[pos - 1 + ((pos - 1) >> 5)] : OFF_IRREGULAR;
-        const bool head = pos < n && key != OFF_IRREGULAR && (prev == OFF_IRREGULAR || (prev >> 2) != (key >> 2));
+        const bool valid = pos < n && key != OFF_IRREGULAR;
+        const bool head = valid && (prev == OFF_IRREGULAR || (prev >> 2) != (key >> 2));
         const unsigned m = __ballot_sync(0xffffffffu, head);
-        if (head) {
-            const int q = key >> 2;
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, k = pos, kk = key;
-            do {
-                const int d = kk & 3;
-                c0 += d == 0; c1 += d == 1; c2 += d == 2; c3 += d == 3;
-                k++;
-                kk = k < n ? s_buf[k + (k >> 5)] : OFF_IRREGULAR;
-            } while (kk != OFF_IRREGULAR && (kk >> 2) == q);
-            GroupRec g;
-            g.q = q; g.c01 = __floats2half2_rn((float)c0, (float)c1); g.c23 = __floats2half2_rn((float)c2, (float)c3); g.pad = 0;
-            out[ng + __popc(m & ((1u << lane) - 1))] = g;
+        const int d = key & 3;
+        const unsigned m0 = __ballot_sync(0xffffffffu, valid && d == 0), m1 = __ballot_sync(0xffffffffu, valid && d == 1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, valid && d == 2), m3 = __ballot_sync(0xffffffffu, valid && d == 3);
+        const unsigned lead = m ? ((1u << (__ffs(m) - 1)) - 1u) : 0xffffffffu;     // positions continuing the pending run
+        if (pending) { pc0 += __popc(m0 & lead); pc1 += __popc(m1 & lead); pc2 += __popc(m2 & lead); pc3 += __popc(m3 & lead); }
+        if (m) {
+            if (pending) {
+                if (lane == 0) {
+                    GroupRec g;
+                    g.q = pq; g.c01 = __floats2half2_rn((float)pc0, (float)pc1); g.c23 = __floats2half2_rn((float)pc2, (float)pc3); g.pad = 0;
+                    out[ng] = g;
+                }
+                ng++;
+            }
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned higher = lane == 31 ? 0u : (m & ~((2u << lane) - 1u));
+            const unsigned upto = higher ? ((1u << (__ffs(higher) - 1)) - 1u) : 0xffffffffu;
+            const unsigned run = upto & ~below;
+            const int c0 = __popc(m0 & run), c1 = __popc(m1 & run), c2 = __popc(m2 & run), c3 = __popc(m3 & run);
+            if (head && higher) {
+                GroupRec g;
+                g.q = key >> 2; g.c01 = __floats2half2_rn((float)c0, (float)c1); g.c23 = __floats2half2_rn((float)c2, (float)c3); g.pad = 0;
+                out[ng + __popc(m & below)] = g;
+            }
+            const int src = 31 - __clz(m);                                         // last head of the row: the new pending run
+            pq = __shfl_sync(0xffffffffu, key >> 2, src);
+            pc0 = __shfl_sync(0xffffffffu, c0, src); pc1 = __shfl_sync(0xffffffffu, c1, src);
+            pc2 = __shfl_sync(0xffffffffu, c2, src); pc3 = __shfl_sync(0xffffffffu, c3, src);
+            pending = true;
+            ng += __popc(m) - 1;
         }
-        ng += __popc(m);
+    }
+    if (pending) {
+        if (lane == 0) {
+            GroupRec g;
+            g.q = pq; g.c01 = __floats2half2_rn((float)pc0, (float)pc1); g.c23 = __floats2half2_rn((float)pc2, (float)pc3); g.pad = 0;
+            out[ng] = g;
+        }
+        ng++;
     }
     __syncwarp();
     return ng;
@@ -632,7 +663,13 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
     MC_GUARD(p);
     long long pr = blockIdx.x;
     const PairRec* gp = pairs + pr;
-    if (!gp->valid) return;
+    if (!gp->valid) {
+        if (p.zero_fill) {
+            float* o = signals + ((p.seg0 + pr / p.P) * p.P + (pr % p.P)) * (long long)p.T;
+            for (int it = threadIdx.x; it < p.T; it += ACC_TPB) o[it] = 0.f;
+        }
+        return;
+    }
     __shared__ __align__(16) int s_off[ACC_CHUNK];
     __shared__ SampleRec s_rec[ACC_TPB];
     const int tid = threadIdx.x;
@@ -720,8 +757,8 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
     __syncthreads();
 
     // ---- (a) ticks >= it_first that no sample covers: the reference stores total_current = 0 ----
-    for (int it = it_first + tid; it < T; it += ACC_TPB)
-        if (n_live == 0 || it < uni_lo || it > uni_hi) out[it] = 0.f;
+    for (int it = (p.zero_fill ? 0 : it_first) + tid; it < T; it += ACC_TPB)
+        if (it < it_first || n_live - n_irr <= 0 || it < uni_lo || it > uni_hi) out[it] = 0.f;   // (c) adds the irregular samples on top
 
     // ---- (b) edge ticks: inside the union of the sample windows but outside the interior -------
     if (STRIDE > 0 && n_live - n_irr > 0) {
@@ -1000,14 +1037,15 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
     g_mc_last_samples = 0;
-    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.zero_fill = 0;
     return mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states,
                         rng_mode, p, workspace, workspace_bytes, st, 0);
 }
 
 // Fused-chain entry without host synchronisation: `workspace` must hold `lsb_tracks_current_mc_workspace_bytes`
 // of an UPPER BOUND of the sample count; *total_out (device) receives the actual count, *overflow (device)
-// is raised -- and nothing is written -- if the bound was wrong.  Cloud mode only.
+// is raised -- and nothing is written -- if the bound was wrong.  Cloud mode only.  Every element of `signals` is
+// written (zeros included): the caller does not pre-fill it.
 static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S, const int32_t* pixels,
                          int32_t P, float* signals, int32_t T, const void* response, int32_t Rx, int32_t Ry, int32_t Rt,
                          int32_t response_f64, uint64_t* rng_states, int64_t rng_stride, void* workspace,
@@ -1019,7 +1057,7 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
     p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
-    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.zero_fill = 1;
     rc = mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states, 0, p,
                       workspace, workspace_bytes, st, 0);
     if (rc) return rc;
