@@ -109,8 +109,8 @@ struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2*
 // latency every tick.  Each thread therefore keeps small windows of its inputs in shared memory
 // ([slot][thread], conflict-free) and refills them with FEE_NBUF / FEE_QBUF independent loads at a time.
 #define FEE_TRIG_TPB 64
-#define FEE_NBUF 32
-#define FEE_QBUF 16
+#define FEE_NBUF 64
+#define FEE_QBUF 32
 
 // fee.py:548-655 as ONE flat loop: every iteration evaluates the CSA FIR at the pixel's current tick and
 // then does the work of the state it is in (watching for a threshold crossing, or integrating after one),
@@ -187,6 +187,52 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
             // and per-lane refills would expose one memory latency per lane instead of one per warp
             const bool need = !inl && ((idx + 6 > nbase + FEE_NBUF) || (fp.BR > 0 && (ic < qbase || ic >= qbase + FEE_QBUF)));
             if (__any_sync(__activemask(), need) && !inl) { refill_n(idx); if (fp.BR > 0) refill_q(ic); }
+        }
+        if (PRE && !inl && fp.BR > 0 && interval >= 1 && ic >= qbase && idx >= nbase) {
+            // Fast paths.  While no reset lies inside the tap window the FIR values are the pre-computed ones and a tick
+            // of either state is a handful of instructions on the staged windows -- same operations, same order as the
+            // general step below, without its bookkeeping.
+            const int cs = ic - cs_back;
+            if (last_reset <= (cs < 0 ? 0 : cs)) {
+                const double* qb = qbuf + (ic - qbase) * FEE_TRIG_TPB;
+                int nq = qbase + FEE_QBUF - ic;
+                if (Tq - ic < nq) nq = Tq - ic;
+                if (!integrating) {
+                    // watching for a threshold crossing (:559-593): two draws per tick
+                    int nf = (nbase + FEE_NBUF - idx) >> 1;
+                    if (((NMAX - idx) >> 1) < nf) nf = (NMAX - idx) >> 1;
+                    if (nq < nf) nf = nq;
+                    if (Tt - ic < nf) nf = Tt - ic;
+                    if (iadc < max_hits && nf > 0) {
+                        const float* nb = nbuf + (idx - nbase) * FEE_TRIG_TPB;
+                        const double su = fp.unc_noise, sd = fp.disc_noise;
+                        bool trig = false;
+                        int k = 0;
+                        while (k < nf) {
+                            const double q = qb[k * FEE_TRIG_TPB];
+                            q_sum += q; true_q += q;
+                            const double q_noise = (su == 0.0 ? 0.0 : (double)nb[(2 * k) * FEE_TRIG_TPB] * su) * fp.e;
+                            const double disc_noise = (sd == 0.0 ? 0.0 : (double)nb[(2 * k + 1) * FEE_TRIG_TPB] * sd) * fp.e;
+                            if (adc_busy > 0) adc_busy--;
+                            k++;
+                            if (q_sum + q_noise >= thr + disc_noise && adc_busy == 0) { trig = true; break; }
+                        }
+                        ic += k; idx += 2 * k;
+                        if (trig) { integrate_end = ic - 1 + interval; integrating = true; }
+                        continue;
+                    }
+                } else {
+                    // integrating after a crossing (:595-613): all but the last tick of the window, which the general
+                    // step takes together with the read-out
+                    int nf = integrate_end - ic;
+                    if (nq < nf) nf = nq;
+                    if (nf > 0) {
+                        for (int k = 0; k < nf; k++) { const double q = qb[k * FEE_TRIG_TPB]; q_sum += q; true_q += q; }
+                        ic += nf;
+                        continue;
+                    }
+                }
+            }
         }
         if (!integrating) {
             if (!(ic < Tt || adc_busy > 0)) break;                       // :559
