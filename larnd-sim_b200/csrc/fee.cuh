@@ -109,6 +109,13 @@ struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2*
 // latency every tick.  Each thread therefore keeps small windows of its inputs in shared memory
 // ([slot][thread], conflict-free) and refills them with FEE_NBUF / FEE_QBUF independent loads at a time.
 #define FEE_TRIG_TPB 64
+// The state machine is latency-bound (a serial chain per pixel) and a batch has far fewer pixels than the GPU has
+// thread slots: only the first FEE_PPW lanes of each warp carry a pixel, so the pixels spread over 32/FEE_PPW times
+// more warps and every scheduler has several chains to interleave (and fewer pixels in different states per warp).
+#ifndef FEE_PPW
+#define FEE_PPW 8
+#endif
+#define FEE_TRIG_PIX (FEE_TRIG_TPB / 32 * FEE_PPW)          // pixels per block
 #define FEE_NBUF 64
 #define FEE_QBUF 32
 
@@ -123,15 +130,16 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
                                                       double time_padding, unsigned long long* __restrict__ rng_states,
                                                       const double* __restrict__ thresholds, FeeWindow* __restrict__ windows,
                                                       int* __restrict__ n_windows) {
-    __shared__ float s_n[PRE ? FEE_NBUF * FEE_TRIG_TPB : 1];
-    __shared__ double s_q[PRE ? FEE_QBUF * FEE_TRIG_TPB : 1];
-    const long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (ip >= U) return;
+    __shared__ float s_n[PRE ? FEE_NBUF * FEE_TRIG_PIX : 1];
+    __shared__ double s_q[PRE ? FEE_QBUF * FEE_TRIG_PIX : 1];
+    const int slot = (threadIdx.x >> 5) * FEE_PPW + (threadIdx.x & 31);       // pixel slot of this thread within the block
+    const long long ip = blockIdx.x * (long long)FEE_TRIG_PIX + slot;
+    if ((threadIdx.x & 31) >= FEE_PPW || ip >= U) return;
     const double* curre = pixels_signals + ip * Tt;
     const double* qrow = PRE ? pre.q_pre + ip * pre.Tq : nullptr;
     const float* ncol = PRE ? pre.nrm + ip : nullptr;
-    float* nbuf = s_n + (PRE ? threadIdx.x : 0);
-    double* qbuf = s_q + (PRE ? threadIdx.x : 0);
+    float* nbuf = s_n + (PRE ? slot : 0);
+    double* qbuf = s_q + (PRE ? slot : 0);
     const int cs_back = (int)ceil(fp.back);          // floor(ic - back) = ic - ceil(back) for integer ic
     const int NMAX = pre.NMAX, Tq = pre.Tq;
     const int interval = (int)fp.interval, reset_ticks = (int)fp.reset_ticks, busy_ticks = (int)fp.busy_ticks;
@@ -144,12 +152,12 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
     auto refill_n = [&](int i) {
         nbase = i;
 #pragma unroll
-        for (int k = 0; k < FEE_NBUF; k++) nbuf[k * FEE_TRIG_TPB] = (i + k < NMAX) ? __ldg(ncol + (long long)(i + k) * U) : 0.f;
+        for (int k = 0; k < FEE_NBUF; k++) nbuf[k * FEE_TRIG_PIX] = (i + k < NMAX) ? __ldg(ncol + (long long)(i + k) * U) : 0.f;
     };
     auto refill_q = [&](int ic) {
         qbase = ic;
 #pragma unroll
-        for (int k = 0; k < FEE_QBUF; k++) qbuf[k * FEE_TRIG_TPB] = (ic + k < Tq) ? __ldg(qrow + ic + k) : 0.0;
+        for (int k = 0; k < FEE_QBUF; k++) qbuf[k * FEE_TRIG_PIX] = (ic + k < Tq) ? __ldg(qrow + ic + k) : 0.0;
     };
     auto draw = [&](double sigma) -> double {
         if (PRE && !inl && idx >= NMAX) {            // more draws than provisioned: continue inline from the last snapshot
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
         const int i = idx++;
         if (sigma == 0.0) return 0.0;
         if (i >= nbase + FEE_NBUF) refill_n(i);
-        return (double)nbuf[(i - nbase) * FEE_TRIG_TPB] * sigma;
+        return (double)nbuf[(i - nbase) * FEE_TRIG_PIX] * sigma;
     };
     auto fir = [&](int ic, int last_reset) -> double {
         if (PRE && fp.BR > 0) {
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
             if (last_reset <= cs) {
                 if (ic >= Tq) return 0.0;
                 if (ic < qbase || ic >= qbase + FEE_QBUF) refill_q(ic);
-                return qbuf[(ic - qbase) * FEE_TRIG_TPB];
+                return qbuf[(ic - qbase) * FEE_TRIG_PIX];
             }
         }
         return fee_fir(curre, ic, last_reset, Tt, fp);
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
             // general step below, without its bookkeeping.
             const int cs = ic - cs_back;
             if (last_reset <= (cs < 0 ? 0 : cs)) {
-                const double* qb = qbuf + (ic - qbase) * FEE_TRIG_TPB;
+                const double* qb = qbuf + (ic - qbase) * FEE_TRIG_PIX;
                 int nq = qbase + FEE_QBUF - ic;
                 if (Tq - ic < nq) nq = Tq - ic;
                 if (!integrating) {
@@ -204,15 +212,15 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
                     if (nq < nf) nf = nq;
                     if (Tt - ic < nf) nf = Tt - ic;
                     if (iadc < max_hits && nf > 0) {
-                        const float* nb = nbuf + (idx - nbase) * FEE_TRIG_TPB;
+                        const float* nb = nbuf + (idx - nbase) * FEE_TRIG_PIX;
                         const double su = fp.unc_noise, sd = fp.disc_noise;
                         bool trig = false;
                         int k = 0;
                         while (k < nf) {
-                            const double q = qb[k * FEE_TRIG_TPB];
+                            const double q = qb[k * FEE_TRIG_PIX];
                             q_sum += q; true_q += q;
-                            const double q_noise = (su == 0.0 ? 0.0 : (double)nb[(2 * k) * FEE_TRIG_TPB] * su) * fp.e;
-                            const double disc_noise = (sd == 0.0 ? 0.0 : (double)nb[(2 * k + 1) * FEE_TRIG_TPB] * sd) * fp.e;
+                            const double q_noise = (su == 0.0 ? 0.0 : (double)nb[(2 * k) * FEE_TRIG_PIX] * su) * fp.e;
+                            const double disc_noise = (sd == 0.0 ? 0.0 : (double)nb[(2 * k + 1) * FEE_TRIG_PIX] * sd) * fp.e;
                             if (adc_busy > 0) adc_busy--;
                             k++;
                             if (q_sum + q_noise >= thr + disc_noise && adc_busy == 0) { trig = true; break; }
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
                     int nf = integrate_end - ic;
                     if (nq < nf) nf = nq;
                     if (nf > 0) {
-                        for (int k = 0; k < nf; k++) { const double q = qb[k * FEE_TRIG_TPB]; q_sum += q; true_q += q; }
+                        for (int k = 0; k < nf; k++) { const double q = qb[k * FEE_TRIG_PIX]; q_sum += q; true_q += q; }
                         ic += nf;
                         continue;
                     }
@@ -573,11 +581,11 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
             k_fee_rng_normals<<<lsb_blocks(U * nmax, 256), 256, 0, st>>>(uu, nrm, U * nmax);
             LSB_LAUNCH_CHECK("k_fee_rng_normals");
             pre.q_pre = q_pre; pre.nrm = nrm; pre.snaps = snaps;
-            k_fee_trigger<true><<<lsb_blocks(U, FEE_TRIG_TPB), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
+            k_fee_trigger<true><<<lsb_blocks(U, FEE_TRIG_PIX), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
                                                                  adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,
                                                                  pixel_thresholds, windows, n_windows);
         } else {
-            k_fee_trigger<false><<<lsb_blocks(U, FEE_TRIG_TPB), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
+            k_fee_trigger<false><<<lsb_blocks(U, FEE_TRIG_PIX), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
                                                                     adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,
                                                                     pixel_thresholds, windows, n_windows);
         }

@@ -14,7 +14,7 @@ f="gpurun_out/ab_"+os.path.basename(v)[:-3]+".json"
 try:
     d=json.loads(open(f).read().strip().splitlines()[-1])
     k=d["kernels"]
-    print(v, "ms/step %.2f unpiped %.2f | acc %.3f sort %.3f sampler %.3f" % (d["ms_per_step"], d["ms_per_step_unpipelined"], k.get("k_mc_accumulate",{}).get("ms_per_step",0), k.get("k_mc_sort",{}).get("ms_per_step",0), k.get("k_mc_sampler",{}).get("ms_per_step",0)))
+    print(v, "ms/step %.2f unpiped %.2f |" % (d["ms_per_step"], d["ms_per_step_unpipelined"]), " ".join("%s %.3f" % (n.replace("k_", ""), x["ms_per_step"]) for n, x in list(k.items())[:8]))
 except Exception as e:
     print(v, "FAILED", e)
 PY
