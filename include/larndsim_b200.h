@@ -313,6 +313,52 @@ int lsb_chain_run_host_async(lsb_chain* h, void* tracks_host, int64_t S, int32_t
                              double* adc_ticks_host, int64_t U_cap);
 int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out);
 
+/* ---- hit compaction + LArPix packets ---------------------------------------------------- */
+/* One output packet.  packet_type uses the codes of larpix.format.hdf5format (0 data, 4 timestamp, 6 sync,
+ * 7 trigger); sub_type is the sync type ('S') or trigger type (0x02) byte; timestamp_s is the float
+ * timestamp of a TimestampPacket [s]; parity is Packet_v2.assign_parity() of a data packet. */
+typedef struct lsb_packet {
+    uint8_t packet_type, io_group, io_channel, chip_id, channel_id, dataword, first_packet, parity, sub_type, pad[3];
+    uint32_t receipt_timestamp;
+    uint64_t timestamp;
+    double timestamp_s;
+} lsb_packet;
+/* Readout constants of larndsim.consts.detector / light / units that fee.export_to_hdf5 reads (host arrays):
+ * TILE_MAP [2][ntx][nty]; TILE_ORIENTATIONS as the sign of the x / y axis per tile id; PIXEL_CONNECTION_DICT as
+ * chip * 1000 + channel per rotated in-tile pixel (-1: absent); TILE_CHIP_TO_IO as io_group * 1000 + io_channel
+ * per (tile id, chip) (-1: absent); MODULE_TO_IO_GROUPS per module id; io_groups = the groups that receive the
+ * per-event timestamp / sync packets (already restricted to i_mod); bad_channels = sorted keys
+ * ((io_group * 1000 + io_channel) * 1000 + chip) * 64 + channel. */
+typedef struct lsb_readout_tables {
+    double clock_cycle, adc_pedestal, mus, s;
+    int64_t clock_reset_period;
+    int32_t light_trig_mode;
+    int32_t n_pixels[2], n_pixels_per_tile[2], n_tiles_xy[2];
+    int32_t n_tiles, n_modules, max_groups, n_io_groups, n_bad;
+    const int32_t* tile_map;
+    const int32_t* tile_orientation;
+    const int32_t* pixel_connection;
+    const int32_t* tile_chip_to_io;
+    const int32_t* module_n_groups;
+    const int32_t* module_io_groups;
+    const int32_t* io_groups;
+    const int64_t* bad_channels;
+} lsb_readout_tables;
+/* larndsim/fee.py:84-359  export_to_hdf5(event_id_list, adc_list, adc_ticks_list, unique_pix, current_fractions,
+ * track_ids, traj_ids, filename, event_start_times, light_trigger_*, bad_channels, i_mod) without the file I/O:
+ * the packets in the reference's order and the mc_packets_assn rows (n_assn = ASSOCIATION_COUNT_TO_STORE).
+ * Device arrays: event_id i8[U,A], adc (digitised) f8[U,A], adc_ticks f8[U,A], unique_pix i4[U],
+ * current_fractions f8[U,A,K], track_ids / traj_ids i8[U,K]; pix_t0_ticks[i] = int(event_start_times[inv[i]] /
+ * CLOCK_CYCLE) and pix_t0_us[i] = event_start_times[inv[i]] with inv the rank of event_id[i,0] among the sorted
+ * unique events (fee.py:136-137); light triggers (times [us], event, module).  *n_packets receives the packet
+ * count; if it exceeds cap_packets nothing is written and the call fails (retry with that capacity). */
+int lsb_export_packets(const lsb_readout_tables* rt, int64_t U, int32_t A, int32_t K, const int64_t* event_id,
+                       const double* adc, const double* adc_ticks, const int32_t* unique_pix, const double* current_fractions,
+                       const int64_t* track_ids, const int64_t* traj_ids, const int64_t* pix_t0_ticks, const double* pix_t0_us,
+                       int32_t n_trig, const double* trig_times, const int64_t* trig_event, const int32_t* trig_module,
+                       int64_t cap_packets, lsb_packet* packets, int64_t* assn_event, int64_t* assn_segment, double* assn_fraction,
+                       int64_t* assn_traj, double* assn_fraction_traj, int32_t n_assn, int64_t* n_packets, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,6 @@
-"""Drop-in for the device part of ``larndsim.fee`` (reference: larndsim/fee.py:499-655).
-Packet export (fee.py:30-497) is host I/O and out of scope."""
+"""Drop-in for ``larndsim.fee``: the device kernels (reference: larndsim/fee.py:499-655) and the hit -> LArPix
+packet builder of ``export_to_hdf5`` (fee.py:84-359; GPU: packets.py / csrc/packets.cuh).  Writing the HDF5 file
+itself needs the third-party ``larpix`` and ``h5py`` packages and is done only when they are importable."""
 import ctypes as C
 
 import numpy as np
@@ -53,3 +54,65 @@ def get_adc_values(pixels_signals, pixels_signals_tracks, time_ticks, adc_list, 
                                          C.c_int32(tt.shape[0]), adc.c, tks.c, C.c_int32(A), C.c_double(float(time_padding)),
                                          st.c, C.c_int64(n_rng), cf.c, thr.c, _l.stream()), "get_adc_values")
     _l.finish(adc, tks, cf, st)
+
+
+def export_to_hdf5(event_id_list, adc_list, adc_ticks_list, unique_pix, current_fractions, track_ids, traj_ids, filename,
+                   event_start_times, light_trigger_times=None, light_trigger_event_id=None, light_trigger_modules=None,
+                   bad_channels=None, i_mod=-1):
+    """``export_to_hdf5(...)`` (fee.py:84-359) with the reference's arguments.  The packets (data, timestamp, sync
+    and trigger packets in the reference's order, with its clock-rollover logic) and the ``mc_packets_assn`` rows
+    are built on the GPU and returned as ``(packets, packets_mc_ds)``: ``packets`` is a structured array
+    (``packets.PACKET_DTYPE``) instead of a list of ``larpix`` objects.  If ``filename`` is given and ``larpix`` and
+    ``h5py`` are importable the file is written like the reference does (larpix ``hdf5format`` + ``mc_packets_assn``)."""
+    from . import packets as _p
+    tables = _p.ReadoutTables.from_consts(i_mod=i_mod)
+    packets, ds = _p.export_packets(tables, event_id_list, adc_list, adc_ticks_list, unique_pix, current_fractions, track_ids,
+                                    traj_ids, event_start_times, light_trigger_times, light_trigger_event_id, light_trigger_modules,
+                                    bad_channels=bad_channels)
+    if filename and len(packets):
+        try:
+            import h5py                                                  # noqa: F401
+            from larpix.format import hdf5format                         # noqa: F401
+        except ImportError:
+            return packets, ds
+        _write_larpix_file(filename, packets, ds)
+    return packets, ds
+
+
+def _write_larpix_file(filename, packets, ds):
+    """fee.py:287-289 and :344-357 -- turn the records into larpix packet objects and append the truth table."""
+    import h5py
+    from larpix.packet import Packet_v2, TimestampPacket, TriggerPacket, SyncPacket, PacketCollection
+    from larpix.key import Key
+    from larpix.format import hdf5format
+    from . import packets as _p
+    from . import consts as _consts
+    out = []
+    for r in packets:
+        t = int(r["packet_type"])
+        if t == _p.PT_DATA:
+            p = Packet_v2()
+            p.dataword = int(r["dataword"]); p.timestamp = int(r["timestamp"])
+            p.chip_key = "%i-%i-%i" % (r["io_group"], r["io_channel"], r["chip_id"])
+            p.channel_id = int(r["channel_id"]); p.receipt_timestamp = int(r["receipt_timestamp"])
+            p.packet_type = 0; p.first_packet = 1
+            p.assign_parity()
+        elif t == _p.PT_TIMESTAMP:
+            p = TimestampPacket(timestamp=float(r["timestamp_s"]))
+            p.chip_key = Key(int(r["io_group"]), 0, 0)
+        elif t == _p.PT_SYNC:
+            p = SyncPacket(sync_type=bytes([int(r["sub_type"])]), timestamp=int(r["timestamp"]), io_group=int(r["io_group"]))
+        else:
+            p = TriggerPacket(io_group=int(r["io_group"]), trigger_type=bytes([int(r["sub_type"])]), timestamp=int(r["timestamp"]))
+        out.append(p)
+    hdf5format.to_file(filename, PacketCollection(out, read_id=0, message=""), workers=1)
+    d = _consts.provider().detector
+    with h5py.File(filename, "a") as f:
+        if "mc_packets_assn" not in f.keys():
+            f.create_dataset("mc_packets_assn", data=ds, maxshape=(None,))
+        else:
+            f["mc_packets_assn"].resize((f["mc_packets_assn"].shape[0] + ds.shape[0]), axis=0)
+            f["mc_packets_assn"][-ds.shape[0]:] = ds
+        for key, val in (("vdrift", d.V_DRIFT), ("long_diff", d.LONG_DIFF), ("tran_diff", d.TRAN_DIFF),
+                         ("lifetime", d.ELECTRON_LIFETIME), ("drift_length", d.DRIFT_LENGTH)):
+            f["configs"].attrs[key] = val

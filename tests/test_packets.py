@@ -33,3 +33,101 @@ def test_parity_is_odd_over_the_word():
         word = (chip << 2) | (ch << 10) | (ts << 16) | (1 << 47) | (dw << 48)
         p = po.data_parity(chip, ch, ts, 1, dw)
         assert (bin(word).count("1") + p) % 2 == 1
+
+
+# ---------------------------------------------------------------------------------------- GPU
+def _gpu_export(z, device_inputs=False):
+    import torch
+    from larndsim_b200 import packets as lp
+    tables = lp.ReadoutTables.from_dict(pu.tables_from_npz(z))
+    inp = pu.inputs(z)
+    if device_inputs:
+        for k in ("event_id_list", "adc_list", "adc_ticks_list", "unique_pix", "current_fractions", "track_ids", "traj_ids"):
+            inp[k] = torch.from_numpy(np.ascontiguousarray(inp[k])).cuda()
+    return lp.export_packets(tables, bad_channels=pu.bad_channels_from_npz(z), **inp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", pu.CASES)
+def test_gpu_packets_identical_to_oracle_and_reference(cuda, name):
+    from larndsim_b200 import _launch as ll
+    z = pu.load(name)
+    launches0 = ll.lib().lsb_launch_count()
+    packets, ds = _gpu_export(z, device_inputs=(name == "2x2"))
+    assert ll.lib().lsb_launch_count() - launches0 >= 8
+    o_packets, o_ds = po.export_packets(pu.tables_from_npz(z), bad_channels=pu.bad_channels_from_npz(z), **pu.inputs(z))
+    assert packets.dtype == o_packets.dtype and len(packets) == len(o_packets)
+    for f in packets.dtype.names:
+        assert np.array_equal(packets[f], o_packets[f]), f
+    for f in ds.dtype.names:
+        assert np.array_equal(ds[f], o_ds[f]), f
+    pu.check_against_reference(packets, ds, z)
+
+
+@pytest.mark.gpu
+def test_gpu_packets_edge_cases(cuda):
+    from larndsim_b200 import packets as lp
+    z = pu.load("module0")
+    t = pu.tables_from_npz(z)
+    tables = lp.ReadoutTables.from_dict(t)
+    inp = pu.inputs(z)
+    # no pixels at all
+    empty = {k: (v[:0] if k not in ("event_start_times", "light_trigger_times", "light_trigger_event_id", "light_trigger_modules") else v)
+             for k, v in inp.items()}
+    packets, ds = lp.export_packets(tables, **empty)
+    assert len(packets) == 0 and len(ds) == 0
+    # pixels but no hit above the pedestal
+    quiet = dict(inp)
+    quiet["adc_list"] = np.full_like(inp["adc_list"], t["adc_pedestal"])
+    packets, ds = lp.export_packets(tables, **quiet)
+    assert len(packets) == 0
+    # no light triggers: same as the oracle
+    nolight = dict(inp, light_trigger_times=None, light_trigger_event_id=None, light_trigger_modules=None)
+    packets, ds = lp.export_packets(tables, **nolight)
+    o_packets, o_ds = po.export_packets(t, **nolight)
+    assert len(packets) == len(o_packets) and all(np.array_equal(packets[f], o_packets[f]) for f in packets.dtype.names)
+    assert all(np.array_equal(ds[f], o_ds[f]) for f in ds.dtype.names)
+    # a single pixel, every ADC slot used
+    one = {k: (v[:1].copy() if k not in ("event_start_times", "light_trigger_times", "light_trigger_event_id", "light_trigger_modules") else v)
+           for k, v in inp.items()}
+    one["adc_list"][:] = t["adc_pedestal"] + 40
+    one["adc_ticks_list"][0] = np.arange(one["adc_list"].shape[1]) * 3.1
+    one["event_start_times"] = inp["event_start_times"][:1]
+    packets, ds = lp.export_packets(tables, **one)
+    o_packets, o_ds = po.export_packets(t, **one)
+    assert (packets["packet_type"] == po.PT_DATA).sum() == one["adc_list"].shape[1]
+    assert all(np.array_equal(packets[f], o_packets[f]) for f in packets.dtype.names)
+    assert all(np.array_equal(ds[f], o_ds[f]) for f in ds.dtype.names)
+
+
+@pytest.mark.gpu
+def test_gpu_packets_from_the_chain_output(cuda):
+    """End of the charge chain: hits of a simulated batch -> packets; every hit above the pedestal becomes exactly one
+    data packet with its ADC word, timestamps are non-decreasing within a pixel, truth rows carry the batch's segments."""
+    import helpers as h
+    from larndsim_b200 import chain as lchain, consts as lc, synth, _launch as ll, packets as lp
+    tracks = h.production_tracks(300, "module0", 21, "cosmic")
+    mod = lc.load_snapshot("module0")
+    ch = lchain.Chain(tracks.dtype, synth.response_lut(mod.detector))
+    res = ch.run(ll.DeviceRecords(host=tracks), rng_seed=3, n_events=1)
+    z = pu.load("module0")
+    t = pu.tables_from_npz(z)
+    tables = lp.ReadoutTables.from_dict(t)
+    U = res.n_unique_pixels
+    A, K = res.adc_digit.shape[1], res.track_pixel_map.shape[1]
+    ev = np.zeros((U, A), dtype=np.int64)
+    traj = np.where(res.track_pixel_map.cpu().numpy() >= 0, res.track_pixel_map.cpu().numpy() // 7, -1)
+    packets, ds = lp.export_packets(tables, ev, res.adc_digit, res.adc_ticks_list, res.unique_pix, res.current_fractions,
+                                    res.track_pixel_map, traj, np.array([1000.0]))
+    adc = res.adc_digit.cpu().numpy()
+    n_hits = int((adc > t["adc_pedestal"]).sum())
+    data = packets["packet_type"] == po.PT_DATA
+    assert n_hits > 50 and data.sum() == n_hits
+    assert np.array_equal(np.sort(packets["dataword"][data]), np.sort(adc[adc > t["adc_pedestal"]].astype(np.uint8)))
+    o_packets, o_ds = po.export_packets(t, ev, adc, res.adc_ticks_list.cpu().numpy(), res.unique_pix.cpu().numpy(),
+                                        res.current_fractions.cpu().numpy(), res.track_pixel_map.cpu().numpy(), traj, np.array([1000.0]))
+    assert all(np.array_equal(packets[f], o_packets[f]) for f in packets.dtype.names)
+    assert all(np.array_equal(ds[f], o_ds[f]) for f in ds.dtype.names)
+    seg = ds["segment_ids"][data]
+    assert ((seg >= -1) & (seg < len(tracks))).all() and (seg[:, 0] >= 0).all()
+    ch.close()
