@@ -58,11 +58,13 @@ def load_snapshot(name):
     for ns, key in ((detector, "detector"), (light, "light"), (sim, "sim"), (physics, "physics"), (units, "units")):
         ns.__dict__.clear()
         for k, v in snap[key].items():
-            if isinstance(v, list):
+            if isinstance(v, list) and k != "PIXEL_CONNECTION_DICT":
                 v = np.array(v)
             setattr(ns, k, v)
     detector.TIME_TICKS = np.linspace(detector.TIME_INTERVAL[0], detector.TIME_INTERVAL[1], int(detector.N_TIME_TICKS))
     detector.N_PIXELS = tuple(int(v) for v in detector.N_PIXELS)
+    if hasattr(detector, "PIXEL_CONNECTION_DICT"):          # stored as rows [x, y, chip, channel]
+        detector.PIXEL_CONNECTION_DICT = {(r[0], r[1]): (r[2], r[3]) for r in detector.PIXEL_CONNECTION_DICT}
     _loaded = name
     return sys.modules[__name__]
 

@@ -130,8 +130,10 @@ class ReadoutTables:
         """Read the tables from ``larndsim.consts`` (or the provider set with ``consts.use``) now."""
         p = provider or _consts.provider()
         d, li, si, un = p.detector, p.light, p.sim, p.units
-        from . import fee as _fee
-        ped = float(np.asarray(_fee.digitize(np.zeros(1)))[0])
+        # digitize(0) (fee.py:499-515): the ADC word of an empty pixel, a constant of the configuration
+        mV = un.mV
+        ped = float(min(np.around(max(0.0 + d.V_PEDESTAL * mV - d.V_CM * mV, 0) * d.ADC_COUNTS / (d.V_REF * mV - d.V_CM * mV)),
+                        d.ADC_COUNTS - 1))
         return cls(d.CLOCK_CYCLE, d.CLOCK_RESET_PERIOD, li.LIGHT_TRIG_MODE, ped, un.mus, un.s, d.N_PIXELS, d.N_PIXELS_PER_TILE,
                    d.MODULE_TO_IO_GROUPS, d.TILE_MAP, d.TILE_ORIENTATIONS, d.PIXEL_CONNECTION_DICT, d.TILE_CHIP_TO_IO,
                    si.MAX_TRACKS_PER_PIXEL, si.ASSOCIATION_COUNT_TO_STORE, i_mod=i_mod)

@@ -131,3 +131,15 @@ def test_gpu_packets_from_the_chain_output(cuda):
     seg = ds["segment_ids"][data]
     assert ((seg >= -1) & (seg < len(tracks))).all() and (seg[:, 0] >= 0).all()
     ch.close()
+
+
+def test_readout_tables_from_the_config_snapshot_match_the_reference_run():
+    """configs/module0.json (derived from the reference YAMLs) gives the tables the reference's export used."""
+    from larndsim_b200 import consts as lc, packets as lp
+    z = pu.load("module0")
+    a = lp.ReadoutTables.from_dict(pu.tables_from_npz(z))
+    b = lp.ReadoutTables.from_consts(lc.load_snapshot("module0"))
+    for name in ("_tile_map", "_tile_orient", "_pix_conn", "_tile_chip_io", "_module_ng", "_module_io", "_io_groups"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for f in ("clock_cycle", "adc_pedestal", "mus", "s", "clock_reset_period", "light_trig_mode", "n_tiles", "n_modules"):
+        assert getattr(a._c, f) == getattr(b._c, f), f

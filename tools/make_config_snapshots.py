@@ -23,7 +23,9 @@ DET = ["LAR_DENSITY", "E_FIELD", "V_DRIFT", "ELECTRON_LIFETIME", "LONG_DIFF", "T
        "SAMPLED_POINTS", "RESPONSE_SAMPLING", "RESPONSE_BIN_SIZE", "DEFAULT_PLANE_INDEX", "N_PIXELS",
        "N_PIXELS_PER_TILE", "PIXEL_PITCH", "DISCRIMINATION_THRESHOLD", "ADC_HOLD_DELAY", "ADC_BUSY_DELAY",
        "RESET_CYCLES", "CLOCK_CYCLE", "GAIN", "BUFFER_RISETIME", "V_CM", "V_REF", "V_PEDESTAL", "ADC_COUNTS",
-       "RESET_NOISE_CHARGE", "UNCORRELATED_NOISE_CHARGE", "DISCRIMINATOR_NOISE", "MODULE_TO_TPCS"]
+       "RESET_NOISE_CHARGE", "UNCORRELATED_NOISE_CHARGE", "DISCRIMINATOR_NOISE", "MODULE_TO_TPCS",
+       # readout tables of the packet builder (fee.export_to_hdf5)
+       "CLOCK_RESET_PERIOD", "MODULE_TO_IO_GROUPS", "TILE_MAP", "TILE_ORIENTATIONS", "TILE_CHIP_TO_IO"]
 LIGHT = ["LIGHT_SIMULATED", "ENABLE_LUT_SMEARING", "N_OP_CHANNEL", "OP_CHANNEL_EFFICIENCY", "OP_CHANNEL_TO_TPC",
          "SCINT_PRESCALE", "W_PH", "LIGHT_TICK_SIZE", "LIGHT_WINDOW", "SINGLET_FRACTION", "TAU_S", "TAU_T",
          "LIGHT_GAIN", "SIPM_RESPONSE_MODEL", "LIGHT_RESPONSE_TIME", "LIGHT_OSCILLATION_PERIOD",
@@ -33,7 +35,7 @@ SIM = ["BATCH_SIZE", "EVENT_BATCH_SIZE", "EVENT_SEPARATOR", "MAX_TRACKS_PER_PIXE
        "MC_SAMPLE_MULTIPLIER", "ASSOCIATION_COUNT_TO_STORE", "MAX_ADC_VALUES", "MAX_MC_TRUTH_IDS",
        "MC_TRUTH_THRESHOLD"]
 PHYS = ["BOX_ALPHA", "BOX_BETA", "BIRKS_Ab", "BIRKS_kb", "W_ION", "BOX", "BIRKS"]
-UNITS = ["e", "mV", "ns", "mus", "cm", "mm"]
+UNITS = ["e", "mV", "ns", "mus", "cm", "mm", "s"]
 
 CONFIGS = {
     # name: (detector yaml, pixel layout, sim yaml, i_module)
@@ -74,6 +76,9 @@ def main():
                 "physics": {k: jsonable(getattr(consts.physics, k)) for k in PHYS},
                 "units": {k: jsonable(getattr(consts.units, k)) for k in UNITS}}
         snap["detector"]["N_TIME_TICKS"] = int(len(consts.detector.TIME_TICKS))
+        # {(x, y): (chip, channel)} -> rows [x, y, chip, channel] (JSON has no tuple keys)
+        snap["detector"]["PIXEL_CONNECTION_DICT"] = sorted([int(k[0]), int(k[1]), int(v[0]), int(v[1])]
+                                                           for k, v in consts.detector.PIXEL_CONNECTION_DICT.items())
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(snap, f, indent=0, separators=(",", ":"))
         print(name, "TPCs", consts.detector.TPC_BORDERS.shape[0], "N_PIXELS", consts.detector.N_PIXELS,
