@@ -313,6 +313,14 @@ int lsb_chain_run_host_async(lsb_chain* h, void* tracks_host, int64_t S, int32_t
                              double* adc_ticks_host, int64_t U_cap);
 int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out);
 
+/* ---- static key -> value table ----------------------------------------------------------- */
+/* larndsim/util/cuda_dict.py:1-230  CudaDict lookup / contains (per-pixel thresholds and gains,
+ * cli/simulate_pixels.py:1080-1100): out[i] = value of query[i] or *default_host; exists[i] = 1 if present.
+ * keys_sorted: int32 ascending, unique; values: n elements of value_bytes (4 or 8) each, copied bit for bit. */
+int lsb_table_lookup(const int32_t* keys_sorted, const void* values, int64_t n, int32_t value_bytes,
+                     const int32_t* query, int64_t nq, const void* default_host, void* out, uint8_t* exists,
+                     void* stream);
+
 /* ---- hit compaction + LArPix packets ---------------------------------------------------- */
 /* One output packet.  packet_type uses the codes of larpix.format.hdf5format (0 data, 4 timestamp, 6 sync,
  * 7 trigger); sub_type is the sync type ('S') or trigger type (0x02) byte; timestamp_s is the float

@@ -248,3 +248,49 @@ LSB_EXPORT int lsb_digitize(const lsb_consts* c, const double* integral_list, co
     LSB_LAUNCH_CHECK("k_digitize");
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// static key -> value table (larndsim/util/cuda_dict.py: per-pixel thresholds and gains,
+// cli/simulate_pixels.py:1080-1100).  The reference keeps an open-addressing hash table; the keys are
+// fixed after loading, so a sorted key array + one binary search per query gives the same answers
+// (value of the key, or the default) without atomics or probing sequences.
+// ---------------------------------------------------------------------------------------
+template <typename V>
+__global__ void k_table_lookup(const int32_t* __restrict__ keys, const V* __restrict__ values, long long n,
+                               const int32_t* __restrict__ query, long long nq, V dflt, V* __restrict__ out,
+                               uint8_t* __restrict__ exists) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int32_t q = query[i];
+    long long lo = 0, hi = n - 1, at = -1;
+    while (lo <= hi) {
+        const long long mid = (lo + hi) >> 1;
+        const int32_t k = __ldg(keys + mid);
+        if (k == q) { at = mid; break; }
+        if (k < q) lo = mid + 1; else hi = mid - 1;
+    }
+    if (out) out[i] = at >= 0 ? values[at] : dflt;
+    if (exists) exists[i] = at >= 0 ? 1 : 0;
+}
+LSB_EXPORT int lsb_table_lookup(const int32_t* keys_sorted, const void* values, int64_t n, int32_t value_bytes,
+                                const int32_t* query, int64_t nq, const void* default_host, void* out, uint8_t* exists,
+                                void* stream) {
+    if (nq == 0) return 0;
+    LSB_REQUIRE(query && (n == 0 || keys_sorted) && (out || exists), "table_lookup: null pointer");
+    LSB_REQUIRE(!out || (default_host && (n == 0 || values)), "table_lookup: values / default missing");
+    LSB_REQUIRE(value_bytes == 4 || value_bytes == 8, "table_lookup: values must be 4 or 8 bytes wide");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (value_bytes == 8) {
+        unsigned long long d = 0;
+        if (default_host) memcpy(&d, default_host, 8);
+        k_table_lookup<unsigned long long><<<lsb_blocks(nq, 256), 256, 0, st>>>(keys_sorted, (const unsigned long long*)values, n, query, nq, d,
+                                                                               (unsigned long long*)out, exists);
+    } else {
+        unsigned int d = 0;
+        if (default_host) memcpy(&d, default_host, 4);
+        k_table_lookup<unsigned int><<<lsb_blocks(nq, 256), 256, 0, st>>>(keys_sorted, (const unsigned int*)values, n, query, nq, d,
+                                                                         (unsigned int*)out, exists);
+    }
+    LSB_LAUNCH_CHECK("k_table_lookup");
+    return 0;
+}
