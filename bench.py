@@ -230,6 +230,8 @@ def run_ours(args, rank, world, local_rank):
         step(dev_copies[args.warmup + i])
     while pipe._inflight:
         collect(pipe.collect())
+    if gatherer[0] is not None:
+        gatherer[0].flush()                  # every hit table has reached rank 0 inside the timed region
     e1.record()
     sync()
     launches = lib.lsb_launch_count() - launches0

@@ -53,29 +53,55 @@ class HitTableGather:
     """Sync-free gather of the per-batch hit table to `dst`: every rank sends ONE fixed-size buffer
     [cap + 1, 1 + 2A] of float64 -- row 0 holds the number of valid rows, rows 1..U hold
     (pixel id | ADC codes[A] | timestamps[A]) -- so no count exchange and no host synchronisation is needed
-    (the pixel count U is already known to the host from the chain result).  `dst` compacts it into packets
-    with :func:`hit_packets` whenever it wants to."""
+    (the pixel count U is already known to the host from the chain result).  The collective is issued
+    asynchronously on NCCL's own stream with `depth` rotating send / receive buffers: the compute streams never
+    wait for it, so ranks are not forced into lock-step every batch; a buffer is only waited for when it comes
+    round again (or in :meth:`flush`).  `dst` compacts a received table into packets with :func:`hit_packets`."""
 
-    def __init__(self, cap, n_adc, device, dst=0, group=None):
+    def __init__(self, cap, n_adc, device, dst=0, group=None, depth=3):
         self.cap, self.A, self.dst, self.group = int(cap), int(n_adc), dst, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.send = torch.zeros((self.cap + 1, 1 + 2 * self.A), dtype=torch.float64, device=device)
-        self.recv = ([torch.empty_like(self.send) for _ in range(self.world)] if self.rank == dst else None)
+        self.depth = max(1, int(depth)) if self.world > 1 else 1
+        self.sends = [torch.zeros((self.cap + 1, 1 + 2 * self.A), dtype=torch.float64, device=device) for _ in range(self.depth)]
+        self.recvs = [([torch.empty_like(self.sends[0]) for _ in range(self.world)] if self.rank == dst else None)
+                      for _ in range(self.depth)]
+        self.pending = [None] * self.depth
+        self.i = 0
+
+    @property
+    def send(self):
+        return self.sends[(self.i - 1) % self.depth]
+
+    @property
+    def recv(self):
+        return self.recvs[(self.i - 1) % self.depth]
 
     def gather(self, unique_pix, adc_digit, adc_ticks):
         U = int(unique_pix.shape[0])
         if U > self.cap:
             raise ValueError("hit table larger than the gather buffer (%d > %d)" % (U, self.cap))
-        b = self.send
+        k = self.i % self.depth
+        self.i += 1
+        if self.pending[k] is not None:
+            self.pending[k].wait()                      # the buffer is about to be overwritten
+            self.pending[k] = None
+        b = self.sends[k]
         b[0, 0] = float(U)
         b[1:U + 1, 0] = unique_pix.to(torch.float64)
         b[1:U + 1, 1:1 + self.A] = adc_digit
         b[1:U + 1, 1 + self.A:] = adc_ticks
         if self.world == 1:
             return [b]
-        dist.gather(b, self.recv, dst=self.dst, group=self.group)
-        return self.recv
+        self.pending[k] = dist.gather(b, self.recvs[k], dst=self.dst, group=self.group, async_op=True)
+        return self.recvs[k]
+
+    def flush(self):
+        """Make the current stream wait for every outstanding gather (call before reading the received tables)."""
+        for k, w in enumerate(self.pending):
+            if w is not None:
+                w.wait()
+                self.pending[k] = None
 
     def unpack(self, buf):
         U = int(buf[0, 0].item())

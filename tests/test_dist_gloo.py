@@ -43,6 +43,7 @@ def _worker(rank, world, port, q):
     digit = torch.full((U, 2), 80.0 + rank, dtype=torch.float64)
     ticks = torch.full((U, 2), 1.5 * (rank + 1), dtype=torch.float64)
     tabs = g.gather(uniq, digit, ticks)
+    g.flush()                                                     # the collective is asynchronous
     if rank == 0:
         u1, d1, t1 = g.unpack(tabs[1])
         q.put((u1.tolist(), d1.tolist(), t1.tolist(), [int(t[0, 0].item()) for t in tabs]))
