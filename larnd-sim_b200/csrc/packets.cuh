@@ -289,8 +289,8 @@ __global__ void k_pkt_write(PktTables T, PktTrig G, long long N, int A, const Sc
 }
 
 // ---- mc_packets_assn (fee.py:287-342): warp per packet --------------------------------------------------
-// np_sum_schedule: numpy's float64 add.reduce on a contiguous 1-D array is the first element plus the pairwise sum of
-// the rest -- a plain loop below 8 elements, else 8 interleaved accumulators combined as a tree, then the tail (n <= 128)
+// np_sum_schedule: numpy's float64 add.reduce on a contiguous run (checked against numpy 2.3 on random data): a plain
+// loop from 0 below 8 elements, else 8 interleaved accumulators combined as a tree, then the tail (n <= 128)
 #define ASSN_MAXK 128
 #define ASSN_WARPS 4
 __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packets, const long long* __restrict__ src_slot, int A, int K, int NA,
@@ -343,27 +343,25 @@ __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packet
         // np.sum over the matching fractions in sorted order (see np_sum_schedule): streamed, no scratch
         int n = 0;
         for (int j = 0; j < K; j++) n += s_t[w][j] == id;
-        const int m = n - 1, lim = m - (m % 8);
-        double first_v = 0.0, res = 0.0, r[8];
+        const int lim = n - (n % 8);
+        double res = 0.0, r[8];
         int c = 0;
         for (int j = 0; j < K; j++) {
             if (s_t[w][j] != id) continue;
             const double v = s_f[w][j];
-            const int k = c++ - 1;                            // index in b = a[1:]
-            if (k < 0) first_v = v;
-            else if (m < 8) res += v;
+            const int k = c++;
+            if (n < 8) res += v;
             else if (k < 8) r[k] = v;
             else if (k < lim) r[k & 7] += v;
         }
-        if (m >= 8) {
+        if (n >= 8) {
             res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
             c = 0;
             for (int j = 0; j < K; j++) {
                 if (s_t[w][j] != id) continue;
-                if (c++ - 1 >= lim) res += s_f[w][j];
+                if (c++ >= lim) res += s_f[w][j];
             }
         }
-        res = first_v + res;
         tj[tidx] = id;
         ftj[tidx] = (double)__double2float_rn(res);
     }
