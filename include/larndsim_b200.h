@@ -313,6 +313,29 @@ int lsb_chain_run_host_async(lsb_chain* h, void* tracks_host, int64_t S, int32_t
                              double* adc_ticks_host, int64_t U_cap);
 int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out);
 
+/* ---- light triggers and waveform digitisation ---------------------------------------------- */
+/* larndsim/light_sim.py:380-477  get_triggers (threshold mode): per trigger group (channels_per_group consecutive
+ * rows of `signal`) the channel sum, averaged over blocks of sample_factor ticks (zero padded), is compared with
+ * group_threshold; chan_module[d] = module slot (0..n_modules-1) of signal row d, or -1; every module then searches
+ * its triggers sequentially with a dead time of digit_ticks, the reference's index bookkeeping included.
+ * Outputs: trig_idx[module][max_trig] (tick indices as the reference reports them), n_trig[module]. */
+int lsb_light_get_triggers(const void* signal, int32_t signal_f64, int32_t ndet, int64_t nticks, int32_t channels_per_group,
+                           int32_t sample_factor, const double* group_threshold, const int32_t* chan_module, int32_t n_modules,
+                           int64_t digit_ticks, int32_t max_trig, int64_t* trig_idx, int32_t* n_trig, void* stream);
+/* larndsim/light_sim.py:480-543 digitize_signal + the zero padding / missing-channel rows / LIGHT_NBIT rounding of
+ * sim_triggers (:545-619).  The padded, channel-sorted waveform array the reference builds is described, not
+ * materialised: row k of it has channel row_channel[k] and is row row_source[k] of `signal` (-1: all zeros), shifted
+ * right by front_pad ticks inside a length of padded_len; array_is_f32 = that array would be float32 (no padding, no
+ * added rows, float32 input).  truncate = 1 applies round(x / 2^(16-nbit)) * 2^(16-nbit).  Truth outputs must be
+ * pre-filled (-1 / 0) by the caller like the reference does. */
+int lsb_light_digitize(const void* signal, int32_t signal_f64, int64_t nticks, int32_t n_rows, const int64_t* row_channel,
+                       const int32_t* row_source, int64_t front_pad, int64_t padded_len, int32_t array_is_f32,
+                       const int64_t* true_track_id, const double* true_photons, int32_t n_truth, int64_t n_trig,
+                       const int64_t* trig_channel, int32_t n_det_module, int32_t n_samples, double digit_sample_spacing,
+                       double light_tick_size, double mc_truth_threshold, int32_t light_nbit, int32_t truncate,
+                       double* digit_signal, int64_t* digit_true_track_id, double* digit_true_photons, int32_t n_truth_out,
+                       void* stream);
+
 /* ---- static key -> value table ----------------------------------------------------------- */
 /* larndsim/util/cuda_dict.py:1-230  CudaDict lookup / contains (per-pixel thresholds and gains,
  * cli/simulate_pixels.py:1080-1100): out[i] = value of query[i] or *default_host; exists[i] = 1 if present.

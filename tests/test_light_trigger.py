@@ -39,3 +39,86 @@ def test_oracle_trigger_search_keeps_the_reference_bookkeeping():
     z, C, sig, op, tid, tph = _case("module0")
     trig, _, _ = lo.get_triggers(sig, ltu.thresholds(C, op), op, 0, C)
     assert trig.tolist() == [300, 4200]
+
+
+# ---------------------------------------------------------------------------------------- GPU
+def _provider(name):
+    from larndsim_b200 import consts as lc
+    return lc.load_snapshot("module0" if name.startswith("module0") else "2x2")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ltu.CASES)
+def test_gpu_triggers_and_waveforms_identical(cuda, name):
+    import torch
+    from larndsim_b200 import light_sim, _launch as ll
+    z, C, sig, op, tid, tph = _case(name)
+    p = _provider(name)
+    assert int(p.light.LIGHT_TRIG_MODE) == C["LIGHT_TRIG_MODE"] and np.array_equal(np.asarray(p.light.LIGHT_TRIG_THRESHOLD), C["LIGHT_TRIG_THRESHOLD"])
+    thr = ltu.thresholds(C, op)
+    launches0 = ll.lib().lsb_launch_count()
+    for isub in (0, 1):
+        trig, chans, kinds = light_sim.get_triggers(sig if isub else torch.from_numpy(sig).cuda(), thr, op, isub)
+        assert np.array_equal(trig, z["trig_idx_%d" % isub]) and np.array_equal(kinds, z["trig_type_%d" % isub])
+        assert np.array_equal(chans, z["trig_chan_%d" % isub])
+    trig, chans, _ = light_sim.get_triggers(sig, thr, op, 0)
+    ns = int(z["digit_samples"])
+    d, d_id, d_ph = light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig, op, tid, tph, trig, chans, ns, np.zeros((C["N_OP_CHANNEL"], 33)))
+    assert ll.lib().lsb_launch_count() > launches0
+    d, d_id, d_ph = d.cpu().numpy(), d_id.cpu().numpy(), d_ph.cpu().numpy()
+    o, o_id, o_ph = lo.sim_triggers(sig, op, tid, tph, trig, chans, ns, C)
+    assert np.array_equal(d, o) and np.array_equal(d_id, o_id) and np.array_equal(d_ph, o_ph)
+    assert np.array_equal(d, z["out_digit"]) and np.array_equal(d_id, z["out_digit_id"]) and np.array_equal(d_ph, z["out_digit_photons"])
+
+
+@pytest.mark.gpu
+def test_gpu_raw_digitize_kernel_on_padded_arrays(cuda):
+    """digitize_signal[...] itself (no padding, no rounding): fed with the padded arrays sim_triggers would build, and
+    rounded afterwards, it gives the reference's waveforms."""
+    from math import ceil
+    from larndsim_b200 import light_sim
+    z, C, sig, op, tid, tph = _case("2x2")
+    _provider("2x2")
+    trig, chans = z["trig_idx_0"], z["trig_chan_0"]
+    ns = int(z["digit_samples"])
+    pre = int(ceil(C["LIGHT_TRIG_WINDOW"][0] / C["LIGHT_TICK_SIZE"]))
+    front = pre - int(trig.min())
+    assert front > 0
+    psig = np.concatenate([np.zeros((sig.shape[0], front)), sig], axis=-1)
+    ptid = np.concatenate([np.full((sig.shape[0], front, tid.shape[2]), -1, dtype=tid.dtype), tid], axis=1)
+    ptph = np.concatenate([np.zeros((sig.shape[0], front, tph.shape[2])), tph], axis=1)
+    d = np.zeros((len(trig), chans.shape[1], ns)); d_id = np.full(d.shape + (tid.shape[2],), -1, dtype=np.int64); d_ph = np.zeros(d.shape + (tid.shape[2],))
+    light_sim.digitize_signal[(1, 1, 16), (1, 1, 64)](psig, op, trig + front, chans, ptid, ptph, d, d_id, d_ph)
+    q = 2 ** (16 - C["LIGHT_NBIT"])
+    assert np.array_equal(np.round(d / q) * q, z["out_digit"]) and np.array_equal(d_id, z["out_digit_id"]) and np.array_equal(d_ph, z["out_digit_photons"])
+
+
+@pytest.mark.gpu
+def test_gpu_trigger_edge_cases_and_noise(cuda):
+    import torch
+    from larndsim_b200 import light_sim
+    z, C, sig, op, tid, tph = _case("module0")
+    p = _provider("module0")
+    thr = ltu.thresholds(C, op)
+    # nothing above threshold: no triggers, empty outputs of the reference's shapes
+    quiet = np.zeros_like(sig)
+    trig, chans, kinds = light_sim.get_triggers(quiet, thr, op, 0)
+    assert trig.shape == (0,) and chans.shape == (0, len(op)) and kinds.shape == (0,)
+    d, d_id, d_ph = light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig, op, tid, tph, trig, chans, 256, np.zeros((96, 33)))
+    assert tuple(d.shape) == (0, len(op), 256) and tuple(d_id.shape) == (0, len(op), 256, 2)
+    # tick count divisible by the sample factor (a whole block of padding) and a pulse at the very end
+    s2 = sig[:, :8990].copy()
+    o_trig, o_ch, _ = lo.get_triggers(s2, thr, op, 0, C)
+    g_trig, g_ch, _ = light_sim.get_triggers(s2, thr, op, 0)
+    assert np.array_equal(o_trig, g_trig) and np.array_equal(o_ch, g_ch)
+    # noise: flat spectrum -> waveforms differ from the noiseless ones by multiples of the ADC quantum, zero mean, not constant
+    trig, chans, _ = light_sim.get_triggers(sig, thr, op, 0)
+    spec = np.full((96, 33), 40.0)
+    a = light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig, op, tid, tph, trig, chans, 256, spec)[0].cpu().numpy()
+    b = light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig, op, tid, tph, trig, chans, 256, spec)[0].cpu().numpy()
+    clean = z["out_digit"]
+    q = 2 ** (16 - C["LIGHT_NBIT"])
+    assert np.array_equal(np.round(a / q) * q, a) and (a != clean).mean() > 0.2 and (a != b).mean() > 0.2
+    assert abs((a - clean).mean()) < 0.2 * (a - clean).std()
+    n = light_sim.gen_light_detector_noise((4, 1001), spec[:4]).cpu().numpy()
+    assert n.shape == (4, 1001) and np.array_equal(np.round(n / q) * q, n) and n.std() > 0

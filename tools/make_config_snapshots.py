@@ -30,7 +30,8 @@ LIGHT = ["LIGHT_SIMULATED", "ENABLE_LUT_SMEARING", "N_OP_CHANNEL", "OP_CHANNEL_E
          "SCINT_PRESCALE", "W_PH", "LIGHT_TICK_SIZE", "LIGHT_WINDOW", "SINGLET_FRACTION", "TAU_S", "TAU_T",
          "LIGHT_GAIN", "SIPM_RESPONSE_MODEL", "LIGHT_RESPONSE_TIME", "LIGHT_OSCILLATION_PERIOD",
          "IMPULSE_MODEL", "IMPULSE_TICK_SIZE", "LIGHT_TRIG_MODE", "OP_CHANNEL_PER_TRIG",
-         "LIGHT_DIGIT_SAMPLE_SPACING", "LIGHT_NBIT", "LIGHT_TRIG_WINDOW"]
+         "LIGHT_DIGIT_SAMPLE_SPACING", "LIGHT_NBIT", "LIGHT_TRIG_WINDOW", "TPC_TO_OP_CHANNEL", "LIGHT_TRIG_THRESHOLD",
+         "LIGHT_DET_NOISE_SAMPLE_SPACING"]
 SIM = ["BATCH_SIZE", "EVENT_BATCH_SIZE", "EVENT_SEPARATOR", "MAX_TRACKS_PER_PIXEL", "MIN_STEP_SIZE",
        "MC_SAMPLE_MULTIPLIER", "ASSOCIATION_COUNT_TO_STORE", "MAX_ADC_VALUES", "MAX_MC_TRUTH_IDS",
        "MC_TRUTH_THRESHOLD"]
