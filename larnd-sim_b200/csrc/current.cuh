@@ -206,10 +206,41 @@ __device__ __forceinline__ long long resp_k(double tick, double t0) { return __d
 //   k_mc_sampler   warp per (segment,pixel): lane = sample; live samples are compacted in order (ballot prefix)
 struct SampleU { float u[6]; };
 
+// k_mc_uniforms walks a pair's stream sequentially, so a warp is as slow as its longest pair.  Sample counts range from 0
+// (no pixel / no overlap) to several hundred: the pairs are therefore handed out in descending order of their count
+// (counting sort into MC_NBUCKET buckets of 16 samples; the order inside a bucket is arbitrary and does not matter --
+// every pair writes its own slots), which makes the lanes of a warp finish together.
+#define MC_NBUCKET 64
+__device__ __forceinline__ int mc_bucket_of(uint32_t n) { const uint32_t b = n >> 4; return MC_NBUCKET - 1 - (int)(b < MC_NBUCKET - 1 ? b : MC_NBUCKET - 1); }
+__global__ void k_mc_bucket_count(const uint32_t* __restrict__ nsamp, long long npair, int* __restrict__ bucket) {
+    __shared__ int s_cnt[MC_NBUCKET];
+    if (threadIdx.x < MC_NBUCKET) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pr < npair) atomicAdd(&s_cnt[mc_bucket_of(nsamp[pr])], 1);
+    __syncthreads();
+    if (threadIdx.x < MC_NBUCKET && s_cnt[threadIdx.x]) atomicAdd(&bucket[threadIdx.x], s_cnt[threadIdx.x]);
+}
+__global__ void k_mc_bucket_scan(int* __restrict__ bucket) {          // counts [0, NB) -> cursors [NB, 2NB)
+    if (threadIdx.x == 0) { int run = 0; for (int b = 0; b < MC_NBUCKET; b++) { bucket[MC_NBUCKET + b] = run; run += bucket[b]; } }
+}
+__global__ void k_mc_bucket_scatter(const uint32_t* __restrict__ nsamp, long long npair, int* __restrict__ bucket, int* __restrict__ perm) {
+    __shared__ int s_cnt[MC_NBUCKET], s_base[MC_NBUCKET];
+    if (threadIdx.x < MC_NBUCKET) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int b = 0, local = 0;
+    if (pr < npair) { b = mc_bucket_of(nsamp[pr]); local = atomicAdd(&s_cnt[b], 1); }
+    __syncthreads();
+    if (threadIdx.x < MC_NBUCKET && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&bucket[MC_NBUCKET + threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (pr < npair) perm[s_base[b] + local] = (int)pr;
+}
+
 #define UNI_TPB 64
 #define UNI_CHUNK 16         // samples generated per thread between two cooperative write-outs (16*6 floats = 3 warp rows)
-__global__ void __launch_bounds__(UNI_TPB) k_mc_uniforms(McParams p, const PairRec* __restrict__ pairs, SampleU* __restrict__ uu,
-                                                        unsigned long long* __restrict__ rng_states) {
+__global__ void __launch_bounds__(UNI_TPB) k_mc_uniforms(McParams p, const PairRec* __restrict__ pairs, const int* __restrict__ perm,
+                                                        SampleU* __restrict__ uu, unsigned long long* __restrict__ rng_states) {
     // thread = (segment,pixel).  Each thread's samples are contiguous in `uu`, so direct stores would scatter
     // 24-byte pieces over 32 different places per warp; the values go through shared memory and leave as
     // contiguous 192-byte runs per pair instead.
@@ -219,8 +250,9 @@ __global__ void __launch_bounds__(UNI_TPB) k_mc_uniforms(McParams p, const PairR
     __shared__ long long s_n[UNI_TPB];
     __shared__ long long s_max;
     const int tid = threadIdx.x;
-    const long long pr = blockIdx.x * (long long)UNI_TPB + tid;
-    const bool valid = pr < p.S * p.P && pairs[pr].valid;
+    const long long slot = blockIdx.x * (long long)UNI_TPB + tid;
+    const long long pr = slot < p.S * p.P ? perm[slot] : 0;
+    const bool valid = slot < p.S * p.P && pairs[pr].valid;
     const long long n = valid ? pairs[pr].nstep * d_c.mc_sample_multiplier : 0;
     Rng rng; rng.s0 = 0; rng.s1 = 0;
     unsigned long long* sp = nullptr;
@@ -896,13 +928,14 @@ __global__ void k_mc_replay(McParams p, const PairRec* __restrict__ pairs, const
 // ---------------------------------------------------------------------------------------
 struct McWs {
     PairRec* pairs; uint32_t* nsamp; long long* offs; long long* block_sums; long long* total;
+    int* perm; int* bucket;   // pairs ordered by descending sample count (k_mc_uniforms), 2 x MC_NBUCKET counters
     SampleRec* samples; int* offs32; SampleU* uu; long long sample_cap;
 };
 #define MC_BYTES_PER_SAMPLE ((long long)(sizeof(SampleRec) + 4 + sizeof(SampleU)))
 static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 static inline long long mc_fixed_bytes(long long npair) {
     return align_up(npair * (long long)sizeof(PairRec), 256) + align_up(npair * 4, 256) + align_up(npair * 8, 256) +
-           align_up((scan_num_blocks(npair) + 1) * 8, 256) + 256;
+           align_up((scan_num_blocks(npair) + 1) * 8, 256) + 256 + align_up(npair * 4, 256) + 1024;
 }
 LSB_EXPORT int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total) {
     return mc_fixed_bytes(S * (long long)P) + align_up(max_steps_total * (long long)sizeof(SampleRec), 256) +
@@ -917,6 +950,8 @@ static inline bool mc_carve(void* ws, long long bytes, long long npair, McWs& w)
     w.offs = (long long*)p; p += align_up(npair * 8, 256);
     w.block_sums = (long long*)p; p += align_up((scan_num_blocks(npair) + 1) * 8, 256);
     w.total = (long long*)p; p += 256;
+    w.perm = (int*)p; p += align_up(npair * 4, 256);
+    w.bucket = (int*)p; p += 1024;
     long long rest = bytes - fixed;
     w.sample_cap = (rest - 1024) / MC_BYTES_PER_SAMPLE;
     w.samples = (SampleRec*)p; p += align_up(w.sample_cap * (long long)sizeof(SampleRec), 256);
@@ -998,7 +1033,14 @@ static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixe
     }
     k_mc_set_offsets<<<lsb_blocks(npair, 256), 256, 0, st>>>(p, w.pairs, w.offs, npair);
     LSB_LAUNCH_CHECK("k_mc_set_offsets");
-    k_mc_uniforms<<<lsb_blocks(npair, UNI_TPB), UNI_TPB, 0, st>>>(p, w.pairs, w.uu, rng);
+    LSB_CUDA(cudaMemsetAsync(w.bucket, 0, 2 * MC_NBUCKET * sizeof(int), st));
+    k_mc_bucket_count<<<lsb_blocks(npair, 256), 256, 0, st>>>(w.nsamp, npair, w.bucket);
+    LSB_LAUNCH_CHECK("k_mc_bucket_count");
+    k_mc_bucket_scan<<<1, 32, 0, st>>>(w.bucket);
+    LSB_LAUNCH_CHECK("k_mc_bucket_scan");
+    k_mc_bucket_scatter<<<lsb_blocks(npair, 256), 256, 0, st>>>(w.nsamp, npair, w.bucket, w.perm);
+    LSB_LAUNCH_CHECK("k_mc_bucket_scatter");
+    k_mc_uniforms<<<lsb_blocks(npair, UNI_TPB), UNI_TPB, 0, st>>>(p, w.pairs, w.perm, w.uu, rng);
     LSB_LAUNCH_CHECK("k_mc_uniforms");
     k_mc_sampler<<<lsb_blocks(npair, SMP_WARPS), 32 * SMP_WARPS, 0, st>>>(p, w.pairs, w.uu, w.samples, w.offs32);
     LSB_LAUNCH_CHECK("k_mc_sampler");
