@@ -118,6 +118,7 @@ struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2*
 #define FEE_TRIG_PIX (FEE_TRIG_TPB / 32 * FEE_PPW)          // pixels per block
 #define FEE_NBUF 64
 #define FEE_QBUF 32
+#define FEE_WBLK 8          // ticks per block of the watching loop
 
 // fee.py:548-655 as ONE flat loop: every iteration evaluates the CSA FIR at the pixel's current tick and
 // then does the work of the state it is in (watching for a threshold crossing, or integrating after one),
@@ -216,7 +217,29 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
                         const double su = fp.unc_noise, sd = fp.disc_noise;
                         bool trig = false;
                         int k = 0;
-                        while (k < nf) {
+                        // blocks of FEE_WBLK ticks: the noise terms and right-hand sides of the block do not depend on the
+                        // running sum, so they are evaluated first (independent instructions, issued back to back); the
+                        // serial part per tick is then two adds and a compare
+                        while (!trig && k + FEE_WBLK <= nf) {
+                            double qv[FEE_WBLK], qn[FEE_WBLK], rhs[FEE_WBLK];
+#pragma unroll
+                            for (int u = 0; u < FEE_WBLK; u++) {
+                                qv[u] = qb[(k + u) * FEE_TRIG_PIX];
+                                qn[u] = (su == 0.0 ? 0.0 : (double)nb[(2 * (k + u)) * FEE_TRIG_PIX] * su) * fp.e;
+                                const double disc_noise = (sd == 0.0 ? 0.0 : (double)nb[(2 * (k + u) + 1) * FEE_TRIG_PIX] * sd) * fp.e;
+                                rhs[u] = thr + disc_noise;
+                            }
+#pragma unroll
+                            for (int u = 0; u < FEE_WBLK; u++) {
+                                if (!trig) {
+                                    q_sum += qv[u]; true_q += qv[u];
+                                    if (adc_busy > 0) adc_busy--;
+                                    k++;
+                                    if (q_sum + qn[u] >= rhs[u] && adc_busy == 0) trig = true;
+                                }
+                            }
+                        }
+                        while (!trig && k < nf) {
                             const double q = qb[k * FEE_TRIG_PIX];
                             q_sum += q; true_q += q;
                             const double q_noise = (su == 0.0 ? 0.0 : (double)nb[(2 * k) * FEE_TRIG_PIX] * su) * fp.e;
