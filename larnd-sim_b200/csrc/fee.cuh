@@ -133,9 +133,15 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
                                                       int* __restrict__ n_windows) {
     __shared__ float s_n[PRE ? FEE_NBUF * FEE_TRIG_PIX : 1];
     __shared__ double s_q[PRE ? FEE_QBUF * FEE_TRIG_PIX : 1];
-    const int slot = (threadIdx.x >> 5) * FEE_PPW + (threadIdx.x & 31);       // pixel slot of this thread within the block
-    const long long ip = blockIdx.x * (long long)FEE_TRIG_PIX + slot;
-    if ((threadIdx.x & 31) >= FEE_PPW || ip >= U) return;
+    // lanes 0..FEE_PPW-1 of a warp each run one pixel ("main" lanes); the other lanes only help with the window refills
+    const int lane = threadIdx.x & 31, wslot0 = (threadIdx.x >> 5) * FEE_PPW;
+    const int ps = lane % FEE_PPW, part = lane / FEE_PPW;                      // pixel slot this lane serves, its share of a refill
+    constexpr int NPART = 32 / FEE_PPW;
+    const int slot = wslot0 + ps;
+    const long long ip_s = blockIdx.x * (long long)FEE_TRIG_PIX + slot;         // pixel served (valid if < U)
+    const bool is_main = lane < FEE_PPW && ip_s < U;
+    if (!PRE && !is_main) return;                                              // no staged windows without the pre-computed inputs
+    const long long ip = is_main ? ip_s : 0;
     const double* curre = pixels_signals + ip * Tt;
     const double* qrow = PRE ? pre.q_pre + ip * pre.Tq : nullptr;
     const float* ncol = PRE ? pre.nrm + ip : nullptr;
@@ -188,14 +194,34 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
     int ic = 0, adc_busy = 0, last_reset = 0, iadc = 0, cleared = 0, integrate_end = 0;
     bool integrating = false, broke = false;
     double true_q = 0.0;
-    double q_sum = draw(fp.reset_noise) * fp.e;                          // fee.py:557
+    bool done = !is_main;
+    double q_sum = is_main ? draw(fp.reset_noise) * fp.e : 0.0;         // fee.py:557
     FeeWindow* win = windows + ip * (A + 1);
     for (;;) {
         if (PRE) {
-            // refill the staging windows for the whole warp at once: lanes drift apart by a tick or two per hit,
-            // and per-lane refills would expose one memory latency per lane instead of one per warp
-            const bool need = !inl && ((idx + 6 > nbase + FEE_NBUF) || (fp.BR > 0 && (ic < qbase || ic >= qbase + FEE_QBUF)));
-            if (__any_sync(__activemask(), need) && !inl) { refill_n(idx); if (fp.BR > 0) refill_q(ic); }
+            if (!__any_sync(0xffffffffu, !done)) break;
+            // refill the staging windows for the whole warp at once (lanes drift apart by a tick or two per hit, and per-lane
+            // refills would expose one memory latency per lane instead of one per warp); all 32 lanes share the loads:
+            // lane = (pixel slot, part), part p fetches entries p, p + NPART, ... of that pixel's windows
+            const bool mine = !done && !inl;
+            const bool need = mine && ((idx + 6 > nbase + FEE_NBUF) || (fp.BR > 0 && (ic < qbase || ic >= qbase + FEE_QBUF)));
+            if (__any_sync(0xffffffffu, need)) {
+                const int idx_s = __shfl_sync(0xffffffffu, idx, ps), ic_s = __shfl_sync(0xffffffffu, ic, ps);
+                const bool act_s = __shfl_sync(0xffffffffu, mine ? 1 : 0, ps) != 0;
+                if (act_s) {
+                    const float* src = pre.nrm + (long long)idx_s * U + ip_s;
+#pragma unroll
+                    for (int k = part; k < FEE_NBUF; k += NPART) nbuf[k * FEE_TRIG_PIX] = (idx_s + k < NMAX) ? __ldg(src + (long long)k * U) : 0.f;
+                    if (fp.BR > 0) {
+                        const double* qs = pre.q_pre + ip_s * pre.Tq + ic_s;
+#pragma unroll
+                        for (int k = part; k < FEE_QBUF; k += NPART) qbuf[k * FEE_TRIG_PIX] = (ic_s + k < Tq) ? __ldg(qs + k) : 0.0;
+                    }
+                }
+                __syncwarp();
+                if (mine) { nbase = idx; if (fp.BR > 0) qbase = ic; }
+            }
+            if (done) continue;
         }
         if (PRE && !inl && fp.BR > 0 && interval >= 1 && ic >= qbase && idx >= nbase) {
             // Fast paths.  While no reset lies inside the tap window the FIR values are the pre-computed ones and a tick
@@ -266,8 +292,8 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
             }
         }
         if (!integrating) {
-            if (!(ic < Tt || adc_busy > 0)) break;                       // :559
-            if (iadc >= max_hits) { broke = true; break; }               // :561-563 (and the rows of the outputs)
+            if (!(ic < Tt || adc_busy > 0)) { if (PRE) { done = true; continue; } break; }                 // :559
+            if (iadc >= max_hits) { broke = true; if (PRE) { done = true; continue; } break; }             // :561-563 (and the rows of the outputs)
         }
         const double q = fir(ic, last_reset);                            // :565-578 / :597-610
         q_sum += q; true_q += q;
@@ -312,6 +338,7 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
         cleared = 0;
         iadc++;
     }
+    if (!is_main) return;
     int nw = iadc;
     if (!broke && iadc < A && (ic - 1 >= last_reset || cleared)) {
         // trailing window: accumulated but never normalised (the reference leaves it in the row)
