@@ -118,7 +118,9 @@ struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2*
 #define FEE_TRIG_PIX (FEE_TRIG_TPB / 32 * FEE_PPW)          // pixels per block
 #define FEE_NBUF 64
 #define FEE_QBUF 32
+#ifndef FEE_WBLK
 #define FEE_WBLK 8          // ticks per block of the watching loop
+#endif
 
 // fee.py:548-655 as ONE flat loop: every iteration evaluates the CSA FIR at the pixel's current tick and
 // then does the work of the state it is in (watching for a threshold crossing, or integrating after one),
