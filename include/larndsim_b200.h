@@ -293,6 +293,10 @@ int        lsb_chain_set_dense(lsb_chain* h, int32_t dense);
  * summation order (bit-identical float64), exact=0 (default) evaluates the same double sum as order-free weighted
  * sums over each hit window (agrees to ~1e-15 relative; hits, timestamps and charges do not depend on it). */
 int        lsb_chain_set_exact_fractions(lsb_chain* h, int32_t exact);
+/* lsb_chain_result.signals is stored sparsely by the fused chain (per row only the ticks covered by the pair's samples are
+ * written; later stages never read the rest).  Call this before reading the dense f4[S, P, T] array: it zero-fills the
+ * unwritten parts of the last batch on `stream` (idempotent). */
+int        lsb_chain_signals_dense(lsb_chain* h, void* stream);
 /* tracks on the device, modified in place by quench/drift like the reference */
 int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
                   int32_t n_events, lsb_chain_result* out, void* stream);

@@ -16,7 +16,8 @@ STAGES = ("quench+drift", "max/get_pixels", "unique_pix", "time_intervals", "tra
 
 
 class ChainResult:
-    def __init__(self, r, K, A, Tt):
+    def __init__(self, r, K, A, Tt, handle=None):
+        self._handle = handle
         self.n_segments, self.n_unique_pixels = int(r.n_segments), int(r.n_unique_pixels)
         self.max_active, self.max_neighbors, self.n_ticks = int(r.max_active), int(r.max_neighbors), int(r.n_ticks)
         self.n_hits, self.n_samples = int(r.n_hits), int(r.n_samples)
@@ -64,6 +65,10 @@ class ChainResult:
 
     @property
     def signals(self):
+        """f4[S, P, T] induced currents.  The fused chain stores the rows sparsely (only the ticks a pair's samples cover are
+        written, nothing downstream reads the rest); the first access zero-fills the unwritten parts of this batch."""
+        if self._handle:
+            _l.check(_l.lib().lsb_chain_signals_dense(C.c_void_p(self._handle), _l.stream()), "chain_signals_dense")
         return self._view(self._r.signals, (self.n_segments, self.max_neighbors, self.n_ticks), np.float32)
 
     @property
@@ -155,7 +160,7 @@ class Chain:
         qm = int(self._c.mode_birks if quench_mode is None else quench_mode)
         _l.check(_l.lib().lsb_chain_run(C.c_void_p(self._h), t.c, C.c_int64(t.shape[0]), C.c_int32(qm),
                                         C.c_uint64(int(rng_seed)), C.c_int32(int(n_events)), C.byref(r), _l.stream()), "chain_run")
-        return ChainResult(r, self._K, self._A, self._Tt)
+        return ChainResult(r, self._K, self._A, self._Tt, self._h)
 
     def run_async(self, tracks_dev, quench_mode=None, rng_seed=0, n_events=1):
         """Queue one batch on this chain's own streams and return immediately; collect with :meth:`wait`."""
@@ -182,7 +187,7 @@ class Chain:
         r = _abi.ChainResult()
         _l.check(_l.lib().lsb_chain_wait(C.c_void_p(self._h), C.byref(r)), "chain_wait")
         self._keep = None
-        return ChainResult(r, self._K, self._A, self._Tt)
+        return ChainResult(r, self._K, self._A, self._Tt, self._h)
 
     def run_host(self, tracks_host, unique_pix_out, adc_out, ticks_out, quench_mode=None, rng_seed=0, n_events=1):
         """tracks_host: structured host array (ideally pinned); outputs: preallocated (pinned) host
@@ -197,4 +202,4 @@ class Chain:
         _l.check(_l.lib().lsb_chain_run_host(C.c_void_p(self._h), p(tracks_host), C.c_int64(n), C.c_int32(qm),
                                              C.c_uint64(int(rng_seed)), C.c_int32(int(n_events)), p(unique_pix_out), p(adc_out),
                                              p(ticks_out), C.c_int64(ucap), C.byref(r), _l.stream()), "chain_run_host")
-        return ChainResult(r, self._K, self._A, self._Tt)
+        return ChainResult(r, self._K, self._A, self._Tt, self._h)

@@ -37,6 +37,9 @@ struct lsb_chain {
     lsb_consts c;
     lsb_track_layout L;
     const void* response; int Rx, Ry, Rt, f64, rng_mode, timing;
+    DevBuf sig_ranges;        // int2 per (segment, pixel) row of `signals`: ticks that hold data (rows are stored sparsely)
+    int signals_dense;        // the rows of the last batch have been zero-filled outside their ranges
+    long long last_rows; int last_T;
     DevBuf tracks, scal, active, neigh, nrad, npl, uniq, uniq_ws, starts, signals, mc_ws, pim, tpm, psig, pts, oflow, tticks,
            integral, adc_digit, adc_ticks, cf, thr, rng, nhits, sx_slot, sx_counts, sx_cursor, sx_raw, sx_offs, sx_bsums, sx_sorted;
     DevBuf arena_buf; TmpArena arena;
@@ -132,8 +135,21 @@ LSB_EXPORT int lsb_chain_set_exact_fractions(lsb_chain* h, int32_t exact) {
     h->exact_fractions = exact ? 1 : 0;
     return 0;
 }
+// `signals` rows are stored sparsely by the fused MC stage (only the ticks covered by a pair's samples are written; the
+// rest is zero by definition and no later stage reads it).  A caller who wants to look at the dense [S, P, T] array --
+// lsb_chain_result.signals -- calls this first: it zero-fills the unwritten parts of the last batch (idempotent).
+LSB_EXPORT int lsb_chain_signals_dense(lsb_chain* h, void* stream) {
+    LSB_REQUIRE(h, "chain_signals_dense: null handle");
+    if (h->signals_dense || h->last_rows <= 0 || h->last_T <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_signals_dense<<<(unsigned)h->last_rows, 128, 0, st>>>((float*)h->signals.p, (const int2*)h->sig_ranges.p, h->last_rows, h->last_T);
+    LSB_LAUNCH_CHECK("k_signals_dense");
+    h->signals_dense = 1;
+    return 0;
+}
 LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
     if (!h) return;
+    h->sig_ranges.release();
     DevBuf* all[] = {&h->tracks, &h->scal, &h->active, &h->neigh, &h->nrad, &h->npl, &h->uniq, &h->uniq_ws, &h->starts, &h->signals,
                      &h->mc_ws, &h->pim, &h->tpm, &h->psig, &h->pts, &h->oflow, &h->tticks, &h->integral, &h->adc_digit,
                      &h->adc_ticks, &h->cf, &h->thr, &h->rng, &h->nhits, &h->sx_slot, &h->sx_counts, &h->sx_cursor, &h->sx_raw,
@@ -240,6 +256,8 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     CH_STAGE(4);
     // ---- tracks_current_mc (:1007-1016) -------------------------------------------------
     if ((rc = h->signals.need((size_t)S * P * T * 4))) return rc;
+    if ((rc = h->sig_ranges.need((size_t)S * P * sizeof(int2)))) return rc;
+    h->signals_dense = 0; h->last_rows = S * P; h->last_T = (int)T;
     long long need_rng = S * P;
     long long need_rng2 = 128LL * ((U + 127) / 128);
     if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
@@ -281,9 +299,12 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
             if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
             if ((rc = mc_run_nosync(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
                                     h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, S, h->mc_ws.p,
-                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, st))) return rc;
+                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, (int2*)h->sig_ranges.p, st))) return rc;
         } else {
             LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
+            k_ranges_full<<<lsb_blocks(S * P, 256), 256, 0, st>>>((int2*)h->sig_ranges.p, S * P, (int)T);
+            LSB_LAUNCH_CHECK("k_ranges_full");
+            h->signals_dense = 1;
             long long guess = S * 4000LL;
             long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, guess);
             if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
@@ -337,8 +358,10 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
         sx.offs = (long long*)h->sx_offs.p; sx.bsums = (long long*)h->sx_bsums.p; sx.sorted = (SumEntry*)h->sx_sorted.p;
         if ((rc = lsb_upload_consts(c, st))) return rc;
         if ((rc = sum_build_entries(sx, U, S, (int)P, (const double*)h->starts.p, (const long long*)h->pim.p, (const long long*)h->tpm.p, K,
-                                    (double*)h->oflow.p, st))) return rc;
+                                    (double*)h->oflow.p, nullptr, (int)T, st))) return rc;
         if (st_mc != st) { LSB_CUDA(cudaStreamWaitEvent(st, h->ev_mc, 0)); cudaEventRecord(h->tl[4], st); }
+        k_sum_apply_ranges<<<lsb_blocks(U, 128), 128, 0, st>>>(sx.offs, sx.counts, U, (const int2*)h->sig_ranges.p, sx.sorted);
+        LSB_LAUNCH_CHECK("k_sum_apply_ranges");
         if ((rc = sum_run(sx, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, (int)T, K, h->dense ? (double*)h->pts.p : nullptr, st))) return rc;
     }
     CH_STAGE(7);

@@ -58,7 +58,9 @@ struct McParams {
     // sync-free operation (fused chain): the sample total stays on the device; every kernel after the scan
     // returns at once if it exceeds the capacity the caller provisioned (and *overflow is raised)
     const long long* total_dev; long long cap; int* overflow;
-    int zero_fill;            // k_mc_accumulate also stores the zeros the caller would otherwise have to pre-fill (fused chain)
+    int2* ranges;             // fused chain: rows of `signals` are stored sparsely -- only the ticks [lo, hi] covered by the pair's
+                              // samples are written, and (lo, hi) is recorded here (empty: lo > hi); everything else is zero by
+                              // definition and is neither written nor read (lsb_chain_signals_dense fills it in on request)
 };
 #define MC_GUARD(p) do { if ((p).total_dev && *(p).total_dev > (p).cap) return; } while (0)
 
@@ -696,10 +698,7 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
     long long pr = blockIdx.x;
     const PairRec* gp = pairs + pr;
     if (!gp->valid) {
-        if (p.zero_fill) {
-            float* o = signals + ((p.seg0 + pr / p.P) * p.P + (pr % p.P)) * (long long)p.T;
-            for (int it = threadIdx.x; it < p.T; it += ACC_TPB) o[it] = 0.f;
-        }
+        if (p.ranges && threadIdx.x == 0) p.ranges[(p.seg0 + pr / p.P) * p.P + (pr % p.P)] = make_int2(0, -1);
         return;
     }
     __shared__ __align__(16) int s_off[ACC_CHUNK];
@@ -789,8 +788,16 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
     __syncthreads();
 
     // ---- (a) ticks >= it_first that no sample covers: the reference stores total_current = 0 ----
-    for (int it = (p.zero_fill ? 0 : it_first) + tid; it < T; it += ACC_TPB)
-        if (it < it_first || n_live - n_irr <= 0 || it < uni_lo || it > uni_hi) out[it] = 0.f;   // (c) adds the irregular samples on top
+    if (p.ranges) {
+        // sparse rows: only [uni_lo, uni_hi] is stored.  The interior / edge paths write every tick of it; if there are only
+        // irregular samples it is zeroed here and (c) adds them on top.
+        if (tid == 0) p.ranges[itrk * p.P + (pr % p.P)] = n_live > 0 ? make_int2(uni_lo, uni_hi) : make_int2(0, -1);
+        if (n_live > 0 && n_live - n_irr <= 0)
+            for (int it = uni_lo + tid; it <= uni_hi; it += ACC_TPB) out[it] = 0.f;
+    } else {
+        for (int it = it_first + tid; it < T; it += ACC_TPB)
+            if (n_live - n_irr <= 0 || it < uni_lo || it > uni_hi) out[it] = 0.f;   // (c) adds the irregular samples on top
+    }
 
     // ---- (b) edge ticks: inside the union of the sample windows but outside the interior -------
     if (STRIDE > 0 && n_live - n_irr > 0) {
@@ -1079,19 +1086,19 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
     g_mc_last_samples = 0;
-    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.zero_fill = 0;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.ranges = nullptr;
     return mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states,
                         rng_mode, p, workspace, workspace_bytes, st, 0);
 }
 
 // Fused-chain entry without host synchronisation: `workspace` must hold `lsb_tracks_current_mc_workspace_bytes`
 // of an UPPER BOUND of the sample count; *total_out (device) receives the actual count, *overflow (device)
-// is raised -- and nothing is written -- if the bound was wrong.  Cloud mode only.  Every element of `signals` is
-// written (zeros included): the caller does not pre-fill it.
+// is raised -- and nothing is written -- if the bound was wrong.  Cloud mode only.  `signals` is stored sparsely: row e
+// holds data in ticks ranges[e].x .. ranges[e].y only (see McParams::ranges); the caller does not pre-fill it.
 static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S, const int32_t* pixels,
                          int32_t P, float* signals, int32_t T, const void* response, int32_t Rx, int32_t Ry, int32_t Rt,
                          int32_t response_f64, uint64_t* rng_states, int64_t rng_stride, void* workspace,
-                         int64_t workspace_bytes, long long* total_out, int* overflow, cudaStream_t st) {
+                         int64_t workspace_bytes, long long* total_out, int* overflow, int2* ranges, cudaStream_t st) {
     if (S == 0 || P == 0 || T == 0) return 0;
     if (require_current_fields(L, true)) return -1;
     int rc = lsb_upload_consts(c, st); if (rc) return rc;
@@ -1099,7 +1106,7 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
     p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
-    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.zero_fill = 1;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.ranges = ranges;
     rc = mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states, 0, p,
                       workspace, workspace_bytes, st, 0);
     if (rc) return rc;
@@ -1336,4 +1343,19 @@ LSB_EXPORT int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L
                                                           (const float*)response, Rx, Ry, Rt, signals);
     LSB_LAUNCH_CHECK("k_tracks_current");
     return 0;
+}
+
+// zero everything outside the stored tick range of every row (sparse -> dense `signals`)
+__global__ void k_signals_dense(float* __restrict__ signals, const int2* __restrict__ ranges, long long n_rows, int T) {
+    const long long row = blockIdx.x;
+    if (row >= n_rows) return;
+    const int2 g = ranges[row];
+    float* o = signals + row * (long long)T;
+    for (int it = threadIdx.x; it < T; it += blockDim.x)
+        if (it < g.x || it > g.y) o[it] = 0.f;
+}
+// full ranges (dense producer, e.g. replay mode)
+__global__ void k_ranges_full(int2* __restrict__ ranges, long long n_rows, int T) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_rows) ranges[i] = make_int2(0, T - 1);
 }

@@ -432,17 +432,19 @@ __global__ void __launch_bounds__(128) k_fee_fractions_sparse(FeeParams fp, cons
     if (nw == 0) return;
     // value of this (pixel, slot) waveform at pixel tick ic, as the dense tensor would hold it
     const int start32 = (int)(start < -2000000000LL ? -2000000000LL : (start > 2000000000LL ? 2000000000LL : start));
+    const int my_lo = L[me].lo, my_hi = L[me].hi;                       // ticks of the row that hold data
+    const int my_lo_safe = my_lo >= 0 && my_lo < T ? my_lo : 0;
     auto sample = [&](int ic) -> double {
         // branch-free so that the FEE_RING loads of a block are issued back to back
-        const unsigned it = (unsigned)(ic - start32);
-        const bool ok = (ic < Tt) && (it < (unsigned)T);
-        const float f = __ldg(row + (ok ? it : 0u));
+        const int it = ic - start32;
+        const bool ok = (ic < Tt) && it >= my_lo && it <= my_hi;
+        const float f = __ldg(row + (ok ? it : my_lo_safe));
         double v = ok ? (double)f : 0.0;
         if (n_same && ic < Tt) {                     // several row entries of one segment on this pixel (not produced by get_pixels)
             for (int q = me + 1; q < n; q++)
                 if (L[q].slot == slot) {
                     long long it2 = ic - L[q].start_tick;
-                    if (it2 >= 0 && it2 < T) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
+                    if (it2 >= L[q].lo && it2 <= L[q].hi) v += (double)__ldg(signals + (long long)L[q].e * T + it2);
                 }
         }
         return v;
@@ -534,8 +536,8 @@ __global__ void __launch_bounds__(128) k_fee_fractions_fast(FeeParams fp, const 
             if (L[q].slot != slot) continue;
             const float* row = signals + (long long)L[q].e * T;
             const long long start = L[q].start_tick;
-            long long lo = w.ic0 > start ? w.ic0 : start;                 // ticks where this row has samples
-            long long up = hi < start + T - 1 ? hi : start + T - 1;
+            long long lo = w.ic0 > start + L[q].lo ? w.ic0 : start + L[q].lo;      // ticks where this row has samples
+            long long up = hi < start + L[q].hi ? hi : start + L[q].hi;
             for (long long jc = lo + lane; jc <= up; jc += 32) {
                 const double v = (double)__ldg(row + (jc - start));
                 const int m = (int)(w.ic1 - jc);

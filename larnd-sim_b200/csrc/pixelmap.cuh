@@ -166,7 +166,9 @@ LSB_EXPORT int lsb_get_track_pixel_map2(int64_t* track_pixel_map, int32_t K, con
 // ---------------------------------------------------------------------------------------
 // sum_pixel_signals
 // ---------------------------------------------------------------------------------------
-struct SumEntry { int e; int slot; long long start_tick; };
+// one (segment, pixel) waveform feeding a pixel: flat row index, slot in track_pixel_map, the ticks [lo, hi] of the row that
+// hold data (everything outside is zero and need not be stored), tick of the row's first sample in the pixel's time frame
+struct SumEntry { int e; int slot; int lo; int hi; long long start_tick; };
 
 // bucket = pixel_index_map value; slot = position of the segment in track_pixel_map[pixel] (first match)
 __global__ void k_sum_bucket(const long long* __restrict__ pim, long long n_entries, int P, long long U,
@@ -196,7 +198,8 @@ __global__ void k_sum_fill(const long long* __restrict__ pim, const int* __restr
 }
 __global__ void k_sum_sort(const long long* __restrict__ pim, const int* __restrict__ slot_of, long long n_entries, int P,
                            const long long* __restrict__ offs, const int* __restrict__ counts, const int* __restrict__ raw,
-                           const double* __restrict__ track_starts, SumEntry* __restrict__ sorted) {
+                           const double* __restrict__ track_starts, const int2* __restrict__ ranges, int T,
+                           SumEntry* __restrict__ sorted) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n_entries) return;
     int slot = slot_of[e];
@@ -206,6 +209,7 @@ __global__ void k_sum_sort(const long long* __restrict__ pim, const int* __restr
     int n = counts[p], rank = 0;
     for (int i = 0; i < n; i++) if (L[i] < (int)e) rank++;
     SumEntry r; r.e = (int)e; r.slot = slot;
+    if (ranges) { const int2 g = ranges[e]; r.lo = g.x; r.hi = g.y; } else { r.lo = 0; r.hi = T - 1; }
     r.start_tick = __double2ll_rn(track_starts[e / P] / d_c.time_sampling);      // detsim.py:504
     sorted[offs[p] + rank] = r;
 }
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restric
         if (!active) continue;
         for (int i = 0; i < nc; i++) {
             long long itick = (long long)t - s_e[i].start_tick;
-            if (itick < 0 || itick >= T) continue;
+            if (itick < s_e[i].lo || itick > s_e[i].hi) continue;
             float s = __ldg(signals + (long long)s_e[i].e * T + itick);
             if (s == 0.f) continue;                            // x + 0 == x: skipping is exact
             acc += (double)s;
@@ -245,12 +249,22 @@ __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restric
     if (active) pixels_signals[p * Tt + t] = acc;
 }
 
+// tick ranges of sparsely stored rows -> entries (thread per pixel)
+__global__ void k_sum_apply_ranges(const long long* __restrict__ offs, const int* __restrict__ counts, long long U,
+                                   const int2* __restrict__ ranges, SumEntry* __restrict__ sorted) {
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= U) return;
+    SumEntry* L = sorted + offs[p];
+    for (int i = 0; i < counts[p]; i++) { const int2 g = ranges[L[i].e]; L[i].lo = g.x; L[i].hi = g.y; }
+}
+
 // entries of every pixel, sorted by flat (segment,pixel) index, in caller-provided buffers
 struct SumCtx {
     int* slot_of; int* counts; int* cursor; int* raw; long long* offs; long long* bsums; SumEntry* sorted;
 };
 static int sum_build_entries(const SumCtx& x, long long U, long long S, int P, const double* track_starts,
-                             const long long* pim, const long long* tpm, int K, double* overflow_flag, cudaStream_t st) {
+                             const long long* pim, const long long* tpm, int K, double* overflow_flag, const int2* ranges, int T,
+                             cudaStream_t st) {
     long long n_entries = S * P;
     LSB_CUDA(cudaMemsetAsync(x.counts, 0, U * 4, st));
     LSB_CUDA(cudaMemsetAsync(x.cursor, 0, U * 4, st));
@@ -260,7 +274,7 @@ static int sum_build_entries(const SumCtx& x, long long U, long long S, int P, c
     if (rc) return rc;
     k_sum_fill<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pim, x.slot_of, n_entries, x.offs, x.cursor, x.raw);
     LSB_LAUNCH_CHECK("k_sum_fill");
-    k_sum_sort<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pim, x.slot_of, n_entries, P, x.offs, x.counts, x.raw, track_starts, x.sorted);
+    k_sum_sort<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(pim, x.slot_of, n_entries, P, x.offs, x.counts, x.raw, track_starts, ranges, T, x.sorted);
     LSB_LAUNCH_CHECK("k_sum_sort");
     return 0;
 }
@@ -296,7 +310,7 @@ LSB_EXPORT int lsb_sum_pixel_signals(const lsb_consts* c, double* pixels_signals
     LSB_CUDA(tp.get(&x.bsums, scan_num_blocks(U) + 1));
     LSB_CUDA(tp.get(&x.sorted, n_entries));
     rc = sum_build_entries(x, U, S, P, track_starts, (const long long*)pixel_index_map, (const long long*)track_pixel_map, K,
-                           overflow_flag, st);
+                           overflow_flag, nullptr, T, st);
     if (rc) return rc;
     return sum_run(x, pixels_signals, U, Tt, signals, T, K, pixels_tracks_signals, st);
 }
