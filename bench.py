@@ -346,9 +346,9 @@ def run_ours(args, rank, world, local_rank):
     # T_act = ticks with time >= 0 actually written (about half of T for uniformly distributed drift times)
     n_valid = 0.61 * S * P_
     alg = {
-        # out: every element of signals (the fused chain has no memset); in: group records (16 B, ~1 per 3 samples),
-        # sample records for the edge ticks (24 B), pair records
-        "k_mc_accumulate": 4.0 * S * P_ * T + 24.0 * n_samples + 16.0 * n_samples / 3.0 + 160.0 * S * P_,
+        # out: the ticks of signals the samples cover (rows are stored sparsely, about half of T per valid pair); in: group
+        # records (16 B, ~1 per 3 samples), sample records for the edge ticks (24 B), pair records
+        "k_mc_accumulate": 4.0 * n_valid * T * 0.5 + 24.0 * n_samples + 16.0 * n_samples / 3.0 + 160.0 * S * P_,
         "k_fee_trigger": 8.0 * U * Tt + 4.0 * U * 4480 + 2 * 8.0 * U * A,
         "k_sum_pixel_signals": 4.0 * n_valid * T + 2 * 8.0 * U * Tt,
         "k_mc_sampler": 24.0 * n_samples + 28.0 * n_samples,
@@ -410,7 +410,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments), charge readout quench->ADC, noise on",
                        "segments_per_batch": S, "pixels_per_segment_row": P_, "unique_pixels": U, "ticks": T, "hits": n_hits,
                        "mc_sample_points": n_samples, "rng": "cloud (one sample cloud per segment x pixel)",
-                       "l2": "per-step working set (signals %.2f GB, per-segment pixel waveforms %.2f GB) >> 126 MB L2; fresh input copy each step"
+                       "l2": "per-step working set (signals %.2f GB dense-equivalent, per-segment pixel waveforms %.2f GB) >> 126 MB L2; fresh input copy each step"
                              % (4.0 * S * P_ * T / 1e9, 8.0 * U * Tt * K / 1e9),
                        "pipeline": "2 batches in flight per GPU (FEE stage of batch i under the MC stage of batch i+1)",
                        "parallelism": "1 batch stream per rank, no collective in the chain; NCCL gather of hit packets to rank 0" if world > 1 else "single GPU"},

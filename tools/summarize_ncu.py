@@ -2,6 +2,7 @@
 
   python tools/summarize_ncu.py launches gpurun_out/launches.csv  > profiles/rNN_launches.md
   python tools/summarize_ncu.py report   gpurun_out/prof.ncu-rep  > profiles/rNN_top_kernels.md
+  python tools/summarize_ncu.py traffic  gpurun_out/prof.ncu-rep  > profiles/rNN_traffic.json   (read by bench.py)
 """
 import csv
 import io
@@ -60,5 +61,38 @@ def report(path):
         print()
 
 
+def traffic(path):
+    """Per kernel (first captured launch of each): DRAM bytes and the counters bench.py quotes in its roofline block."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+
+    def val(r, k, scale=True):
+        if k not in hdr:
+            return None
+        i = hdr.index(k)
+        v = float(r[i].replace(",", ""))
+        u = units[i].lower()
+        if scale and "byte" in u:
+            v *= {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
+        return v
+    res = {"_source": "ncu --set full --clock-control none capture of `python bench.py --steps 2 --warmup 1` (%s), per launch: "
+                      "dram__bytes_read.sum + dram__bytes_write.sum" % path.split("/")[-1]}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        if name in res:
+            continue
+        t = val(r, "gpu__time_duration.sum")
+        tu = units[hdr.index("gpu__time_duration.sum")].lower()
+        ms = t * {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(tu, 1.0)
+        res[name] = {"dram_bytes": int(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")), "ms": round(ms, 4),
+                     "l1tex_throughput_pct": val(r, "l1tex__throughput.avg.pct_of_peak_sustained_active"),
+                     "l1_global_load_requests": val(r, "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"),
+                     "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     "dram_throughput_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
