@@ -43,18 +43,21 @@ def make_batch(seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe).  nvidia-smi needs a moment to
+    start, so the sampler runs from before the warm-up; `begin()` / `end()` bracket the timed regions (device-resident and e2e)
+    and only samples taken inside them are reported (the nearest ones if a region is shorter than the sampling period)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.lines = []
+        self.lines = []               # (arrival time, text)
+        self.windows = []
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -63,32 +66,43 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def begin(self):
+        self._t0 = time.perf_counter()
+
+    def end(self):
+        self.windows.append((self._t0, time.perf_counter()))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        parsed = []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for t, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                parsed.append((t, float(f[1]), float(f[2]), [nm for nm, val in zip(names, f[5:9]) if val.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [p for p in parsed if any(a - 0.03 <= p[0] <= b + 0.03 for a, b in self.windows)]
+        where = "inside the timed regions"
+        if not inside and parsed and self.windows:
+            mid = 0.5 * (self.windows[0][0] + self.windows[-1][1])
+            inside = sorted(parsed, key=lambda p: abs(p[0] - mid))[:3]
+            where = "nearest to the timed regions"
+        sm = [p[1] for p in inside]
+        reasons = sorted({r for p in inside for r in p[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(p[2] for p in inside) if inside else None,
+                "reasons": reasons, "samples": len(sm), "sampled": where, "samples_whole_run": len(parsed)}
 
 
 def measured_peaks():
@@ -214,17 +228,18 @@ def run_ours(args, rank, world, local_rank):
             collect(pipe.collect())          # consume the oldest result before its chain is reused
         pipe.submit(batch, rng_seed=1)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(dev_copies[i])
     while pipe._inflight:
         collect(pipe.collect())
     sync()
     results.clear()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.lsb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     e0.record()
     for i in range(args.steps):
         step(dev_copies[args.warmup + i])
@@ -234,8 +249,8 @@ def run_ours(args, rank, world, local_rank):
         gatherer[0].flush()                  # every hit table has reached rank 0 inside the timed region
     e1.record()
     sync()
+    sampler.end()
     launches = lib.lsb_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     assert len(results) == args.steps
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -279,6 +294,7 @@ def run_ours(args, rank, world, local_rank):
         pipe.submit_host(host_batches[i], *outs[i % 3], rng_seed=1)
     pipe.drain()
     sync()
+    sampler.begin()
     e0.record()
     for i in range(args.steps):
         if pipe.full():
@@ -287,6 +303,8 @@ def run_ours(args, rank, world, local_rank):
     r2 = pipe.drain()[-1]
     e1.record()
     sync()
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
     ms_e2e = e0.elapsed_time(e1)
     t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
