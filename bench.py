@@ -178,11 +178,17 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if os.environ.get("LSB_BENCH_BACKEND") == "gloo":       # diagnostic: control plane without NCCL (no hit gather)
+            os.environ["LSB_NO_GATHER"] = "1"
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from larndsim_b200 import _launch as ll, chain as lchain, consts as lc
     lib = ll.lib()
     lib.lsb_profile_end.restype = C.c_int64
-    mod, tracks, response = make_batch(12345 + 1000 * rank)
+    # weak scaling: every rank simulates a batch of the same size AND the same content (independent detector modules seeing
+    # identical muons), so the per-rank work is exactly fixed as N grows and max-over-ranks is not a lottery over batches
+    mod, tracks, response = make_batch(12345)
     S = len(tracks)
     itemsize = tracks.dtype.itemsize
     ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud", stage_timing=True)
@@ -201,11 +207,13 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 or os.environ.get("LSB_NO_GATHER"):
             return
         if gatherer[0] is None:
-            gatherer[0] = ldist.HitTableGather(int(res.n_unique_pixels * 1.3) + 1024, A, "cuda")
+            from larndsim_b200 import packets as lp
+            ped = lp.ReadoutTables.from_consts()._c.adc_pedestal              # digitize(0): a hit is an ADC code above it
+            gatherer[0] = ldist.HitTableGather(2 * int(res.n_unique_pixels) + 4096, ped, "cuda")
         gatherer[0].gather(res.unique_pix, res.adc_digit, res.adc_ticks_list)
 
     def sync():
-        if world > 1:
+        if world > 1 and not os.environ.get("LSB_BENCH_NO_BARRIER"):       # (diagnostic switch)
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -223,10 +231,15 @@ def run_ours(args, rank, world, local_rank):
             results.append(r)
             gather_packets(r)
 
+    host_t = {"collect": 0.0, "submit": 0.0, "n": 0}
+
     def step(batch):
+        w0 = time.perf_counter()
         if pipe.full():
             collect(pipe.collect())          # consume the oldest result before its chain is reused
+        w1 = time.perf_counter()
         pipe.submit(batch, rng_seed=1)
+        host_t["collect"] += w1 - w0; host_t["submit"] += time.perf_counter() - w1; host_t["n"] += 1
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -239,6 +252,7 @@ def run_ours(args, rank, world, local_rank):
     results.clear()
     launches0 = lib.lsb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_t.update(collect=0.0, submit=0.0, n=0)
     sampler.begin()
     e0.record()
     for i in range(args.steps):
@@ -254,7 +268,14 @@ def run_ours(args, rank, world, local_rank):
     assert len(results) == args.steps
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    per_rank = [{"ms_per_step": ms / args.steps, "mc_sample_points": int(results[-1].n_samples)}]
     if world > 1:
+        # every rank simulates different muons (independent units): batches differ in their number of sample points
+        rdev = "cpu" if dist.get_backend() == "gloo" else "cuda"
+        t = t.to(rdev)
+        allv = [torch.zeros(2, device=rdev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allv, torch.tensor([ms / args.steps, float(results[-1].n_samples)], device=rdev, dtype=torch.float64))
+        per_rank = [{"ms_per_step": float(v[0].item()), "mc_sample_points": int(v[1].item())} for v in allv]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * S * args.steps / (ms_max * 1e-3)
@@ -306,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms_e2e], device="cpu" if (world > 1 and dist.get_backend() == "gloo") else "cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * args.steps / (float(t.item()) * 1e-3)
@@ -431,10 +452,12 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "per-step working set (signals %.2f GB dense-equivalent, per-segment pixel waveforms %.2f GB) >> 126 MB L2; fresh input copy each step"
                              % (4.0 * S * P_ * T / 1e9, 8.0 * U * Tt * K / 1e9),
                        "pipeline": "2 batches in flight per GPU (FEE stage of batch i under the MC stage of batch i+1)",
-                       "parallelism": "1 batch stream per rank, no collective in the chain; NCCL gather of hit packets to rank 0" if world > 1 else "single GPU"},
+                       "parallelism": "1 batch stream per rank (identical batch on every rank), no collective in the chain; NCCL gather of the compacted hit packets to rank 0" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": float(t.item()) / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block,
+            "gpu_launches": int(launches), "per_rank": per_rank, "host_ms_per_step": {"wait_for_oldest_batch": 1e3 * host_t["collect"] / max(host_t["n"], 1),
+                                                              "submit_next_batch": 1e3 * host_t["submit"] / max(host_t["n"], 1)},
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block,
             "ms_per_step_unpipelined": ms_serial,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}, "kernels": kernels}
     print(json.dumps(line), flush=True)

@@ -50,47 +50,40 @@ def gather_packets(rec, dst=0, group=None):
 
 
 class HitTableGather:
-    """Sync-free gather of the per-batch hit table to `dst`: every rank sends ONE fixed-size buffer
-    [cap + 1, 1 + 2A] of float64 -- row 0 holds the number of valid rows, rows 1..U hold
-    (pixel id | ADC codes[A] | timestamps[A]) -- so no count exchange and no host synchronisation is needed
-    (the pixel count U is already known to the host from the chain result).  The collective is issued
-    asynchronously on NCCL's own stream with `depth` rotating send / receive buffers: the compute streams never
-    wait for it, so ranks are not forced into lock-step every batch; a buffer is only waited for when it comes
-    round again (or in :meth:`flush`).  `dst` compacts a received table into packets with :func:`hit_packets`."""
+    """Sync-free gather of the per-batch hits to `dst`.  Every rank compacts its hit table on the device into ONE
+    fixed-size buffer [cap + 1, 3] of float64 -- row 0 holds the number of hits, rows 1.. hold (pixel id, ADC code,
+    timestamp) of the hits in (pixel, hit) order -- with a prefix sum and a scatter (no `nonzero`, so no host
+    synchronisation), and the buffers are gathered with one NCCL collective: no count exchange is needed.  The collective
+    is issued asynchronously on NCCL's own stream with `depth` rotating send / receive buffers: the compute streams never
+    wait for it, so ranks are not forced into lock-step every batch; a buffer is only waited for when it comes round again
+    (or in :meth:`flush`)."""
 
-    def __init__(self, cap, n_adc, device, dst=0, group=None, depth=3):
-        self.cap, self.A, self.dst, self.group = int(cap), int(n_adc), dst, group
+    def __init__(self, cap, pedestal_adc, device, dst=0, group=None, depth=3):
+        self.cap, self.ped, self.dst, self.group = int(cap), float(pedestal_adc), dst, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.depth = max(1, int(depth)) if self.world > 1 else 1
-        self.sends = [torch.zeros((self.cap + 1, 1 + 2 * self.A), dtype=torch.float64, device=device) for _ in range(self.depth)]
+        self.sends = [torch.zeros((self.cap + 2, 3), dtype=torch.float64, device=device) for _ in range(self.depth)]   # last row: overflow dump
         self.recvs = [([torch.empty_like(self.sends[0]) for _ in range(self.world)] if self.rank == dst else None)
                       for _ in range(self.depth)]
         self.pending = [None] * self.depth
         self.i = 0
 
-    @property
-    def send(self):
-        return self.sends[(self.i - 1) % self.depth]
-
-    @property
-    def recv(self):
-        return self.recvs[(self.i - 1) % self.depth]
-
     def gather(self, unique_pix, adc_digit, adc_ticks):
-        U = int(unique_pix.shape[0])
-        if U > self.cap:
-            raise ValueError("hit table larger than the gather buffer (%d > %d)" % (U, self.cap))
         k = self.i % self.depth
         self.i += 1
         if self.pending[k] is not None:
             self.pending[k].wait()                      # the buffer is about to be overwritten
             self.pending[k] = None
         b = self.sends[k]
-        b[0, 0] = float(U)
-        b[1:U + 1, 0] = unique_pix.to(torch.float64)
-        b[1:U + 1, 1:1 + self.A] = adc_digit
-        b[1:U + 1, 1 + self.A:] = adc_ticks
+        hit = (adc_digit > self.ped).reshape(-1)
+        pos = torch.cumsum(hit, 0)                       # 1-based row of every hit
+        n = pos[-1:] if hit.numel() else torch.zeros(1, dtype=torch.int64, device=b.device)
+        row = torch.where(hit & (pos <= self.cap), pos, torch.full_like(pos, self.cap + 1))     # non-hits / overflow -> dump row
+        A = adc_digit.shape[1]
+        pix = unique_pix.to(torch.float64).repeat_interleave(A)
+        b.index_copy_(0, row, torch.stack([pix, adc_digit.reshape(-1), adc_ticks.reshape(-1)], dim=1))
+        b[0, 0] = n[0].to(torch.float64) if hit.numel() else 0.0
         if self.world == 1:
             return [b]
         self.pending[k] = dist.gather(b, self.recvs[k], dst=self.dst, group=self.group, async_op=True)
@@ -104,5 +97,6 @@ class HitTableGather:
                 self.pending[k] = None
 
     def unpack(self, buf):
-        U = int(buf[0, 0].item())
-        return buf[1:U + 1, 0].to(torch.int32), buf[1:U + 1, 1:1 + self.A], buf[1:U + 1, 1 + self.A:]
+        """(pixel ids i4[n], ADC codes f8[n], timestamps f8[n]) of one received buffer"""
+        n = min(int(buf[0, 0].item()), self.cap)
+        return buf[1:n + 1, 0].to(torch.int32), buf[1:n + 1, 1], buf[1:n + 1, 2]

@@ -37,10 +37,11 @@ def _worker(rank, world, port, q):
         q.put([o.tolist() for o in out])
     else:
         assert out is None
-    g = ldist.HitTableGather(cap=6, n_adc=2, device="cpu")
+    g = ldist.HitTableGather(cap=6, pedestal_adc=74.0, device="cpu")
     U = 2 + rank
     uniq = torch.arange(U, dtype=torch.int32) + 10 * rank
-    digit = torch.full((U, 2), 80.0 + rank, dtype=torch.float64)
+    digit = torch.full((U, 2), 74.0, dtype=torch.float64)
+    digit[:, 0] = 80.0 + rank                                       # one hit per pixel, second slot at the pedestal
     ticks = torch.full((U, 2), 1.5 * (rank + 1), dtype=torch.float64)
     tabs = g.gather(uniq, digit, ticks)
     g.flush()                                                     # the collective is asynchronous
@@ -70,4 +71,4 @@ def test_gather_packets_world2_gloo():
     assert len(got) == 2 and len(got[0]) == 3 and len(got[1]) == 5
     assert got[1][0] == [100.0, 101.0, 102.0] and got[0][2] == [6.0, 7.0, 8.0]
     assert shapes == [(0, 3), (0, 3)]
-    assert table[0] == [10, 11, 12] and table[1] == [[81.0, 81.0]] * 3 and table[2] == [[3.0, 3.0]] * 3 and table[3] == [2, 3]
+    assert table[0] == [10, 11, 12] and table[1] == [81.0] * 3 and table[2] == [3.0] * 3 and table[3] == [2, 3]
