@@ -359,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
         packets_block = {"ms_per_batch": pk_ms, "packets_per_batch": int(len(pk)), "data_packets": int((pk["packet_type"] == 0).sum()),
                          "packets_per_s": len(pk) / (pk_ms * 1e-3), "launches_per_batch": (lib.lsb_launch_count() - l0) / args.steps,
                          "timed": "wall clock around the public call (device inputs, results copied to host arrays)",
-                         "algorithmic_bytes": alg_bytes, "note": "latency-bound at this size (17 launches, 2 syncs); not part of `value`"}
+                         "algorithmic_bytes": alg_bytes, "note": "latency-bound at this size (10 launches, 2 host syncs, 2 D2H copies); not part of `value`"}
         if not os.environ.get("LSB_BENCH_NO_CPU"):
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import packets_oracle as po
@@ -373,6 +373,42 @@ def run_ours(args, rank, world, local_rank):
             packets_block["cpu_python_restatement"] = {"packets_per_s": len(opk) / cpu_s, "sample": "first %d pixels, %.2f s, 1 core" % (nsub, cpu_s)}
     except Exception as exc:                                   # the packet stage is an extra: never lose the headline line
         packets_block = {"error": repr(exc)}
+    # ---------------- next stage: light triggers + digitisation of one module's waveforms ----------------
+    light_block = None
+    try:
+        from larndsim_b200 import light_sim
+        import light_trigger_util as ltu
+        C_l = ltu.consts_from_npz(ltu.load("module0"))
+        sig_l, op_l, tid_l, tph_l = ltu.case_inputs("module0", C_l["OP_CHANNEL_PER_TRIG"], C_l["N_OP_CHANNEL"])
+        thr_l = ltu.thresholds(C_l, op_l)
+        sig_d = torch.from_numpy(sig_l).cuda(); tid_d = torch.from_numpy(tid_l).cuda(); tph_d = torch.from_numpy(tph_l).cuda()
+        zero_noise = np.zeros((C_l["N_OP_CHANNEL"], 33))
+        ns_l = 256
+
+        def light_once():
+            trig, chans, _ = light_sim.get_triggers(sig_d, thr_l, op_l, 0)
+            return light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig_d, op_l, tid_d, tph_d, trig, chans, ns_l, zero_noise), trig
+        light_once()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            (dg, _, _), trig_l = light_once()
+        torch.cuda.synchronize()
+        l_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+        light_block = {"ms_per_call": l_ms, "channels": int(sig_l.shape[0]), "ticks": int(sig_l.shape[1]), "triggers": int(len(trig_l)),
+                       "digitised_samples": int(dg.numel()), "workload": "tests/light_trigger_util.py case module0 (96 channels x 9000 ticks, 2 truth slots)",
+                       "timed": "wall clock around get_triggers + sim_triggers (device inputs)",
+                       "algorithmic_bytes": 4.0 * sig_l.size + 8.0 * dg.numel() * (1 + 2 * tid_l.shape[2])}
+        if not os.environ.get("LSB_BENCH_NO_CPU"):
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import light_trigger_oracle as lo
+            w0 = time.perf_counter()
+            t_o, c_o, _ = lo.get_triggers(sig_l, thr_l, op_l, 0, C_l)
+            lo.sim_triggers(sig_l, op_l, tid_l, tph_l, t_o[:1], c_o[:1, :8], ns_l, C_l)
+            cpu_s = time.perf_counter() - w0
+            light_block["cpu_python_restatement"] = {"seconds": cpu_s, "sample": "trigger search on all channels + digitisation of 1 trigger x 8 channels (of %d x %d), 1 core" % (len(t_o), c_o.shape[1])}
+    except Exception as exc:
+        light_block = {"error": repr(exc)}
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peaks()
     Tt = int(lc.snapshot().n_time_ticks)
@@ -457,7 +493,7 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": float(t.item()) / args.steps},
             "gpu_launches": int(launches), "per_rank": per_rank, "host_ms_per_step": {"wait_for_oldest_batch": 1e3 * host_t["collect"] / max(host_t["n"], 1),
                                                               "submit_next_batch": 1e3 * host_t["submit"] / max(host_t["n"], 1)},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block, "light_triggers": light_block,
             "ms_per_step_unpipelined": ms_serial,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}, "kernels": kernels}
     print(json.dumps(line), flush=True)

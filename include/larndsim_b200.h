@@ -385,14 +385,15 @@ typedef struct lsb_readout_tables {
  * Device arrays: event_id i8[U,A], adc (digitised) f8[U,A], adc_ticks f8[U,A], unique_pix i4[U],
  * current_fractions f8[U,A,K], track_ids / traj_ids i8[U,K]; pix_t0_ticks[i] = int(event_start_times[inv[i]] /
  * CLOCK_CYCLE) and pix_t0_us[i] = event_start_times[inv[i]] with inv the rank of event_id[i,0] among the sorted
- * unique events (fee.py:136-137); light triggers (times [us], event, module).  *n_packets receives the packet
+ * unique events (fee.py:136-137); light triggers (times [us], event, module).  assn_rows: cap_packets records of the
+ * mc_packets_assn dtype (event_ids i8[1] | segment_ids i8[n] | fraction f8[n] | file_traj_ids i8[n] | fraction_traj f8[n],
+ * 8 + 32 n bytes each).  *n_packets receives the packet
  * count; if it exceeds cap_packets nothing is written and the call fails (retry with that capacity). */
 int lsb_export_packets(const lsb_readout_tables* rt, int64_t U, int32_t A, int32_t K, const int64_t* event_id,
                        const double* adc, const double* adc_ticks, const int32_t* unique_pix, const double* current_fractions,
                        const int64_t* track_ids, const int64_t* traj_ids, const int64_t* pix_t0_ticks, const double* pix_t0_us,
                        int32_t n_trig, const double* trig_times, const int64_t* trig_event, const int32_t* trig_module,
-                       int64_t cap_packets, lsb_packet* packets, int64_t* assn_event, int64_t* assn_segment, double* assn_fraction,
-                       int64_t* assn_traj, double* assn_fraction_traj, int32_t n_assn, int64_t* n_packets, void* stream);
+                       int64_t cap_packets, lsb_packet* packets, void* assn_rows, int32_t n_assn, int64_t* n_packets, void* stream);
 
 #ifdef __cplusplus
 }

@@ -303,7 +303,10 @@ __device__ __forceinline__ float normal_from_uniforms(float u1, float u2) {     
 }
 
 #define SMP_WARPS 4
-__global__ void __launch_bounds__(32 * SMP_WARPS) k_mc_sampler(McParams p, PairRec* __restrict__ pairs,
+#ifndef SMP_MINB
+#define SMP_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParams p, PairRec* __restrict__ pairs,
                                                                const SampleU* __restrict__ uu, SampleRec* __restrict__ samples,
                                                                int* __restrict__ offs32) {
     MC_GUARD(p);

@@ -296,19 +296,21 @@ __global__ void k_pkt_write(PktTables T, PktTrig G, long long N, int A, const Sc
 __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packets, const long long* __restrict__ src_slot, int A, int K, int NA,
                                                               const long long* __restrict__ event_id, const double* __restrict__ cf,
                                                               const long long* __restrict__ track_ids, const long long* __restrict__ traj_ids,
-                                                              long long* __restrict__ o_event, long long* __restrict__ o_seg,
-                                                              double* __restrict__ o_frac, long long* __restrict__ o_traj,
-                                                              double* __restrict__ o_ftraj) {
+                                                              char* __restrict__ rows) {
+    // one output row = the mc_packets_assn record: event_ids i8[1] | segment_ids i8[NA] | fraction f8[NA] | file_traj_ids i8[NA] |
+    // fraction_traj f8[NA]  (8 + 32 NA bytes, every field 8-byte aligned)
     __shared__ double s_f[ASSN_WARPS][ASSN_MAXK];        // fractions in sorted order
     __shared__ long long s_t[ASSN_WARPS][ASSN_MAXK];     // trajectory ids in sorted order
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long ipk = blockIdx.x * (long long)ASSN_WARPS + w;
     if (ipk >= n_packets) return;
     const long long s = src_slot[ipk];
-    long long* seg = o_seg + ipk * NA; double* fr = o_frac + ipk * NA;
-    long long* tj = o_traj + ipk * NA; double* ftj = o_ftraj + ipk * NA;
+    char* row = rows + ipk * (8LL + 32LL * NA);
+    long long* o_event = reinterpret_cast<long long*>(row);
+    long long* seg = reinterpret_cast<long long*>(row + 8); double* fr = reinterpret_cast<double*>(row + 8 + 8LL * NA);
+    long long* tj = reinterpret_cast<long long*>(row + 8 + 16LL * NA); double* ftj = reinterpret_cast<double*>(row + 8 + 24LL * NA);
     for (int j = lane; j < NA; j += 32) { seg[j] = -1; fr[j] = 0.0; tj[j] = -1; ftj[j] = 0.0; }
-    if (lane == 0) o_event[ipk] = s >= 0 ? event_id[s] : -1;
+    if (lane == 0) o_event[0] = s >= 0 ? event_id[s] : -1;
     if (s < 0) return;
     __syncwarp();
     const long long ip = s / A;
@@ -392,8 +394,7 @@ LSB_EXPORT int lsb_export_packets(const lsb_readout_tables* rt, int64_t U, int32
                                   const double* adc, const double* adc_ticks, const int32_t* unique_pix, const double* current_fractions,
                                   const int64_t* track_ids, const int64_t* traj_ids, const int64_t* pix_t0_ticks, const double* pix_t0_us,
                                   int32_t n_trig, const double* trig_times, const int64_t* trig_event, const int32_t* trig_module,
-                                  int64_t cap_packets, lsb_packet* packets, int64_t* assn_event, int64_t* assn_segment, double* assn_fraction,
-                                  int64_t* assn_traj, double* assn_fraction_traj, int32_t n_assn, int64_t* n_packets, void* stream) {
+                                  int64_t cap_packets, lsb_packet* packets, void* assn_rows, int32_t n_assn, int64_t* n_packets, void* stream) {
     LSB_REQUIRE(rt && n_packets, "export_packets: null tables / n_packets");
     LSB_REQUIRE(K >= 0 && K <= ASSN_MAXK, "export_packets: MAX_TRACKS_PER_PIXEL above the supported 128");
     LSB_REQUIRE(U * (long long)A < 2147483647LL, "export_packets: more than 2^31 hit slots in one call");
@@ -437,15 +438,12 @@ LSB_EXPORT int lsb_export_packets(const lsb_readout_tables* rt, int64_t U, int32
     *n_packets = n_out;
     if (n_out > cap_packets) return lsb_fail_arg("export_packets: output capacity too small (n_packets holds the required count)");
     if (n_out == 0) return 0;
-    LSB_REQUIRE(packets && assn_event && assn_segment && assn_fraction && assn_traj && assn_fraction_traj && current_fractions && track_ids &&
-                traj_ids, "export_packets: null output / truth pointer");
+    LSB_REQUIRE(packets && assn_rows && current_fractions && track_ids && traj_ids, "export_packets: null output / truth pointer");
     k_pkt_write<<<lsb_blocks(N, 256), 256, 0, st>>>(T, G, N, A, sc, adc_ticks, adc, (const long long*)pix_t0_ticks, pix_t0_us,
                                                     (const long long*)event_id, info, offs, cap_packets, packets, src);
     LSB_LAUNCH_CHECK("k_pkt_write");
     k_pkt_assn<<<lsb_blocks(n_out, ASSN_WARPS), 32 * ASSN_WARPS, 0, st>>>(n_out, src, A, K, n_assn, (const long long*)event_id, current_fractions,
-                                                                         (const long long*)track_ids, (const long long*)traj_ids,
-                                                                         (long long*)assn_event, (long long*)assn_segment, assn_fraction,
-                                                                         (long long*)assn_traj, assn_fraction_traj);
+                                                                         (const long long*)track_ids, (const long long*)traj_ids, (char*)assn_rows);
     LSB_LAUNCH_CHECK("k_pkt_assn");
     LSB_CUDA(cudaStreamSynchronize(st));      // the uploaded tables are temporaries of this call
     return 0;

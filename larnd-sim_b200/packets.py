@@ -171,7 +171,10 @@ def export_packets(tables, event_id_list, adc_list, adc_ticks_list, unique_pix, 
     if U == 0:
         return np.zeros(0, dtype=PACKET_DTYPE), np.zeros(0, dtype=assn_dtype(n_assn))
     # per-pixel event start (fee.py:136-137): rank of the pixel's first-slot event among the sorted unique events
-    ev0 = _host(event_id_list)[:, 0] if not isinstance(event_id_list, np.ndarray) else event_id_list[:, 0]
+    if isinstance(event_id_list, np.ndarray):
+        ev0 = event_id_list[:, 0]
+    else:
+        ev0 = torch.as_tensor(event_id_list, device="cuda")[:, 0].cpu().numpy()          # one column, not the whole table
     _, inv = np.unique(ev0, return_inverse=True)
     est = np.asarray(_host(event_start_times), dtype=np.float64)
     t0_us = np.ascontiguousarray(est[inv])
@@ -188,29 +191,26 @@ def export_packets(tables, event_id_list, adc_list, adc_ticks_list, unique_pix, 
     cap = 4 * U + 4096                 # a first guess; the call reports the exact count if it is too small
     lib = _l.lib()
     n_out = C.c_int64(0)
+    adt = assn_dtype(n_assn)
     for _ in range(2):
         pk = torch.empty(cap * PACKET_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        a_ev = torch.empty(cap, dtype=torch.int64, device="cuda")
-        a_seg = torch.empty((cap, n_assn), dtype=torch.int64, device="cuda")
-        a_fr = torch.empty((cap, n_assn), dtype=torch.float64, device="cuda")
-        a_tj = torch.empty((cap, n_assn), dtype=torch.int64, device="cuda")
-        a_ft = torch.empty((cap, n_assn), dtype=torch.float64, device="cuda")
+        rows = torch.empty(cap * adt.itemsize, dtype=torch.uint8, device="cuda")          # mc_packets_assn records, written in place
         rc = lib.lsb_export_packets(C.byref(tables._c), C.c_int64(U), C.c_int32(A), C.c_int32(K), ev.c, adc.c, tks.c, pix.c, cf.c, trk.c, trj.c,
                                     t0t.c, t0u.c, C.c_int32(n_trig), tt.c if tt else None, te.c if te else None, tm.c if tm else None,
-                                    C.c_int64(cap), C.c_void_p(pk.data_ptr()), C.c_void_p(a_ev.data_ptr()), C.c_void_p(a_seg.data_ptr()),
-                                    C.c_void_p(a_fr.data_ptr()), C.c_void_p(a_tj.data_ptr()), C.c_void_p(a_ft.data_ptr()),
-                                    C.c_int32(n_assn), C.byref(n_out), _l.stream())
+                                    C.c_int64(cap), C.c_void_p(pk.data_ptr()), C.c_void_p(rows.data_ptr()), C.c_int32(n_assn),
+                                    C.byref(n_out), _l.stream())
         if rc != 0 and n_out.value > cap:
             cap = int(n_out.value)
             continue
         _l.check(rc, "export_packets")
         break
     n = int(n_out.value)
-    packets = pk[: n * PACKET_DTYPE.itemsize].cpu().numpy().view(PACKET_DTYPE)
-    ds = np.empty(n, dtype=assn_dtype(n_assn))
-    ds["event_ids"] = a_ev[:n].cpu().numpy()[:, None]
-    ds["segment_ids"] = a_seg[:n].cpu().numpy()
-    ds["fraction"] = a_fr[:n].cpu().numpy()
-    ds["file_traj_ids"] = a_tj[:n].cpu().numpy()
-    ds["fraction_traj"] = a_ft[:n].cpu().numpy()
+    # one D2H copy per table into pinned memory; the NumPy results are views of those buffers
+    h_pk = torch.empty(n * PACKET_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    h_rows = torch.empty(n * adt.itemsize, dtype=torch.uint8, pin_memory=True)
+    h_pk.copy_(pk[: n * PACKET_DTYPE.itemsize], non_blocking=True)
+    h_rows.copy_(rows[: n * adt.itemsize], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    packets = h_pk.numpy().view(PACKET_DTYPE)
+    ds = h_rows.numpy().view(adt)
     return packets, ds
