@@ -304,7 +304,7 @@ __device__ __forceinline__ float normal_from_uniforms(float u1, float u2) {     
 
 #define SMP_WARPS 4
 #ifndef SMP_MINB
-#define SMP_MINB 1
+#define SMP_MINB 8
 #endif
 __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParams p, PairRec* __restrict__ pairs,
                                                                const SampleU* __restrict__ uu, SampleRec* __restrict__ samples,
