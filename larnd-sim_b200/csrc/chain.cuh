@@ -345,7 +345,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     // (pixel, slot) entry list.  dense=1 reproduces the reference's buffers.
     if ((rc = h->psig.need((size_t)U * Tt * 8)) || (rc = h->oflow.need((size_t)U * 8))) return rc;
     if (h->dense && (rc = h->pts.need((size_t)U * Tt * K * 8))) return rc;
-    LSB_CUDA(cudaMemsetAsync(h->psig.p, 0, (size_t)U * Tt * 8, st)); LSB_MARK("memset_psig", st);
+    if (h->dense) { LSB_CUDA(cudaMemsetAsync(h->psig.p, 0, (size_t)U * Tt * 8, st)); LSB_MARK("memset_psig", st); }   // else: written fresh by the sum kernel
     if (h->dense) { LSB_CUDA(cudaMemsetAsync(h->pts.p, 0, (size_t)U * Tt * K * 8, st)); LSB_MARK("memset_pts", st); }
     LSB_CUDA(cudaMemsetAsync(h->oflow.p, 0, (size_t)U * 8, st));
     SumCtx sx;
@@ -362,7 +362,8 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
         if (st_mc != st) { LSB_CUDA(cudaStreamWaitEvent(st, h->ev_mc, 0)); cudaEventRecord(h->tl[4], st); }
         k_sum_apply_ranges<<<lsb_blocks(U, 128), 128, 0, st>>>(sx.offs, sx.counts, U, (const int2*)h->sig_ranges.p, sx.sorted);
         LSB_LAUNCH_CHECK("k_sum_apply_ranges");
-        if ((rc = sum_run(sx, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, (int)T, K, h->dense ? (double*)h->pts.p : nullptr, st))) return rc;
+        if ((rc = sum_run(sx, (double*)h->psig.p, U, Tt, (const float*)h->signals.p, (int)T, K, h->dense ? (double*)h->pts.p : nullptr, st,
+                          !h->dense))) return rc;
     }
     CH_STAGE(7);
     // ---- get_adc_values (:1072-1095) ----------------------------------------------------

@@ -216,7 +216,8 @@ __global__ void k_sum_sort(const long long* __restrict__ pim, const int* __restr
 
 #define SUM_TPB 256
 #define SUM_CHUNK 64
-template <bool WITH_PTS>
+// FRESH: pixels_signals holds no earlier contributions (fused chain): it is written without being read or pre-zeroed
+template <bool WITH_PTS, bool FRESH>
 __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restrict__ pixels_signals, long long U, int Tt,
                                                                const float* __restrict__ signals, int T,
                                                                const long long* __restrict__ offs, const int* __restrict__ counts,
@@ -225,11 +226,11 @@ __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restric
     __shared__ SumEntry s_e[SUM_CHUNK];
     const long long p = blockIdx.x;
     const int n = counts[p];
-    if (n == 0) return;
     const int t = blockIdx.y * SUM_TPB + threadIdx.x;
     const bool active = t < Tt;
+    if (n == 0) { if (FRESH && active) pixels_signals[p * Tt + t] = 0.0; return; }
     const SumEntry* L = sorted + offs[p];
-    double acc = active ? pixels_signals[p * Tt + t] : 0.0;
+    double acc = (active && !FRESH) ? pixels_signals[p * Tt + t] : 0.0;
     double* prow = pts + (p * Tt + (active ? t : 0)) * (long long)K;
     for (int c0 = 0; c0 < n; c0 += SUM_CHUNK) {
         int nc = n - c0 < SUM_CHUNK ? n - c0 : SUM_CHUNK;
@@ -279,11 +280,13 @@ static int sum_build_entries(const SumCtx& x, long long U, long long S, int P, c
     return 0;
 }
 static int sum_run(const SumCtx& x, double* pixels_signals, long long U, int Tt, const float* signals, int T, int K, double* pts,
-                   cudaStream_t st) {
-    if (T <= 0 || Tt <= 0) return 0;
+                   cudaStream_t st, bool fresh = false) {
+    if (Tt <= 0) return 0;
+    if (T <= 0) { if (fresh) LSB_CUDA(cudaMemsetAsync(pixels_signals, 0, (size_t)U * Tt * 8, st)); return 0; }
     dim3 grid((unsigned)U, (unsigned)((Tt + SUM_TPB - 1) / SUM_TPB));
-    if (pts) k_sum_pixel_signals<true><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, pts);
-    else k_sum_pixel_signals<false><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, nullptr);
+    if (pts) k_sum_pixel_signals<true, false><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, pts);
+    else if (fresh) k_sum_pixel_signals<false, true><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, nullptr);
+    else k_sum_pixel_signals<false, false><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, nullptr);
     LSB_LAUNCH_CHECK("k_sum_pixel_signals");
     return 0;
 }
