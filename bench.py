@@ -409,6 +409,43 @@ def run_ours(args, rank, world, local_rank):
             light_block["cpu_python_restatement"] = {"seconds": cpu_s, "sample": "trigger search on all channels + digitisation of 1 trigger x 8 channels (of %d x %d), 1 core" % (len(t_o), c_o.shape[1])}
     except Exception as exc:
         light_block = {"error": repr(exc)}
+    # ---------------- BASELINE metric, second half: the deterministic tracks_current kernel (detsim.py:351-453) ----------------
+    # (not called by the CLI; a bounded sample of the same batch: SAMPLED_POINTS^2 x z_steps rho evaluations per pair and tick slab)
+    tc_block = None
+    try:
+        import helpers as hh
+        from larndsim_b200 import detsim, quenching, drifting, pixels_from_track as pft
+        n_tc = 128
+        sub = tracks[:n_tc].copy()
+        d_sub = ll.DeviceRecords(host=sub)
+        quenching.quench[1, 1](d_sub, int(lc.snapshot().mode_birks))
+        drifting.drift[1, 1](d_sub)
+        fr = hh.oracle_front(sub.copy(), hh.Oracle(lc.snapshot()))         # pixel lists / tick count of the sample (host)
+        neigh = torch.from_numpy(fr["neigh"]).cuda()
+        sig_tc = torch.zeros((n_tc, fr["P"], fr["T"]), dtype=torch.float32, device="cuda")
+        resp_d = torch.from_numpy(response).cuda()
+        detsim.tracks_current[1, 1](sig_tc, neigh, d_sub, resp_d)
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sig_tc.zero_()
+        t0e.record()
+        detsim.tracks_current[1, 1](sig_tc, neigh, d_sub, resp_d)
+        t1e.record()
+        torch.cuda.synchronize()
+        tc_ms = t0e.elapsed_time(t1e)
+        live_pairs = int((sig_tc != 0).any(dim=2).sum().item())
+        live_ticks = int((sig_tc != 0).sum().item())
+        sp = int(mod.detector.SAMPLED_POINTS)
+        n_rho = float(live_pairs) * sp * sp * sp                              # z_steps >= SAMPLED_POINTS: a lower bound
+        flops = 110.0 * n_rho + 2.0 * sp * sp * sp * live_ticks                # 110 N_rho + 2 N_rho T_act
+        sm_clk_tc = 1965.0
+        tc_block = {"segments": n_tc, "ms": tc_ms, "segments_per_s": n_tc / (tc_ms * 1e-3), "live_pairs": live_pairs,
+                    "flops_lower_bound": flops, "achieved_tflops_lower_bound": flops / (tc_ms * 1e-3) / 1e12,
+                    "fp32_peak_tflops": 148 * 128 * 2 * sm_clk_tc * 1e6 / 1e12, "frac_of_fp32_peak_lower_bound": flops / (tc_ms * 1e-3) / (148 * 128 * 2 * sm_clk_tc * 1e6),
+                    "note": "the kernel evaluates rho (erf, exp, log) and the table products in float64 like the reference, so its own ceiling is the "
+                            "FP64 / transcendental rate, not FP32 FFMA; flops count the algorithmic formulation with z_steps = SAMPLED_POINTS"}
+    except Exception as exc:
+        tc_block = {"error": repr(exc)}
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peaks()
     Tt = int(lc.snapshot().n_time_ticks)
@@ -493,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": float(t.item()) / args.steps},
             "gpu_launches": int(launches), "per_rank": per_rank, "host_ms_per_step": {"wait_for_oldest_batch": 1e3 * host_t["collect"] / max(host_t["n"], 1),
                                                               "submit_next_batch": 1e3 * host_t["submit"] / max(host_t["n"], 1)},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block, "light_triggers": light_block,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block, "light_triggers": light_block, "tracks_current": tc_block,
             "ms_per_step_unpipelined": ms_serial,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}, "kernels": kernels}
     print(json.dumps(line), flush=True)

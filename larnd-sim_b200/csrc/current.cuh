@@ -1128,6 +1128,10 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
 #define TC_TPB 256
 #define TC_RMAX 8
 #define TC_MAXNP 64
+#define TC_MAXBIN 24          // response bins per axis the binned path handles (24 * 0.044 cm > 8 sigma_T + a bin)
+#ifndef TC_BINNED
+#define TC_BINNED 1
+#endif
 
 struct TcPair {
     double start[3], seg[3], dir[3], sig[3];
@@ -1135,7 +1139,36 @@ struct TcPair {
     double x_start, y_start, x_step, y_step, z_start_int, z_step;
     long long z_steps;
     int valid, c32, s32;
+    // point-independent parts of rho (same expressions as rho_dev, evaluated once per pair)
+    double r_ux, r_uy, r_uz, r_d0, r_d1, r_d2, r_e0, r_e1, r_e2, r_sqrt_a_2, r_two_a_Dr, r_four_a, r_factor, r_log_factor;
 };
+
+// rho with the pair's invariants taken from TcPair (bit-identical to rho_dev)
+__device__ __forceinline__ void rho_prepare(TcPair& g) {
+    const bool c32 = g.c32, s32 = g.s32;
+    const double* seg = g.seg; const double* sig = g.sig;
+    double Dr = seg_length(seg, c32);
+    g.r_ux = R32(seg[0] / Dr, c32); g.r_uy = R32(seg[1] / Dr, c32); g.r_uz = R32(seg[2] / Dr, c32);
+    double a = R32(g.r_ux * g.r_ux, c32) / (2 * sig[0] * sig[0]) + R32(g.r_uy * g.r_uy, c32) / (2 * sig[1] * sig[1]) +
+               R32(g.r_uz * g.r_uz, c32) / (2 * sig[2] * sig[2]);
+    double sprod = R32(R32(sig[0] * sig[1], s32) * sig[2], s32);
+    g.r_factor = g.q / Dr / (sprod * sqrt(8 * M_PI * M_PI * M_PI));
+    g.r_log_factor = log(g.r_factor);
+    g.r_sqrt_a_2 = 2 * sqrt(a);
+    g.r_d0 = R32(sig[0] * sig[0], s32); g.r_d1 = R32(sig[1] * sig[1], s32); g.r_d2 = R32(sig[2] * sig[2], s32);
+    g.r_e0 = 2 * sig[0] * sig[0]; g.r_e1 = 2 * sig[1] * sig[1]; g.r_e2 = 2 * sig[2] * sig[2];
+    g.r_two_a_Dr = 2 * a * Dr;
+    g.r_four_a = 4 * a;
+}
+__device__ __forceinline__ double rho_fast(double x, double y, double z, const TcPair& g) {
+    const double dx = x - g.start[0], dy = y - g.start[1], dz = z - g.start[2];
+    double b = -(dx / g.r_d0 * g.r_ux + dy / g.r_d1 * g.r_uy + dz / g.r_d2 * g.r_uz);
+    double delta = dx * dx / g.r_e0 + dy * dy / g.r_e1 + dz * dz / g.r_e2;
+    double integral = sqrt(M_PI) * (-erf(b / g.r_sqrt_a_2) + erf((b + g.r_two_a_Dr) / g.r_sqrt_a_2)) / g.r_sqrt_a_2;
+    double expo = 0;
+    if (g.r_factor != 0 && integral != 0) expo = exp(b * b / g.r_four_a - delta + g.r_log_factor + log(integral));
+    return expo;
+}
 
 __device__ double rho_dev(const double* pt, const TcPair& g) {
     const bool c32 = g.c32, s32 = g.s32;
@@ -1203,6 +1236,7 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
                                                            float* __restrict__ signals) {
     __shared__ TcPair g;
     __shared__ double s_charge[TC_MAXNP * TC_MAXNP];
+    __shared__ double s_bin[TC_MAXBIN * TC_MAXBIN];
     __shared__ int s_i[TC_MAXNP], s_j[TC_MAXNP];
     __shared__ int s_xok[TC_MAXNP], s_yok[TC_MAXNP];
     __shared__ int s_anyx;
@@ -1251,6 +1285,7 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
             long long plane = (long long)fld_get(L, t, LSB_F_PIXEL_PLANE);
             if (plane < 0 || plane >= d_c.n_tpc) break;
             g.z_anode = d_c.tpc_borders[plane][2][0];
+            rho_prepare(g);
             g.valid = 1;
         } while (0);
         s_anyx = 0;
@@ -1273,6 +1308,14 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
     }
     __syncthreads();
     const int anyx = s_anyx;
+    // response bins touched by the grid: [imin, imin + nbi) x [jmin, jmin + nbj); the binned path needs them to fit s_bin
+    int imin = 1 << 30, imax = -1, jmin = 1 << 30, jmax = -1;
+    for (int q = 0; q < NP; q++) {
+        if (s_i[q] >= 0) { imin = s_i[q] < imin ? s_i[q] : imin; imax = s_i[q] > imax ? s_i[q] : imax; }
+        if (s_j[q] >= 0) { jmin = s_j[q] < jmin ? s_j[q] : jmin; jmax = s_j[q] > jmax ? s_j[q] : jmax; }
+    }
+    const int nbi = imax >= imin ? imax - imin + 1 : 0, nbj = jmax >= jmin ? jmax - jmin + 1 : 0;
+    const bool binned = TC_BINNED && nbi <= TC_MAXBIN && nbj <= TC_MAXBIN;
     float* out = signals + (itrk * P + ipix) * (long long)T;
     const double vol = fabs(g.x_step) * fabs(g.y_step) * fabs(g.z_step);
     for (int base = 0; base < T; base += TC_TPB * TC_RMAX) {
@@ -1290,11 +1333,25 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
                 if (s_xok[ix] && s_yok[iy]) {
                     double pt[3] = {g.x_start + sgx * (ix * g.x_step - 4 * g.sig[0]),
                                     g.y_start + sgy * (iy * g.y_step - 4 * g.sig[1]), z};
-                    ch = rho_dev(pt, g) * fabs(g.x_step) * fabs(g.y_step) * fabs(g.z_step);
+                    ch = rho_fast(pt[0], pt[1], pt[2], g) * fabs(g.x_step) * fabs(g.y_step) * fabs(g.z_step);
                 }
                 s_charge[c] = ch;
             }
             __syncthreads();
+            if (binned) {
+                // charge per response bin, summed in the reference's (ix, iy) order within the bin
+                for (int b = tid; b < nbi * nbj; b += TC_TPB) {
+                    const int bi = b / nbj, bj = b % nbj;
+                    double sum = 0.0;
+                    for (int ix = 0; ix < NP; ix++) {
+                        if (s_i[ix] != imin + bi) continue;                 // (s_i >= 0 implies the point is inside the table in x)
+                        for (int iy = 0; iy < NP; iy++)
+                            if (s_j[iy] == jmin + bj) sum += s_charge[ix * NP + iy];
+                    }
+                    s_bin[bi * TC_MAXBIN + bj] = sum;
+                }
+                __syncthreads();
+            }
 #pragma unroll
             for (int r = 0; r < TC_RMAX; r++) {
                 int it = base + tid + r * TC_TPB;
@@ -1306,15 +1363,29 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
                 long long k = __double2ll_rn((tick - t0) / d_c.response_sampling);
                 bool kok = 0 <= k && k < Rt;
                 double tot = total[r];
-                for (int ix = 0; ix < NP; ix++) {
-                    if (!s_xok[ix]) continue;
-                    int i = s_i[ix];
-                    for (int iy = 0; iy < NP; iy++) {
-                        if (!s_yok[iy]) continue;
-                        int j = s_j[iy];
-                        double w = 0;
-                        if (kok && i >= 0 && j >= 0) w = (double)lut[((long long)i * Ry + j) * Rt + k];
-                        tot += w * s_charge[ix * NP + iy];
+                if (binned) {
+                    // the grid points of the slab fall into a few response bins: one table read per bin, weighted with the
+                    // bin's summed charge (the reference reads the table once per grid point)
+                    if (kok)
+                        for (int bi = 0; bi < nbi; bi++) {
+                            const double* lrow = nullptr;
+                            for (int bj = 0; bj < nbj; bj++) {
+                                const double w = (double)lut[((long long)(imin + bi) * Ry + (jmin + bj)) * Rt + k];
+                                tot += w * s_bin[bi * TC_MAXBIN + bj];
+                            }
+                            (void)lrow;
+                        }
+                } else {
+                    for (int ix = 0; ix < NP; ix++) {
+                        if (!s_xok[ix]) continue;
+                        int i = s_i[ix];
+                        for (int iy = 0; iy < NP; iy++) {
+                            if (!s_yok[iy]) continue;
+                            int j = s_j[iy];
+                            double w = 0;
+                            if (kok && i >= 0 && j >= 0) w = (double)lut[((long long)i * Ry + j) * Rt + k];
+                            tot += w * s_charge[ix * NP + iy];
+                        }
                     }
                 }
                 total[r] = tot;
