@@ -1128,7 +1128,7 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
 #define TC_TPB 256
 #define TC_RMAX 8
 #define TC_MAXNP 64
-#define TC_MAXBIN 24          // response bins per axis the binned path handles (24 * 0.044 cm > 8 sigma_T + a bin)
+#define TC_MAXBIN 40          // response bins per axis the binned path handles (the grid of one pair spans < 2 cm)
 #ifndef TC_BINNED
 #define TC_BINNED 1
 #endif
@@ -1237,6 +1237,7 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
     __shared__ TcPair g;
     __shared__ double s_charge[TC_MAXNP * TC_MAXNP];
     __shared__ double s_bin[TC_MAXBIN * TC_MAXBIN];
+    __shared__ int s_xoff[TC_MAXBIN + 1], s_yoff[TC_MAXBIN + 1], s_xmem[TC_MAXNP], s_ymem[TC_MAXNP];
     __shared__ int s_i[TC_MAXNP], s_j[TC_MAXNP];
     __shared__ int s_xok[TC_MAXNP], s_yok[TC_MAXNP];
     __shared__ int s_anyx;
@@ -1316,6 +1317,20 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
     }
     const int nbi = imax >= imin ? imax - imin + 1 : 0, nbj = jmax >= jmin ? jmax - jmin + 1 : 0;
     const bool binned = TC_BINNED && nbi <= TC_MAXBIN && nbj <= TC_MAXBIN;
+    if (binned && tid < 2) {
+        // grid indices grouped by response bin (counting sort, once per pair; bins do not depend on the z slab)
+        const int* key = tid == 0 ? s_i : s_j;
+        const int kmin = tid == 0 ? imin : jmin, nb = tid == 0 ? nbi : nbj;
+        int* off = tid == 0 ? s_xoff : s_yoff;
+        int* mem = tid == 0 ? s_xmem : s_ymem;
+        int run = 0;
+        for (int b = 0; b < nb; b++) {
+            off[b] = run;
+            for (int q = 0; q < NP; q++) if (key[q] == kmin + b) mem[run++] = q;
+        }
+        off[nb] = run;
+    }
+    __syncthreads();
     float* out = signals + (itrk * P + ipix) * (long long)T;
     const double vol = fabs(g.x_step) * fabs(g.y_step) * fabs(g.z_step);
     for (int base = 0; base < T; base += TC_TPB * TC_RMAX) {
@@ -1343,17 +1358,21 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
                 for (int b = tid; b < nbi * nbj; b += TC_TPB) {
                     const int bi = b / nbj, bj = b % nbj;
                     double sum = 0.0;
-                    for (int ix = 0; ix < NP; ix++) {
-                        if (s_i[ix] != imin + bi) continue;                 // (s_i >= 0 implies the point is inside the table in x)
-                        for (int iy = 0; iy < NP; iy++)
-                            if (s_j[iy] == jmin + bj) sum += s_charge[ix * NP + iy];
+                    for (int a = s_xoff[bi]; a < s_xoff[bi + 1]; a++) {       // members of the bin, ascending ix / iy
+                        const int ix = s_xmem[a];
+                        for (int c2 = s_yoff[bj]; c2 < s_yoff[bj + 1]; c2++) sum += s_charge[ix * NP + s_ymem[c2]];
                     }
                     s_bin[bi * TC_MAXBIN + bj] = sum;
                 }
                 __syncthreads();
             }
+            // per tick of this thread: inside the slab's window?  table index?
+            long long kr[TC_RMAX];
+            bool use[TC_RMAX];
+            bool any_use = false;
 #pragma unroll
             for (int r = 0; r < TC_RMAX; r++) {
+                use[r] = false; kr[r] = 0;
                 int it = base + tid + r * TC_TPB;
                 if (it >= T) continue;
                 double tick = g.t_start + (double)it * d_c.time_sampling;
@@ -1361,21 +1380,35 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
                 if (!(t0 < tick && tick < t0 + d_c.time_window)) continue;
                 if (anyx) written[r] = true;
                 long long k = __double2ll_rn((tick - t0) / d_c.response_sampling);
-                bool kok = 0 <= k && k < Rt;
-                double tot = total[r];
-                if (binned) {
-                    // the grid points of the slab fall into a few response bins: one table read per bin, weighted with the
-                    // bin's summed charge (the reference reads the table once per grid point)
-                    if (kok)
-                        for (int bi = 0; bi < nbi; bi++) {
-                            const double* lrow = nullptr;
-                            for (int bj = 0; bj < nbj; bj++) {
-                                const double w = (double)lut[((long long)(imin + bi) * Ry + (jmin + bj)) * Rt + k];
-                                tot += w * s_bin[bi * TC_MAXBIN + bj];
-                            }
-                            (void)lrow;
+                kr[r] = k;
+                use[r] = 0 <= k && k < Rt;
+                any_use |= use[r];
+            }
+            if (binned) {
+                // the grid points of the slab fall into a few response bins: one table read per bin and tick, weighted with the
+                // bin's summed charge (the reference reads the table once per grid point); the bin loop is outermost so one
+                // row pointer serves the thread's TC_RMAX ticks
+                if (any_use)
+                    for (int bi = 0; bi < nbi; bi++) {
+                        const TL* prow = lut + ((long long)(imin + bi) * Ry + jmin) * Rt;
+                        for (int bj = 0; bj < nbj; bj++, prow += Rt) {
+                            const double B = s_bin[bi * TC_MAXBIN + bj];
+#pragma unroll
+                            for (int r = 0; r < TC_RMAX; r++)
+                                if (use[r]) total[r] += (double)prow[kr[r]] * B;
                         }
-                } else {
+                    }
+            } else {
+#pragma unroll
+                for (int r = 0; r < TC_RMAX; r++) {
+                    int it = base + tid + r * TC_TPB;
+                    if (it >= T) continue;
+                    double tick = g.t_start + (double)it * d_c.time_sampling;
+                    if (tick < 0.) continue;
+                    if (!(t0 < tick && tick < t0 + d_c.time_window)) continue;
+                    const long long k = kr[r];
+                    const bool kok = use[r];
+                    double tot = total[r];
                     for (int ix = 0; ix < NP; ix++) {
                         if (!s_xok[ix]) continue;
                         int i = s_i[ix];
@@ -1387,8 +1420,8 @@ __global__ void __launch_bounds__(TC_TPB) k_tracks_current(Layout L, const char*
                             tot += w * s_charge[ix * NP + iy];
                         }
                     }
+                    total[r] = tot;
                 }
-                total[r] = tot;
             }
         }
 #pragma unroll
