@@ -45,6 +45,13 @@ def launches(path):
     for k, a in sorted(acc.items(), key=lambda kv: -kv[1][1]):
         print("| %s | %d | %.1f | %.1f%% |" % (k, a[0], a[1], 100 * a[1] / tot))
     print("\ntotal %.1f us over %d launches (ncu serialised, cold-cache: compare shares, not absolutes)" % (tot, sum(a[0] for a in acc.values())))
+    # bench.py also measures three stages outside the timed chain (deterministic tracks_current, packet builder, light
+    # triggers): their kernels are in the same process, so the share of the chain's dominant kernel is given separately
+    side = ("k_tracks_current", "k_pkt_", "k_scan3", "k_lt_", "k_table_lookup")
+    chain = {k: a for k, a in acc.items() if not k.startswith(side)}
+    ctot = sum(a[1] for a in chain.values())
+    print("\nkernels of the timed chain only (%.1f us): " % ctot + ", ".join(
+        "%s %.1f%%" % (k.split("<")[0], 100 * a[1] / ctot) for k, a in sorted(chain.items(), key=lambda kv: -kv[1][1])[:6]))
 
 
 def report(path):
