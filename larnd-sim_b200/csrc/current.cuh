@@ -24,6 +24,11 @@
 #include "common.cuh"
 #include "glue.cuh"
 
+#ifndef ACC_GW
+#define ACC_GW 4                         // table words per group of the grouped accumulate path: 4 (lane = 4 ticks, LDG.128
+#endif                                   // windows; default) or 8 (lane = 8 ticks, 256-bit loads: measured slower on B200,
+                                         // 5.05 + 0.75 ms against 4.62 + 0.56 ms, profiles/r01_mc_grouped.md)
+
 struct PairRec {
     double x_p, y_p, t_start, z_anode;
     double sub_start[3];
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
                         if (khi == (long long)p.stride * hi + sh) shift = (int)sh;
                         // the grouped accumulate path reads the table in aligned 4-word blocks: a sample that reaches
                         // the last complete block of the table (or the partial one after it) takes the exact path
-                        const long long L4 = (((long long)p.Rx * p.Ry * p.Rt) & ~3LL) - 4;
+                        const long long L4 = (((long long)p.Rx * p.Ry * p.Rt) & ~(long long)(ACC_GW - 1)) - ACC_GW;
                         if ((long long)s.rowoff + khi >= L4) shift = SHIFT_IRREGULAR;
                     }
                     r.t0 = t0; r.rowoff = s.rowoff; r.shift = shift; r.lo = lo; r.hi = hi;
@@ -412,10 +417,30 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
 // table, off = 4q + d, carrying the number of samples at each d.  Offsets are taken relative to the pair's
 // first interior tick (key = off + int_lo), so key + (tick - int_lo) is the table index and never negative.
 struct __align__(16) GroupRec { int q; __half2 c01, c23; int pad; };      // counts <= 512: exact in binary16
+// 8-word variant (ACC_GW == 8): off = 8q + d, d = 0..7; 24 bytes (the uniforms buffer the records reuse has 24 bytes per sample)
+struct __align__(8) GroupRec8 { int q; int pad; __half2 c[4]; };
+#if ACC_GW == 8
+typedef GroupRec8 GroupRecT;
+#define ACC_GSH 3
+#else
+typedef GroupRec GroupRecT;
+#define ACC_GSH 2
+#endif
+__device__ __forceinline__ void group_store(GroupRecT* dst, int q, const int (&c)[ACC_GW]) {
+    GroupRecT g;
+    g.q = q; g.pad = 0;
+#if ACC_GW == 8
+#pragma unroll
+    for (int k = 0; k < 4; k++) g.c[k] = __floats2half2_rn((float)c[2 * k], (float)c[2 * k + 1]);
+#else
+    g.c01 = __floats2half2_rn((float)c[0], (float)c[1]); g.c23 = __floats2half2_rn((float)c[2], (float)c[3]);
+#endif
+    *dst = g;
+}
 #define SORT_WARPS 4
 #define SORT_MAXKEYS 512
 template <int NR>
-__device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int n, int key_add, int* s_buf, GroupRec* __restrict__ out,
+__device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int n, int key_add, int* s_buf, GroupRecT* __restrict__ out,
                                                int lane) {
     int v[NR];
 #pragma unroll
@@ -454,11 +479,13 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
 #pragma unroll
     for (int r = 0; r < NR; r++) { const int pos = lane * NR + r; s_buf[pos + (pos >> 5)] = v[r]; }
     __syncwarp();
-    // group heads: position whose 4-word block differs from its predecessor's.  Runs are measured with ballots (32
-    // positions at a time); the last run of a row stays "pending" (warp-uniform registers) because it may continue
-    // in the next row.
+    // group heads: position whose aligned ACC_GW-word block differs from its predecessor's.  Runs are measured with ballots
+    // (32 positions at a time); the last run of a row stays "pending" (warp-uniform registers) because it may continue in
+    // the next row.
     int ng = 0;
-    int pq = 0, pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0;
+    int pq = 0, pc[ACC_GW];
+#pragma unroll
+    for (int k = 0; k < ACC_GW; k++) pc[k] = 0;
     bool pending = false;
 #pragma unroll
     for (int r = 0; r < NR; r++) {
@@ -466,46 +493,40 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
         const int key = s_buf[pos + (pos >> 5)];                       // padding keys (INT_MAX) sort last
         const int prev = pos > 0 ? s_buf[pos - 1 + ((pos - 1) >> 5)] : OFF_IRREGULAR;
         const bool valid = pos < n && key != OFF_IRREGULAR;
-        const bool head = valid && (prev == OFF_IRREGULAR || (prev >> 2) != (key >> 2));
+        const bool head = valid && (prev == OFF_IRREGULAR || (prev >> ACC_GSH) != (key >> ACC_GSH));
         const unsigned m = __ballot_sync(0xffffffffu, head);
-        const int d = key & 3;
-        const unsigned m0 = __ballot_sync(0xffffffffu, valid && d == 0), m1 = __ballot_sync(0xffffffffu, valid && d == 1);
-        const unsigned m2 = __ballot_sync(0xffffffffu, valid && d == 2), m3 = __ballot_sync(0xffffffffu, valid && d == 3);
+        const int d = key & (ACC_GW - 1);
+        unsigned md[ACC_GW];
+#pragma unroll
+        for (int k = 0; k < ACC_GW; k++) md[k] = __ballot_sync(0xffffffffu, valid && d == k);
         const unsigned lead = m ? ((1u << (__ffs(m) - 1)) - 1u) : 0xffffffffu;     // positions continuing the pending run
-        if (pending) { pc0 += __popc(m0 & lead); pc1 += __popc(m1 & lead); pc2 += __popc(m2 & lead); pc3 += __popc(m3 & lead); }
+        if (pending) {
+#pragma unroll
+            for (int k = 0; k < ACC_GW; k++) pc[k] += __popc(md[k] & lead);
+        }
         if (m) {
             if (pending) {
-                if (lane == 0) {
-                    GroupRec g;
-                    g.q = pq; g.c01 = __floats2half2_rn((float)pc0, (float)pc1); g.c23 = __floats2half2_rn((float)pc2, (float)pc3); g.pad = 0;
-                    out[ng] = g;
-                }
+                if (lane == 0) group_store(out + ng, pq, pc);
                 ng++;
             }
             const unsigned below = (1u << lane) - 1u;
             const unsigned higher = lane == 31 ? 0u : (m & ~((2u << lane) - 1u));
             const unsigned upto = higher ? ((1u << (__ffs(higher) - 1)) - 1u) : 0xffffffffu;
             const unsigned run = upto & ~below;
-            const int c0 = __popc(m0 & run), c1 = __popc(m1 & run), c2 = __popc(m2 & run), c3 = __popc(m3 & run);
-            if (head && higher) {
-                GroupRec g;
-                g.q = key >> 2; g.c01 = __floats2half2_rn((float)c0, (float)c1); g.c23 = __floats2half2_rn((float)c2, (float)c3); g.pad = 0;
-                out[ng + __popc(m & below)] = g;
-            }
+            int c[ACC_GW];
+#pragma unroll
+            for (int k = 0; k < ACC_GW; k++) c[k] = __popc(md[k] & run);
+            if (head && higher) group_store(out + ng + __popc(m & below), key >> ACC_GSH, c);
             const int src = 31 - __clz(m);                                         // last head of the row: the new pending run
-            pq = __shfl_sync(0xffffffffu, key >> 2, src);
-            pc0 = __shfl_sync(0xffffffffu, c0, src); pc1 = __shfl_sync(0xffffffffu, c1, src);
-            pc2 = __shfl_sync(0xffffffffu, c2, src); pc3 = __shfl_sync(0xffffffffu, c3, src);
+            pq = __shfl_sync(0xffffffffu, key >> ACC_GSH, src);
+#pragma unroll
+            for (int k = 0; k < ACC_GW; k++) pc[k] = __shfl_sync(0xffffffffu, c[k], src);
             pending = true;
             ng += __popc(m) - 1;
         }
     }
     if (pending) {
-        if (lane == 0) {
-            GroupRec g;
-            g.q = pq; g.c01 = __floats2half2_rn((float)pc0, (float)pc1); g.c23 = __floats2half2_rn((float)pc2, (float)pc3); g.pad = 0;
-            out[ng] = g;
-        }
+        if (lane == 0) group_store(out + ng, pq, pc);
         ng++;
     }
     __syncwarp();
@@ -513,7 +534,7 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
 }
 
 __global__ void __launch_bounds__(32 * SORT_WARPS) k_mc_sort(McParams p, PairRec* __restrict__ pairs, const int* __restrict__ offs32,
-                                                             GroupRec* __restrict__ groups) {
+                                                             GroupRecT* __restrict__ groups) {
     MC_GUARD(p);
     __shared__ int s_buf[SORT_WARPS][SORT_MAXKEYS + SORT_MAXKEYS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -526,7 +547,7 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_mc_sort(McParams p, PairRec
     int ng = 0;
     if (n_reg > 0 && gp->int_lo <= gp->int_hi) {
         const int* keys = offs32 + gp->sample_off;
-        GroupRec* out = groups + gp->sample_off;          // <= one record per sample
+        GroupRecT* out = groups + gp->sample_off;         // <= one record per sample
         for (int c0 = 0; c0 < n_live; c0 += SORT_MAXKEYS) {
             const int n = n_live - c0 < SORT_MAXKEYS ? n_live - c0 : SORT_MAXKEYS;
             if (n <= 32) ng += warp_sort_group<1>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
@@ -692,10 +713,68 @@ __device__ __forceinline__ void acc_gather(const float4* __restrict__ lut4, int 
     }
 }
 
+// ---- 8-word groups: lane = 8 consecutive ticks, 16-word window fetched with two 256-bit loads ------------------------
+struct __align__(32) float8 { float v[8]; };
+__device__ __forceinline__ float8 ldg256(const float* p) {
+    float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void acc_apply8(const int2& c0123, const int2& c4567, const float8& lo, const float8& hi, float (&acc)[8]) {
+    const float w[16] = {lo.v[0], lo.v[1], lo.v[2], lo.v[3], lo.v[4], lo.v[5], lo.v[6], lo.v[7],
+                         hi.v[0], hi.v[1], hi.v[2], hi.v[3], hi.v[4], hi.v[5], hi.v[6], hi.v[7]};
+    const int packed[4] = {c0123.x, c0123.y, c4567.x, c4567.y};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (packed[k] == 0) continue;                                   // both counts of the pair are zero
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&packed[k]));
+        if (c.x != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(c.x, w[2 * k + j], acc[j]);
+        }
+        if (c.y != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(c.y, w[2 * k + 1 + j], acc[j]);
+        }
+    }
+}
+// one warp, one block of 256 ticks: walks the pair's group records; record g+1 and its window are in flight while group g
+// is applied; float32 partial sums are folded into float64 every ACC_FLUSH groups
+__device__ __forceinline__ void acc_gather8(const float* __restrict__ lut, int n8m2, const GroupRec8* __restrict__ grp, int ng, int Qb,
+                                            double (&dacc)[8]) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    const int2* recs = reinterpret_cast<const int2*>(grp);              // 3 x int2 per record: {q, pad} {c01, c23} {c45, c67}
+    int2 h = __ldg(recs), ca = __ldg(recs + 1), cb = __ldg(recs + 2);
+    const float* w0 = lut + 8LL * min(Qb + h.x, n8m2);
+    float8 lo = ldg256(w0), hi = ldg256(w0 + 8);
+    for (int g = 0; g < ng; g++) {
+        int2 nh = h, nca = ca, ncb = cb;
+        float8 nlo = lo, nhi = hi;
+        if (g + 1 < ng) {
+            nh = __ldg(recs + 3 * (g + 1)); nca = __ldg(recs + 3 * (g + 1) + 1); ncb = __ldg(recs + 3 * (g + 1) + 2);
+            // blocks past the end of the table are clamped into it: they only feed ticks that are not stored
+            const float* w1 = lut + 8LL * min(Qb + nh.x, n8m2);
+            nlo = ldg256(w1); nhi = ldg256(w1 + 8);
+        }
+        acc_apply8(ca, cb, lo, hi, acc);
+        if ((g & (ACC_FLUSH - 1)) == ACC_FLUSH - 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { dacc[j] += (double)acc[j]; acc[j] = 0.f; }
+        }
+        h = nh; ca = nca; cb = ncb; lo = nlo; hi = nhi;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) dacc[j] += (double)acc[j];
+}
+
 template <typename TL, int STRIDE, bool FAST>
 __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
                                                            const SampleRec* __restrict__ samples,
-                                                           const int* __restrict__ offs32, const GroupRec* __restrict__ groups,
+                                                           const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
                                                            const TL* __restrict__ lut, float* __restrict__ signals) {
     MC_GUARD(p);
     long long pr = blockIdx.x;
@@ -719,14 +798,30 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
     if (STRIDE == 0 || n_live - n_irr <= 0 || int_lo > int_hi) { int_lo = 0; int_hi = -1; }   // no interior
 
     // ---- interior ticks, grouped path ------------------------------------------------
-    // Tick blocks of 128 are dealt round-robin to the warps; warps run independently (no barrier).
+    // Tick blocks are dealt round-robin to the warps; warps run independently (no barrier).
     if constexpr (FAST) {
         constexpr int NW = ACC_TPB / 32;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int ng = gp->n_groups;
+#if ACC_GW == 8
+        // lane = 8 consecutive ticks, block = 256 ticks
+        const int n8m2 = (int)(((long long)p.Rx * p.Ry * p.Rt) >> 3) - 2;
+        const GroupRec8* grp = groups + soff;
+        for (int tb = int_lo + 256 * warp; tb <= int_hi; tb += 256 * NW) {
+            double dacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) dacc[j] = 0.0;
+            acc_gather8(reinterpret_cast<const float*>(lut), n8m2, grp, ng, ((tb - int_lo) >> 3) + lane, dacc);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int it = tb + 8 * lane + j;
+                if (it <= int_hi) out[it] = __double2float_rn(charge * dacc[j]);
+            }
+        }
+#else
         const float4* lut4 = reinterpret_cast<const float4*>(lut);
         const int n4m2 = (int)(((long long)p.Rx * p.Ry * p.Rt) >> 2) - 2;
-        const int lane = tid & 31, warp = tid >> 5;
         const GroupRec* grp = groups + soff;
-        const int ng = gp->n_groups;
         for (int tb = int_lo; tb <= int_hi; tb += 128 * NW * ACC_FB) {
             double dacc[ACC_FB][4];
             int Qb[ACC_FB];
@@ -749,6 +844,7 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
                     if (r < nR && it <= int_hi) out[it] = __double2float_rn(charge * dacc[r][j]);
                 }
         }
+#endif
     }
     // ---- interior ticks, generic path: unconditional gather stream ---------------------
     if (STRIDE > 0 && !FAST) {
@@ -985,10 +1081,10 @@ static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut,
     unsigned grid = (unsigned)(p.S * p.P);
     if (p.stride == 1) {
         if constexpr (sizeof(TL) == 4) {
-            if (lsb_mc_get_grouped() && ((uintptr_t)lut & 15) == 0) {
+            if (lsb_mc_get_grouped() && ((uintptr_t)lut & (4 * ACC_GW - 1)) == 0) {
                 // grouped path: equal / adjacent offsets must be neighbours
                 // group records reuse the uniforms buffer (dead after k_mc_sampler; 24 bytes per sample >= one 16-byte record)
-                GroupRec* groups = reinterpret_cast<GroupRec*>(w.uu);
+                GroupRecT* groups = reinterpret_cast<GroupRecT*>(w.uu);
                 k_mc_sort<<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                 LSB_LAUNCH_CHECK("k_mc_sort");
                 k_mc_accumulate<TL, 1, true><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, lut, signals);
