@@ -180,3 +180,46 @@ def test_beam_spill_batches_other_geometries(cuda, config, kind, n):
     b = _run_chain(n, 777, config=config, kind=kind)
     for k in ("uniq", "tpm", "adc", "digit", "ticks", "cf", "ps_sum"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_chain_edge_batches(cuda):
+    """Degenerate batches through the fused chain: one segment; segments outside every TPC (no pixels, no hits); and the
+    host-buffer entry point (`run_host`, the e2e path) giving the same packets as the device entry point."""
+    import torch
+    from larndsim_b200 import chain as lchain
+    mod = lc.load_snapshot("module0")
+    resp = synth.response_lut(mod.detector)
+    tracks = h.production_tracks(400, "module0", 31, "cosmic")
+    ch = lchain.Chain(tracks.dtype, resp)
+    # (1) a single segment
+    one = tracks[:1].copy()
+    r1 = ch.run(ll.DeviceRecords(host=one), rng_seed=2)
+    assert r1.n_segments == 1 and r1.n_unique_pixels > 0
+    sig = r1.signals
+    assert tuple(sig.shape) == (1, r1.max_neighbors, r1.n_ticks) and torch.isfinite(sig).all()
+    # (2) everything outside the detector: no TPC contains the segments -> no pixels at all
+    out = tracks[:50].copy()
+    for f in ("x", "x_start", "x_end"):
+        out[f] += 1.0e4
+    r2 = ch.run(ll.DeviceRecords(host=out), rng_seed=2)
+    assert r2.n_segments == 50 and r2.n_hits == 0
+    assert r2.n_unique_pixels == 0 or float(r2.pixels_signals.abs().sum()) == 0.0
+    # (3) host entry point == device entry point: identical hit table.  (The RNG states of a chain evolve from batch to batch
+    # like the reference's, simulate_pixels.py:1015,1079 -- so each entry point gets a fresh chain.)
+    ch.close()
+    ch = lchain.Chain(tracks.dtype, resp)
+    dev = ch.run(ll.DeviceRecords(host=tracks.copy()), rng_seed=5)
+    U, A = dev.n_unique_pixels, dev.adc_digit.shape[1]
+    d_uniq, d_adc, d_ticks = dev.unique_pix.cpu().numpy(), dev.adc_digit.cpu().numpy(), dev.adc_ticks_list.cpu().numpy()
+    ucap = U + 100
+    ch.close()
+    ch = lchain.Chain(tracks.dtype, resp)
+    h_tr = torch.from_numpy(tracks.copy().view(np.uint8).reshape(-1)).pin_memory()
+    o_uniq = torch.empty(ucap, dtype=torch.int32).pin_memory()
+    o_adc = torch.empty((ucap, A), dtype=torch.float64).pin_memory()
+    o_ticks = torch.empty((ucap, A), dtype=torch.float64).pin_memory()
+    hr = ch.run_host(h_tr, o_uniq, o_adc, o_ticks, rng_seed=5)
+    assert hr.n_unique_pixels == U and hr.n_hits == dev.n_hits
+    assert np.array_equal(o_uniq.numpy()[:U], d_uniq) and np.array_equal(o_adc.numpy()[:U], d_adc)
+    assert np.array_equal(o_ticks.numpy()[:U], d_ticks)
+    ch.close()
