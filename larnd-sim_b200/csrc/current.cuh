@@ -783,8 +783,12 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
         if (p.ranges && threadIdx.x == 0) p.ranges[(p.seg0 + pr / p.P) * p.P + (pr % p.P)] = make_int2(0, -1);
         return;
     }
-    __shared__ __align__(16) int s_off[ACC_CHUNK];
-    __shared__ SampleRec s_rec[ACC_TPB];
+    // one staging buffer for the phases that follow each other (each separated by a barrier): sample offsets of the generic
+    // interior, 16-byte edge records, full sample records of the irregular path -- less shared memory is more L1 for the table
+    __shared__ __align__(16) char s_stage[ACC_CHUNK * 16];
+    int* s_off = reinterpret_cast<int*>(s_stage);
+    SampleRec* s_rec = reinterpret_cast<SampleRec*>(s_stage);
+    static_assert(sizeof(SampleRec) * ACC_TPB <= ACC_CHUNK * 16, "staging buffer too small for the irregular path");
     const int tid = threadIdx.x;
     const int T = p.T;
     const int it_first = gp->it_first, n_live = gp->n_live;
@@ -910,7 +914,7 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
         // flight together and their float32 sum is folded into float64.
         constexpr int NG = ACC_TPB / 32;
         __shared__ double s_part[NG][32];
-        __shared__ int4 s_erec[ACC_CHUNK];
+        int4* s_erec = reinterpret_cast<int4*>(s_stage);
         const int lane = tid & 31, grp = tid >> 5;
         for (int e0 = 0; e0 < n_edge; e0 += 32) {
             const int e = e0 + lane;
