@@ -122,3 +122,37 @@ def test_gpu_trigger_edge_cases_and_noise(cuda):
     assert abs((a - clean).mean()) < 0.2 * (a - clean).std()
     n = light_sim.gen_light_detector_noise((4, 1001), spec[:4]).cpu().numpy()
     assert n.shape == (4, 1001) and np.array_equal(np.round(n / q) * q, n) and n.std() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_threshold_triggers_across_modules(cuda):
+    """Threshold mode on a 4-module geometry (2x2 tables, LIGHT_TRIG_MODE forced to 0): every module searches its own
+    triggers; pulses on the channels of modules 1 and 3 only.  CUDA == restatement (the single-module cases pin the
+    restatement to the reference)."""
+    from larndsim_b200 import light_sim
+    p = _provider("2x2")
+    z = ltu.load("2x2")
+    C = ltu.consts_from_npz(z)
+    C["LIGHT_TRIG_MODE"] = 0
+    saved = p.light.LIGHT_TRIG_MODE
+    p.light.LIGHT_TRIG_MODE = 0
+    try:
+        rng = np.random.default_rng(9)
+        ndet, nticks = C["N_OP_CHANNEL"], 6000
+        op = np.arange(ndet, dtype=np.int64)
+        sig = rng.normal(0, 3, (ndet, nticks)).astype(np.float32)
+        t2c = np.asarray(C["TPC_TO_OP_CHANNEL"])
+        for mod, t0 in ((1, 700), (3, 1500), (3, 5200)):
+            chans = t2c[C["MODULE_TO_TPCS"][mod]].ravel()
+            sig[chans, t0:t0 + 100] -= (4000.0 * np.exp(-np.arange(100) / 20.0))[None, :].astype(np.float32)
+        thr = ltu.thresholds(C, op)
+        o_trig, o_ch, o_k = lo.get_triggers(sig, thr, op, 0, C)
+        g_trig, g_ch, g_k = light_sim.get_triggers(sig, thr, op, 0)
+        assert len(o_trig) >= 2 and len(set(map(tuple, o_ch))) >= 2 and np.array_equal(o_trig, g_trig) and np.array_equal(o_ch, g_ch) and np.array_equal(o_k, g_k)
+        tid = np.full((ndet, nticks, 0), -1, dtype=np.int64); tph = np.zeros((ndet, nticks, 0))
+        ns = 200
+        d = light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig, op, tid, tph, g_trig, g_ch, ns, np.zeros((ndet, 33)))[0].cpu().numpy()
+        o = lo.sim_triggers(sig, op, tid, tph, o_trig[:1], o_ch[:1, :12], ns, C)[0]
+        assert np.array_equal(d[:1, :12], o) and (d != 0).sum() > 0
+    finally:
+        p.light.LIGHT_TRIG_MODE = saved
