@@ -437,7 +437,9 @@ __device__ __forceinline__ void group_store(GroupRecT* dst, int q, const int (&c
 #endif
     *dst = g;
 }
+#ifndef SORT_WARPS
 #define SORT_WARPS 4
+#endif
 #define SORT_MAXKEYS 512
 template <int NR>
 __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int n, int key_add, int* s_buf, GroupRecT* __restrict__ out,
@@ -533,7 +535,10 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
     return ng;
 }
 
-__global__ void __launch_bounds__(32 * SORT_WARPS) k_mc_sort(McParams p, PairRec* __restrict__ pairs, const int* __restrict__ offs32,
+#ifndef SORT_MINB
+#define SORT_MINB 12
+#endif
+__global__ void __launch_bounds__(32 * SORT_WARPS, SORT_MINB) k_mc_sort(McParams p, PairRec* __restrict__ pairs, const int* __restrict__ offs32,
                                                              GroupRecT* __restrict__ groups) {
     MC_GUARD(p);
     __shared__ int s_buf[SORT_WARPS][SORT_MAXKEYS + SORT_MAXKEYS / 32];
