@@ -635,7 +635,7 @@ __device__ __forceinline__ void acc_interior(const TL* __restrict__ lut, const i
 #define ACC_FB 1                         // 128-tick blocks a warp register-blocks
 #endif
 #ifndef ACC_MINB
-#define ACC_MINB 8
+#define ACC_MINB 10
 #endif
 #define ACC_FLUSH 2                      // groups between two float32 -> float64 folds (<= 8 terms, like the generic path)
 template <int R>
