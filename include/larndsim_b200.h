@@ -340,6 +340,27 @@ int lsb_light_digitize(const void* signal, int32_t signal_f64, int64_t nticks, i
                        double* digit_signal, int64_t* digit_true_track_id, double* digit_true_photons, int32_t n_truth_out,
                        void* stream);
 
+/* ---- active volume + batching (the callers that cut the segment array into units) ------- */
+/* larndsim/active_volume.py:4-46  select_active_volume: first_tpc[i] = lowest TPC index in [tpc_lo, tpc_hi) whose open
+ * box contains the start OR the end point of segment i (float64 comparisons), -1 if none; the reference's return value
+ * (`nonzero(mask)[0]`) is `indices[0 .. *n_selected)` (ascending; optional: pass NULL to skip the compaction).
+ * borders: DEVICE f64[n_tpc,3,2] (either order on the last axis: sorted on load, active_volume.py:24).
+ * i_module >= 1 in the reference is tpc_lo = 2*(i_module-1), tpc_hi = 2*i_module. */
+int64_t lsb_active_volume_ws_bytes(int64_t n);
+int lsb_active_volume(const lsb_track_layout* L, const void* tracks, int64_t n, const double* borders, int32_t n_tpc,
+                      int32_t tpc_lo, int32_t tpc_hi, int32_t* first_tpc, int64_t* indices, int64_t* n_selected,
+                      void* ws, int64_t ws_bytes, void* stream);
+/* larndsim/util/batching.py:17-67  TPCBatcher, every batch of the run in one call.  Unit u = e * n_tpc_batches + b is
+ * the batch the reference's iterator yields at position u: event events_sorted[e] (= np.unique of the event field,
+ * batching.py:29) and TPCs [b*tpc_batch_size, (b+1)*tpc_batch_size).  A segment belongs to the FIRST batch of its
+ * event that contains it (the `_simulated` mask, batching.py:49,63), i.e. b = first_tpc / tpc_batch_size.
+ * order[unit_offsets[u] .. unit_offsets[u+1]) = the rows `mask` selects for unit u, ascending (tracks[mask] order);
+ * rows in no unit follow at order[unit_offsets[n_units] .. n).  event field: byte offset + lsb_dtype in the record. */
+int64_t lsb_batch_units_ws_bytes(int64_t n);
+int lsb_batch_units(const void* tracks, int64_t n, int32_t itemsize, int32_t event_offset, int32_t event_dtype,
+                    const int64_t* events_sorted, int64_t n_events, const int32_t* first_tpc, int32_t tpc_batch_size,
+                    int32_t n_tpc_batches, int64_t* order, int64_t* unit_offsets, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- static key -> value table ----------------------------------------------------------- */
 /* larndsim/util/cuda_dict.py:1-230  CudaDict lookup / contains (per-pixel thresholds and gains,
  * cli/simulate_pixels.py:1080-1100): out[i] = value of query[i] or *default_host; exists[i] = 1 if present.

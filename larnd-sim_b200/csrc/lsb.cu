@@ -99,6 +99,7 @@ LSB_EXPORT int64_t lsb_profile_end(char* out, int64_t cap) {
 #include "light.cuh"
 #include "packets.cuh"
 #include "light_trigger.cuh"
+#include "batching.cuh"
 #include "chain.cuh"
 
 LSB_EXPORT int lsb_abi_version(void) { return LSB_ABI_VERSION; }
