@@ -99,8 +99,9 @@ class TPCBatcher(TrackSegmentBatcher):
         if self._curr_event >= len(self._events):
             raise StopIteration
         self._plan()
-        u = self._curr_event * self.n_tpc_batches + self._curr_tpc // self.tpc_batch_size
         mask = np.zeros(self._n, dtype=bool)
-        mask[self._order[int(self._offsets[u]):int(self._offsets[u + 1])]] = True
+        if self.n_tpc_batches:                                   # (no TPCs: the reference still yields empty masks)
+            u = self._curr_event * self.n_tpc_batches + self._curr_tpc // self.tpc_batch_size
+            mask[self._order[int(self._offsets[u]):int(self._offsets[u + 1])]] = True
         self._curr_tpc += self.tpc_batch_size
         return self._events[self._curr_event], mask
