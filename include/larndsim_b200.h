@@ -340,6 +340,13 @@ int lsb_light_digitize(const void* signal, int32_t signal_f64, int64_t nticks, i
                        double* digit_signal, int64_t* digit_true_track_id, double* digit_true_photons, int32_t n_truth_out,
                        void* stream);
 
+/* larndsim/light_sim.py:24-42 get_nticks and :44-57 get_active_op_channel, device part: over light_incidence[n_segments][ndet]
+ * entries with n_photons_det > 0: t0_minmax[0] = min t0_det, t0_minmax[1] = max t0_det (float32; +inf / -inf when there is
+ * none), active[d] = 1 if any segment gives photons to channel d.  All pointers device. */
+int lsb_light_extent(const void* light_incidence, const lsb_linc_layout* LI, int64_t n_segments, int32_t ndet,
+                     float* t0_minmax, uint8_t* active, void* stream);
+
+
 /* ---- active volume + batching (the callers that cut the segment array into units) ------- */
 /* larndsim/active_volume.py:4-46  select_active_volume: first_tpc[i] = lowest TPC index in [tpc_lo, tpc_hi) whose open
  * box contains the start OR the end point of segment i (float64 comparisons), -1 if none; the reference's return value

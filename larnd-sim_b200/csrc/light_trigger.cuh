@@ -215,3 +215,67 @@ LSB_EXPORT int lsb_light_digitize(const void* signal, int32_t signal_f64, int64_
     LSB_LAUNCH_CHECK("k_lt_digitize");
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// extent of the light simulation window: light_sim.get_nticks (:24-42) and get_active_op_channel (:44-57)
+// One pass over light_incidence[S][ndet]: among entries with n_photons_det > 0 the earliest / latest t0_det (float32,
+// reduced through an order-preserving integer code) and, per channel, whether any segment lights it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f32_ordered(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t c) {
+    return __uint_as_float((c & 0x80000000u) ? (c & 0x7fffffffu) : ~c);
+}
+__global__ void k_lt_extent_init(uint32_t* __restrict__ code, uint8_t* __restrict__ active, int ndet) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { code[0] = 0xffffffffu; code[1] = 0u; }
+    if (i < ndet) active[i] = 0;
+}
+__global__ void k_lt_extent(const char* __restrict__ linc, lsb_linc_layout LI, long long n, int ndet, uint32_t* __restrict__ code,
+                            uint8_t* __restrict__ active) {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const char* rec = linc + i * (long long)LI.itemsize;
+        if (*(const float*)(rec + LI.off_n_photons_det) > 0.0f) {
+            const uint32_t c = f32_ordered(*(const float*)(rec + LI.off_t0_det));
+            lo = min(lo, c);
+            hi = max(hi, c);
+            active[i % ndet] = 1;                       // same value from every writer
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(code, lo);
+        atomicMax(code + 1, hi);
+    }
+}
+__global__ void k_lt_extent_finish(uint32_t* __restrict__ code) {
+    const bool any = code[0] <= code[1];
+    const float lo = any ? f32_unordered(code[0]) : INFINITY, hi = any ? f32_unordered(code[1]) : -INFINITY;
+    ((float*)code)[0] = lo;
+    ((float*)code)[1] = hi;
+}
+
+LSB_EXPORT int lsb_light_extent(const void* light_incidence, const lsb_linc_layout* LI, int64_t n_segments, int32_t ndet,
+                                float* t0_minmax, uint8_t* active, void* stream) {
+    LSB_REQUIRE(LI && t0_minmax && (active || ndet == 0) && (light_incidence || n_segments * (int64_t)ndet == 0),
+                "light_extent: null pointer");
+    LSB_REQUIRE(n_segments >= 0 && ndet >= 0, "light_extent: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* code = (uint32_t*)t0_minmax;
+    k_lt_extent_init<<<lsb_blocks(ndet > 0 ? ndet : 1, 256), 256, 0, st>>>(code, active, ndet);
+    LSB_LAUNCH_CHECK("k_lt_extent_init");
+    const long long n = n_segments * (long long)ndet;
+    if (n > 0) {
+        long long nb = (n + 255) / 256;
+        if (nb > 148 * 16) nb = 148 * 16;
+        k_lt_extent<<<(unsigned)nb, 256, 0, st>>>((const char*)light_incidence, *LI, n, ndet, code, active);
+        LSB_LAUNCH_CHECK("k_lt_extent");
+    }
+    k_lt_extent_finish<<<1, 1, 0, st>>>(code);
+    LSB_LAUNCH_CHECK("k_lt_extent_finish");
+    return 0;
+}

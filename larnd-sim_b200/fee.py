@@ -116,3 +116,117 @@ def _write_larpix_file(filename, packets, ds):
         for key, val in (("vdrift", d.V_DRIFT), ("long_diff", d.LONG_DIFF), ("tran_diff", d.TRAN_DIFF),
                          ("lifetime", d.ELECTRON_LIFETIME), ("drift_length", d.DRIFT_LENGTH)):
             f["configs"].attrs[key] = val
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the small host helpers of the reference module (a handful of records per event: no kernel involved)
+# ---------------------------------------------------------------------------------------------------------
+def get_trig_io():
+    """``get_trig_io()`` (fee.py:28-36): io_group the light trigger is forwarded to."""
+    from . import consts as _consts
+    mode = _consts.provider().light.LIGHT_TRIG_MODE
+    if mode == 0:
+        return 2
+    if mode == 1:
+        return 1
+    raise UnboundLocalError("cannot access local variable 'trig_io' where it is not associated with a value")
+
+
+def rotate_tile(pixel_id, tile_id):
+    """``rotate_tile(pixel_id, tile_id)`` (fee.py:38-62): pixel indices inside a (possibly mirrored) tile."""
+    from . import consts as _consts
+    d = _consts.provider().detector
+    orient = d.TILE_ORIENTATIONS
+    axes = orient[tile_id] if tile_id in orient else orient[str(tile_id)]
+    pix_x, pix_y = pixel_id[0], pixel_id[1]
+    if axes[2] < 0:
+        pix_x = d.N_PIXELS_PER_TILE[0] - pixel_id[0] - 1
+    if axes[1] < 0:
+        pix_y = d.N_PIXELS_PER_TILE[1] - pixel_id[1] - 1
+    return pix_x, pix_y
+
+
+def gen_event_times(nevents, t0=None):
+    """``gen_event_times(nevents, t0=NON_BEAM_EVENT_GAP)`` (fee.py:64-81): cumulative exponential gaps [us], float64 CUDA
+    tensor.  The reference draws from ``cupy.random`` (unseeded, unpinned); torch's CUDA generator is used here."""
+    from . import consts as _consts
+    d = _consts.provider().detector
+    t0 = d.NON_BEAM_EVENT_GAP if t0 is None else t0
+    gaps = torch.empty(int(nevents), dtype=torch.float64, device="cuda").exponential_(1.0 / float(d.EVENT_RATE))
+    return torch.cumsum(gaps, 0) + t0
+
+
+def _host(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    if hasattr(a, "get"):
+        return np.asarray(a.get())
+    return np.asarray(a)
+
+
+def _no_truth_rows(n):
+    from . import packets as _p
+    from . import consts as _consts
+    ds = np.zeros(n, dtype=_p.assn_dtype(int(_consts.provider().sim.ASSOCIATION_COUNT_TO_STORE)))
+    ds["event_ids"], ds["segment_ids"], ds["file_traj_ids"] = -1, -1, -1
+    return ds
+
+
+def _module_io_groups(d, i_mod):
+    mio = {int(k): list(v) for k, v in dict(d.MODULE_TO_IO_GROUPS).items()}
+    if i_mod > 0:
+        return list(mio[i_mod])
+    return np.unique(np.array(list(mio.values()))).tolist()
+
+
+def _finish_export(filename, packets, ds):
+    if filename and len(packets):
+        try:
+            import h5py                                                  # noqa: F401
+            from larpix.format import hdf5format                         # noqa: F401
+        except ImportError:
+            return packets, ds
+        _write_larpix_file(filename, packets, ds)
+    return packets, ds
+
+
+def export_sync_to_hdf5(filename, sync_times, i_mod=-1):
+    """``export_sync_to_hdf5(filename, sync_times, i_mod=-1)`` (fee.py:361-425): one sync packet per (sync time, io_group)
+    -> ``(packets, packets_mc_ds)`` as ``packets.PACKET_DTYPE`` records (the file is written when ``larpix`` / ``h5py``
+    are importable).  Sync times that are not a multiple of the reset period are floored with the reference's warning.
+    With no sync time the reference fails on an unbound name; empty arrays are returned here."""
+    import warnings
+    from . import packets as _p
+    from . import consts as _consts
+    d = _consts.provider().detector
+    io_groups = _module_io_groups(d, i_mod)
+    ticks = _host(sync_times) / d.CLOCK_CYCLE
+    rows = []
+    for tick in np.atleast_1d(ticks):
+        if tick % d.CLOCK_RESET_PERIOD != 0:
+            warnings.warn("The provided sync time is not the mutiply of the reset period!")
+            tick = tick // d.CLOCK_RESET_PERIOD * d.CLOCK_RESET_PERIOD
+        for g in io_groups:
+            rows.append((_p.PT_SYNC, int(g), ord("S"), int(tick)))
+    packets = np.zeros(len(rows), dtype=_p.PACKET_DTYPE)
+    for i, (pt, g, sub, ts) in enumerate(rows):
+        packets[i]["packet_type"], packets[i]["io_group"], packets[i]["sub_type"], packets[i]["timestamp"] = pt, g, sub, ts
+    return _finish_export(filename, packets, _no_truth_rows(len(rows)))
+
+
+def export_timestamp_trigger_to_hdf5(filename, event_start_times, i_mod=-1):
+    """``export_timestamp_trigger_to_hdf5(filename, event_start_times, i_mod=-1)`` (fee.py:427-497): per event start time
+    a timestamp packet [s] and a trigger packet (type 0x02, tick modulo the reset period) on the trigger io_group."""
+    from . import packets as _p
+    from . import consts as _consts
+    p = _consts.provider()
+    d, un = p.detector, p.units
+    times = np.atleast_1d(_host(event_start_times))
+    packets = np.zeros(2 * len(times), dtype=_p.PACKET_DTYPE)
+    for i, evt_time in enumerate(times):
+        g = get_trig_io()
+        a, b = packets[2 * i], packets[2 * i + 1]
+        a["packet_type"], a["io_group"], a["timestamp_s"] = _p.PT_TIMESTAMP, g, evt_time * un.mus / un.s
+        b["packet_type"], b["io_group"], b["sub_type"] = _p.PT_TRIGGER, g, 2
+        b["timestamp"] = int(np.floor(evt_time / d.CLOCK_CYCLE)) % d.CLOCK_RESET_PERIOD
+    return _finish_export(filename, packets, _no_truth_rows(len(packets)))

@@ -107,6 +107,47 @@ def calc_light_detector_response(light_sample_inc, light_sample_inc_true_track_i
 
 
 # ---------------------------------------------------------------------------------------------------------
+# extent of the light window (the callers in front of sum_light_signals, cli/simulate_pixels.py:1119-1135)
+# ---------------------------------------------------------------------------------------------------------
+def _extent(light_incidence):
+    import torch
+    from . import _abi
+    li = _l.dev(light_incidence, name="light_incidence", records=True)
+    if len(li.shape) != 2:
+        raise ValueError("light_incidence must have shape (ntracks, ndet)")
+    S, ndet = li.shape
+    LI = _abi.linc_layout(li.dtype)
+    mm = torch.empty(2, dtype=torch.float32, device="cuda")
+    active = torch.empty(ndet, dtype=torch.uint8, device="cuda")
+    _l.check(_l.lib().lsb_light_extent(li.c, C.byref(LI), C.c_int64(S), C.c_int32(ndet), C.c_void_p(mm.data_ptr()),
+                                       C.c_void_p(active.data_ptr()), _l.stream()), "light_extent")
+    return mm, active
+
+
+def get_nticks(light_incidence):
+    """``get_nticks(light_incidence)`` (light_sim.py:24-42) -> (number of light ticks, time of the first tick [us]).
+    The arithmetic on the float32 extremes is NumPy's (float32 scalars against Python floats), as in the reference."""
+    light = _consts.provider().light
+    mm, active = _extent(light_incidence)
+    lo, hi = (np.float32(v) for v in mm.cpu().numpy())
+    # the reference's constants are Python numbers (consts/light.py:122-123): weakly typed against the float32 extremes
+    w0, w1, tick = (v.item() if hasattr(v, "item") else v for v in (light.LIGHT_WINDOW[0], light.LIGHT_WINDOW[1], light.LIGHT_TICK_SIZE))
+    if bool(active.any().item()) and light.LIGHT_TRIG_MODE == 0:
+        start_time = lo - w0
+        end_time = hi + w1
+        return int(np.ceil((end_time - start_time) / tick)), start_time
+    return int((w1 + w0) / tick), 0
+
+
+def get_active_op_channel(light_incidence):
+    """``get_active_op_channel(light_incidence)`` (light_sim.py:44-57) -> int32 CUDA tensor of the channels some segment
+    gives photons to."""
+    import torch
+    _, active = _extent(light_incidence)
+    return torch.nonzero(active).reshape(-1).to(torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # trigger search and digitisation (SURVEY 8f rank 3)
 # ---------------------------------------------------------------------------------------------------------
 def _host_ids(a):

@@ -165,3 +165,37 @@ def sim_triggers(signal, signal_op_channel_idx, true_track_id, true_photons, tri
                         out_ph[it, im, s, n - 1] = interp(st - t0, (p0, p1), 0, 0)
     q = 2 ** (16 - C["LIGHT_NBIT"])
     return np.round(out / q) * q, out_id, out_ph
+
+
+# ---------------------------------------------------------------------------------------------------------
+# extent of the light window: get_nticks (larndsim/light_sim.py:24-42), get_active_op_channel (:44-57)
+# pinned by tools/gen_golden_light_extent.py -> tests/golden/light_extent.npz
+# ---------------------------------------------------------------------------------------------------------
+def lit_extremes(light_incidence):
+    """(earliest, latest first-photon time among entries with photons, per-channel 'lit' flags), explicit loops"""
+    S, ndet = light_incidence.shape
+    lo = hi = None
+    lit = np.zeros(ndet, dtype=bool)
+    nph, t0 = light_incidence["n_photons_det"], light_incidence["t0_det"]
+    for s in range(S):
+        for d in range(ndet):
+            if nph[s, d] > 0:
+                lit[d] = True
+                v = t0[s, d]
+                lo = v if lo is None or v < lo else lo
+                hi = v if hi is None or v > hi else hi
+    return lo, hi, lit
+
+
+def get_nticks(light_incidence, C):
+    """``C``: LIGHT_TRIG_MODE, LIGHT_WINDOW, LIGHT_TICK_SIZE.  float32 extremes combined with Python floats stay float32."""
+    lo, hi, lit = lit_extremes(light_incidence)
+    if lit.any() and C["LIGHT_TRIG_MODE"] == 0:
+        start = lo - C["LIGHT_WINDOW"][0]
+        stop = hi + C["LIGHT_WINDOW"][1]
+        return int(np.ceil((stop - start) / C["LIGHT_TICK_SIZE"])), start
+    return int((C["LIGHT_WINDOW"][1] + C["LIGHT_WINDOW"][0]) / C["LIGHT_TICK_SIZE"]), 0
+
+
+def get_active_op_channel(light_incidence):
+    return np.nonzero(lit_extremes(light_incidence)[2])[0].astype(np.int32)

@@ -179,3 +179,50 @@ def export_packets(tables, event_id_list, adc_list, adc_ticks_list, unique_pix, 
     store("file_traj_ids", "fraction_traj", t_ids, t_frac, 0.0)
     ds["event_ids"] = np.array(mc_evt)
     return packets, ds
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sync / timestamp + trigger packets between events: export_sync_to_hdf5 (larndsim/fee.py:361-425) and
+# export_timestamp_trigger_to_hdf5 (:427-497).  Pinned by tools/gen_golden_sync_trigger.py ->
+# tests/golden/sync_trigger_<config>.npz (the reference's own functions with recording stand-ins for larpix / h5py).
+# ---------------------------------------------------------------------------------------------------------
+def _blank_truth(n, count):
+    ds = np.zeros(n, dtype=assn_dtype(count))
+    ds["event_ids"] = -1
+    ds["segment_ids"] = -1
+    ds["file_traj_ids"] = -1
+    return ds
+
+
+def sync_packets(tables, sync_times, i_mod=-1):
+    """one 'S' sync packet per (time, io_group); times [us] are converted to clock ticks and floored to the reset period"""
+    groups = np.unique(np.array(list(tables["module_to_io_groups"].values())))
+    if i_mod > 0:
+        groups = tables["module_to_io_groups"][i_mod]
+    out = []
+    for t in np.asarray(sync_times, dtype=np.float64):
+        tick = t / tables["clock_cycle"]
+        period = tables["clock_reset_period"]
+        if tick % period != 0:
+            tick = tick // period * period
+        for g in groups:
+            r = np.zeros((), dtype=PACKET_DTYPE)
+            r["packet_type"], r["io_group"], r["sub_type"], r["timestamp"] = PT_SYNC, g, ord("S"), int(tick)
+            out.append(r)
+    return (np.array(out, dtype=PACKET_DTYPE) if out else np.zeros(0, dtype=PACKET_DTYPE)), \
+        _blank_truth(len(out), tables["association_count"])
+
+
+def timestamp_trigger_packets(tables, event_start_times):
+    """per event start time [us]: a timestamp packet [s] then a trigger packet (0x02) on the trigger io_group"""
+    g = 2 if tables["light_trig_mode"] == 0 else 1
+    out = []
+    for t in np.asarray(event_start_times, dtype=np.float64):
+        a = np.zeros((), dtype=PACKET_DTYPE)
+        a["packet_type"], a["io_group"], a["timestamp_s"] = PT_TIMESTAMP, g, t * tables["mus"] / tables["s"]
+        b = np.zeros((), dtype=PACKET_DTYPE)
+        b["packet_type"], b["io_group"], b["sub_type"] = PT_TRIGGER, g, 2
+        b["timestamp"] = int(np.floor(t / tables["clock_cycle"])) % tables["clock_reset_period"]
+        out += [a, b]
+    return (np.array(out, dtype=PACKET_DTYPE) if out else np.zeros(0, dtype=PACKET_DTYPE)), \
+        _blank_truth(len(out), tables["association_count"])

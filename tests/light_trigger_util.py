@@ -79,3 +79,26 @@ def thresholds(C, op):
     cpt = C["OP_CHANNEL_PER_TRIG"]
     thr_all = np.repeat(np.asarray(C["LIGHT_TRIG_THRESHOLD"])[..., np.newaxis], cpt, axis=-1).ravel()
     return thr_all[op].copy().reshape(-1, cpt)[..., 0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# light window extent (get_nticks / get_active_op_channel)
+# ---------------------------------------------------------------------------------------------------------
+LINC_DTYPE = np.dtype([("segment_id", "u4"), ("n_photons_det", "f4"), ("t0_det", "f4")])
+EXTENT_CASES = ("lit", "dark", "one_entry", "negative_times", "empty")
+
+
+def extent_inputs(case, ndet=96):
+    rng = np.random.default_rng(sum(map(ord, case)))
+    S = {"lit": 150, "dark": 40, "one_entry": 60, "negative_times": 80, "empty": 0}[case]
+    li = np.zeros((S, ndet), dtype=LINC_DTYPE)
+    li["segment_id"] = np.arange(S, dtype=np.uint32)[:, None]
+    li["t0_det"] = (rng.random((S, ndet)) * 300 - (150 if case == "negative_times" else 0)).astype(np.float32)
+    if case in ("lit", "negative_times"):
+        nph = rng.random((S, ndet)) * 50
+        nph[rng.random((S, ndet)) < 0.6] = 0
+        nph[:, rng.random(ndet) < 0.4] = 0              # channels nobody lights
+        li["n_photons_det"] = nph.astype(np.float32)
+    elif case == "one_entry":
+        li["n_photons_det"][S // 2, 17] = 3.5
+    return li

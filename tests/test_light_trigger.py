@@ -156,3 +156,56 @@ def test_gpu_threshold_triggers_across_modules(cuda):
         assert np.array_equal(d[:1, :12], o) and (d != 0).sum() > 0
     finally:
         p.light.LIGHT_TRIG_MODE = saved
+
+
+# ---------------------------------------------------------------------------------------- light window extent
+def _extent_golden(config):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "light_extent_%s.npz" % config))
+    mode, w0, w1, tick = z["consts"]
+    return z, {"LIGHT_TRIG_MODE": int(mode), "LIGHT_WINDOW": (float(w0), float(w1)), "LIGHT_TICK_SIZE": float(tick)}
+
+
+def _extent_input(z, case):
+    inc = ltu.extent_inputs(case)
+    assert np.array_equal([inc["n_photons_det"].sum(dtype=np.float64), inc["t0_det"].sum(dtype=np.float64)], z[case + "_sum"])
+    return inc
+
+
+@pytest.mark.parametrize("config", ("module0", "2x2"))
+def test_oracle_light_extent_matches_reference(config):
+    z, C = _extent_golden(config)
+    for case in ltu.EXTENT_CASES:
+        inc = _extent_input(z, case)
+        n, t0 = lo.get_nticks(inc, C)
+        assert n == int(z[case + "_nticks"])
+        assert np.asarray(t0).dtype == z[case + "_start"].dtype and np.asarray(t0) == z[case + "_start"]
+        act = lo.get_active_op_channel(inc)
+        assert act.dtype == np.int32 and np.array_equal(act, z[case + "_active"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", ("module0", "2x2"))
+def test_gpu_light_extent_identical(cuda, config):
+    import torch
+    from larndsim_b200 import light_sim
+    z, C = _extent_golden(config)
+    p = _provider(config)
+    assert int(p.light.LIGHT_TRIG_MODE) == C["LIGHT_TRIG_MODE"] and tuple(p.light.LIGHT_WINDOW) == C["LIGHT_WINDOW"]
+    for case in ltu.EXTENT_CASES:
+        inc = _extent_input(z, case)
+        n, t0 = light_sim.get_nticks(inc)
+        assert n == int(z[case + "_nticks"])
+        assert np.asarray(t0).dtype == z[case + "_start"].dtype and np.asarray(t0) == z[case + "_start"]
+        act = light_sim.get_active_op_channel(inc)
+        assert isinstance(act, torch.Tensor) and act.is_cuda and act.dtype == torch.int32
+        assert np.array_equal(act.cpu().numpy(), z[case + "_active"])
+    # a table large enough for many blocks: extremes planted at known places
+    big = ltu.extent_inputs("lit")
+    big = np.tile(big, (400, 1))
+    big["t0_det"][31234, 5], big["n_photons_det"][31234, 5] = -1234.5, 1.0
+    big["t0_det"][59999, 95], big["n_photons_det"][59999, 95] = 98765.25, 2.0
+    big["t0_det"][100, 7], big["n_photons_det"][100, 7] = -5e6, 0.0            # no photons: must not count
+    n, t0 = light_sim.get_nticks(big)
+    n_ref, t0_ref = lo.get_nticks(big[[31234, 59999]], C)
+    assert (n, t0) == (n_ref, t0_ref)

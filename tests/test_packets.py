@@ -143,3 +143,75 @@ def test_readout_tables_from_the_config_snapshot_match_the_reference_run():
         assert np.array_equal(getattr(a, name), getattr(b, name)), name
     for f in ("clock_cycle", "adc_pedestal", "mus", "s", "clock_reset_period", "light_trig_mode", "n_tiles", "n_modules"):
         assert getattr(a._c, f) == getattr(b._c, f), f
+
+
+# ---------------------------------------------------------------------------------------- sync / timestamp / trigger
+def _sync_golden(config):
+    import os
+    return np.load(os.path.join(pu.GOLDEN, "sync_trigger_%s.npz" % config))
+
+
+def _check_small(packets, ds, z, prefix):
+    kind = z[prefix + "_pk_kind"]
+    assert packets.dtype == po.PACKET_DTYPE and len(packets) == len(kind) == len(ds) and len(kind) > 0
+    assert np.array_equal(packets["packet_type"], kind)
+    assert np.array_equal(packets["io_group"], z[prefix + "_pk_io_group"])
+    ts = kind == po.PT_TIMESTAMP
+    assert np.array_equal(packets["timestamp_s"][ts], z[prefix + "_pk_ts_float"][ts])            # bit-identical float64
+    assert np.array_equal(packets["timestamp"][~ts].astype(np.int64), z[prefix + "_pk_timestamp"][~ts])
+    assert np.array_equal(packets["sub_type"][~ts].astype(np.int64), z[prefix + "_pk_sub_type"][~ts])
+    for f in ds.dtype.names:
+        assert ds[f].dtype == z[prefix + "_assn_" + f].dtype or ds[f].dtype.kind == z[prefix + "_assn_" + f].dtype.kind
+        assert np.array_equal(ds[f], z[prefix + "_assn_" + f])
+
+
+def _small_tables(z):
+    cc, period, mode, count = z["consts"]
+    return dict(clock_cycle=float(cc), clock_reset_period=int(period), light_trig_mode=int(mode), association_count=int(count))
+
+
+@pytest.mark.parametrize("config", ("module0", "2x2"))
+def test_oracle_sync_and_trigger_packets_match_reference(config):
+    from larndsim_b200 import consts as lc
+    z = _sync_golden(config)
+    p = lc.load_snapshot(config)
+    T = _small_tables(z)
+    T.update(module_to_io_groups={int(k): list(v) for k, v in dict(p.detector.MODULE_TO_IO_GROUPS).items()}, mus=p.units.mus, s=p.units.s)
+    assert (p.detector.CLOCK_CYCLE, int(p.detector.CLOCK_RESET_PERIOD)) == (T["clock_cycle"], T["clock_reset_period"])
+    for m in z["modules"]:
+        _check_small(*po.sync_packets(T, z["in_sync"], int(m)), z, "sync%d" % m)
+        _check_small(*po.timestamp_trigger_packets(T, z["in_starts"]), z, "tt%d" % m)
+
+
+@pytest.mark.parametrize("config", ("module0", "2x2"))
+def test_fee_sync_and_trigger_helpers_match_reference(config):
+    """host helpers of the drop-in (no kernel involved): same packets, same truth rows, same warning"""
+    import warnings
+    from larndsim_b200 import consts as lc, fee
+    z = _sync_golden(config)
+    lc.load_snapshot(config)
+    assert fee.get_trig_io() == int(z["trig_io"])
+    for m in z["modules"]:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            packets, ds = fee.export_sync_to_hdf5(None, z["in_sync"], int(m))
+        assert len(w) == int(z["sync%d_nwarn" % m])
+        _check_small(packets, ds, z, "sync%d" % m)
+        _check_small(*fee.export_timestamp_trigger_to_hdf5(None, z["in_starts"], int(m)), z, "tt%d" % m)
+    for t, px, py, rx, ry in z["rotate_tile"]:
+        assert fee.rotate_tile((int(px), int(py)), int(t)) == (rx, ry)
+    packets, ds = fee.export_sync_to_hdf5(None, np.empty(0))
+    assert len(packets) == 0 and len(ds) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_gen_event_times(cuda):
+    import torch
+    from larndsim_b200 import consts as lc, fee
+    p = lc.load_snapshot("module0")
+    t = fee.gen_event_times(20000, 5.0)
+    assert t.is_cuda and t.dtype == torch.float64 and t.shape == (20000,)
+    gaps = torch.diff(t).cpu().numpy()
+    assert (gaps > 0).all() and float(t[0]) > 5.0
+    assert abs(gaps.mean() / float(p.detector.EVENT_RATE) - 1) < 0.05            # exponential with scale EVENT_RATE
+    assert abs(gaps.std() / float(p.detector.EVENT_RATE) - 1) < 0.1

@@ -25,7 +25,8 @@ DET = ["LAR_DENSITY", "E_FIELD", "V_DRIFT", "ELECTRON_LIFETIME", "LONG_DIFF", "T
        "RESET_CYCLES", "CLOCK_CYCLE", "GAIN", "BUFFER_RISETIME", "V_CM", "V_REF", "V_PEDESTAL", "ADC_COUNTS",
        "RESET_NOISE_CHARGE", "UNCORRELATED_NOISE_CHARGE", "DISCRIMINATOR_NOISE", "MODULE_TO_TPCS",
        # readout tables of the packet builder (fee.export_to_hdf5)
-       "CLOCK_RESET_PERIOD", "MODULE_TO_IO_GROUPS", "TILE_MAP", "TILE_ORIENTATIONS", "TILE_CHIP_TO_IO"]
+       "CLOCK_RESET_PERIOD", "MODULE_TO_IO_GROUPS", "TILE_MAP", "TILE_ORIENTATIONS", "TILE_CHIP_TO_IO",
+       "EVENT_RATE", "NON_BEAM_EVENT_GAP"]
 LIGHT = ["LIGHT_SIMULATED", "ENABLE_LUT_SMEARING", "N_OP_CHANNEL", "OP_CHANNEL_EFFICIENCY", "OP_CHANNEL_TO_TPC",
          "SCINT_PRESCALE", "W_PH", "LIGHT_TICK_SIZE", "LIGHT_WINDOW", "SINGLET_FRACTION", "TAU_S", "TAU_T",
          "LIGHT_GAIN", "SIPM_RESPONSE_MODEL", "LIGHT_RESPONSE_TIME", "LIGHT_OSCILLATION_PERIOD",
