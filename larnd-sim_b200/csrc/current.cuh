@@ -307,7 +307,9 @@ __device__ __forceinline__ float normal_from_uniforms(float u1, float u2) {     
     return __fmul_rn(a, b);
 }
 
+#ifndef SMP_WARPS
 #define SMP_WARPS 4
+#endif
 #ifndef SMP_MINB
 #define SMP_MINB 8
 #endif
@@ -566,9 +568,13 @@ __global__ void __launch_bounds__(32 * SORT_WARPS, SORT_MINB) k_mc_sort(McParams
 }
 
 // ---------------------------------------------------------------------------------------
+#ifndef ACC_TPB
 #define ACC_TPB 128
+#endif
 #define ACC_RMAX 8
+#ifndef ACC_CHUNK
 #define ACC_CHUNK 256      // samples staged per smem chunk
+#endif
 
 // Samples are summed in float32 in groups of ACC_GROUP and the group sums are added in float64: samples
 // that hit the same LUT row with the same tick shift contribute identical values, so a plain float32
