@@ -17,7 +17,9 @@ struct DevBuf {
     int need(size_t bytes) {
         if (bytes <= cap) return 0;
         if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return lsb_fail_cuda(e, "cudaFree"); }
-        size_t want = bytes + bytes / 8 + 256;
+        // batches of a run differ in size (event x TPC group): grow generously so that a run re-allocates a handful of
+        // times, not at every new maximum (a cudaFree + cudaMalloc of GB-sized buffers costs 10-500 ms on the host)
+        size_t want = bytes + (bytes < ((size_t)4 << 30) ? bytes / 2 : bytes / 8) + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
         if (e != cudaSuccess) { p = nullptr; return lsb_fail_cuda(e, "cudaMalloc (chain buffer)"); }
@@ -187,7 +189,17 @@ static int chain_grow_rng(lsb_chain* h, long long n, uint64_t seed, cudaStream_t
     return 0;
 }
 
-#define CH_STAGE(i) do { if (h->timing) cudaEventRecord(h->ev[i], st); } while (0)
+// LSB_CHAIN_TRACE=1: host-side time between the stage markers of one enqueue (allocation growth, host loops), on stderr
+#include <chrono>
+static double g_ch_trace_t0 = 0.0;
+static inline void ch_trace(int i) {
+    static const int on = getenv("LSB_CHAIN_TRACE") ? 1 : 0;
+    if (!on) return;
+    const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (i > 0 && now - g_ch_trace_t0 > 1.0) fprintf(stderr, "[lsb chain trace] host %.1f ms before marker %d\n", now - g_ch_trace_t0, i);
+    g_ch_trace_t0 = now;
+}
+#define CH_STAGE(i) do { ch_trace(i); if (h->timing) cudaEventRecord(h->ev[i], st); } while (0)
 
 // Enqueue one batch.  `st` = stream of the front and FEE stages, `st_mc` = stream of the MC stage (may be the
 // same).  Returns with everything queued; the hit count arrives in h->hs_pinned once `st` has drained.
