@@ -20,7 +20,7 @@ from importlib import import_module as _im  # noqa: E402
 
 consts, synth, active_volume = _im("larnd-sim_b200.consts"), _im("larnd-sim_b200.synth"), _im("larnd-sim_b200.active_volume")
 batching, chain_mod, packets_mod = _im("larnd-sim_b200.util.batching"), _im("larnd-sim_b200.chain"), _im("larnd-sim_b200.packets")
-fee, launch = _im("larnd-sim_b200.fee"), _im("larnd-sim_b200._launch")
+fee, launch, dist_mod = _im("larnd-sim_b200.fee"), _im("larnd-sim_b200._launch"), _im("larnd-sim_b200.dist")
 
 
 def simulate(tracks, config="2x2", event_separator="event_id", tpc_batch_size=2, rand_seed=1, event_gap_us=2.0e5, chain=None):
@@ -53,13 +53,23 @@ def simulate(tracks, config="2x2", event_separator="event_id", tpc_batch_size=2,
     batcher = batching.TPCBatcher(tracks, tracks, event_separator, tpc_batch_size=tpc_batch_size, tpc_borders=det.TPC_BORDERS)
     sizes = batcher.unit_sizes                                                # runs the device pass
     lap("batching")
-    all_packets, all_rows, log = [], [], []
-    last_event = None
-    for ievd, idx in batcher.units():
-        if last_event is None or ievd > last_event:                            # new event: timestamp + trigger packets, :888-897
+    # (2b) several GPUs: the units are independent -- longest-first assignment on the segment counts; every
+    # rank computes the same plan and keeps its share.  The chain's RNG states evolve from batch to batch, so the noise
+    # realisation depends on which batches a chain has seen (true of the reference's own loop order as well).
+    import torch.distributed as tdist
+    world = tdist.get_world_size() if tdist.is_initialized() else 1
+    rank = tdist.get_rank() if tdist.is_initialized() else 0
+    mine = set(dist_mod.assign_units(sizes, world)[rank]) if world > 1 else None
+    nB = batcher.n_tpc_batches
+    unit_ids, unit_packets, unit_rows, log = [], [], [], []
+    for u, (ievd, idx) in enumerate(batcher.units()):
+        if mine is not None and u not in mine:
+            continue
+        all_packets, all_rows = [], []
+        unit_ids.append(u); unit_packets.append(all_packets); unit_rows.append(all_rows)
+        if u % nB == 0:                                                        # first batch of an event: timestamp + trigger packets, :888-897
             p, r = fee.export_timestamp_trigger_to_hdf5(None, [event_times[int(ievd)]])
             all_packets.append(p); all_rows.append(r)
-            last_event = ievd
         if len(idx) == 0:
             log.append((int(ievd), 0, 0, 0))
             continue
@@ -93,8 +103,19 @@ def simulate(tracks, config="2x2", event_separator="event_id", tpc_batch_size=2,
     if chain is None:
         ch.close()
     torch.cuda.synchronize()
-    pk = np.concatenate(all_packets) if all_packets else np.zeros(0, dtype=packets_mod.PACKET_DTYPE)
-    rows = np.concatenate(all_rows) if all_rows else None
+    row_dtype = packets_mod.assn_dtype(int(mod.sim.ASSOCIATION_COUNT_TO_STORE))
+    cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dtype=dt)      # noqa: E731
+    unit_packets = [cat(p, packets_mod.PACKET_DTYPE) for p in unit_packets]
+    unit_rows = [cat(r, row_dtype) for r in unit_rows]
+    if world > 1:                                                             # rank 0 gets every unit back, in file order
+        got_p = dist_mod.gather_unit_records(unit_ids, unit_packets, packets_mod.PACKET_DTYPE, device="cuda")
+        got_r = dist_mod.gather_unit_records(unit_ids, unit_rows, row_dtype, device="cuda")
+        if rank != 0:
+            return dict(packets=None, packets_mc_ds=None, batches=log, seconds=time.perf_counter() - t_start, n_segments=len(tracks),
+                        stage_seconds=stage, unit_sizes=sizes)
+        assert got_p[0] == got_r[0] == list(range(len(sizes)))
+        unit_packets, unit_rows = got_p[1], got_r[1]
+    pk, rows = cat(unit_packets, packets_mod.PACKET_DTYPE), cat(unit_rows, row_dtype)
     return dict(packets=pk, packets_mc_ds=rows, batches=log, seconds=time.perf_counter() - t_start, n_segments=len(tracks),
                 stage_seconds=stage, unit_sizes=sizes)
 
@@ -106,14 +127,28 @@ def main():
     ap.add_argument("--events", type=int, default=4)
     ap.add_argument("--tpc-batch-size", type=int, default=2)
     a = ap.parse_args()
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:                                                             # torchrun --nproc-per-node N examples/run_batches.py ...
+        import torch.distributed as tdist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        tdist.init_process_group("nccl")
     mod = consts.load_snapshot(a.config)
     tracks = synth.beam_spill_segments(a.segments, mod.detector, seed=12345, n_events=a.events)
     tracks["segment_id"] = np.arange(len(tracks))
     ch = chain_mod.Chain(tracks.dtype, synth.response_lut(mod.detector))
     for rep in range(2):          # first pass: the chain's buffers grow to the largest batch; second pass: steady state
         out = simulate(tracks, a.config, tpc_batch_size=a.tpc_batch_size, chain=ch)
-        print("pass %d: %.3f s" % (rep, out["seconds"]))
+        if world > 1:
+            torch.distributed.barrier()
+        print("pass %d: %.3f s (rank %d of %d, %d batches here)" % (rep, out["seconds"], int(os.environ.get("RANK", "0")), world,
+                                                                   len(out["batches"])), flush=True)
     ch.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if out["packets"] is None:
+        return
     pk = out["packets"]
     kinds, counts = np.unique(pk["packet_type"], return_counts=True)
     print("segments %d  batches %d (non-empty %d)  packets %d %s  %.3f s after setup -> %.0f segments/s whole loop" % (

@@ -100,3 +100,54 @@ class HitTableGather:
         """(pixel ids i4[n], ADC codes f8[n], timestamps f8[n]) of one received buffer"""
         n = min(int(buf[0, 0].item()), self.cap)
         return buf[1:n + 1, 0].to(torch.int32), buf[1:n + 1, 1], buf[1:n + 1, 2]
+
+
+def gather_unit_records(unit_ids, records, dtype, dst=0, group=None, device="cpu"):
+    """Reassemble per-unit record arrays (e.g. the packets of every (event, TPC group) batch) on `dst` in UNIT order, i.e.
+    the order in which the reference's sequential loop appends them to its output file ("ordered by (event,
+    module)").  ``unit_ids``: the units this rank simulated (any order), ``records``: one NumPy structured array of
+    ``dtype`` per unit.  Two collectives: the (unit id, record count) table, then one padded byte gather.
+    Returns (unit ids ascending, list of arrays in that order) on `dst`, None elsewhere."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    if len(unit_ids) != len(records):
+        raise ValueError("one record array per unit")
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        order = sorted(range(len(unit_ids)), key=lambda i: int(unit_ids[i]))
+        return [int(unit_ids[i]) for i in order], [np.asarray(records[i], dtype=dtype) for i in order]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    # (1) how many units / records every rank holds
+    head = torch.tensor([len(unit_ids), sum(len(r) for r in records)], dtype=torch.int64, device=device)
+    heads = [torch.zeros_like(head) for _ in range(world)]
+    dist.all_gather(heads, head, group=group)
+    max_units = max(max(int(h[0]) for h in heads), 1)
+    max_bytes = max(max(int(h[1]) for h in heads) * dtype.itemsize, 1)
+    # (2) per rank: [unit id, count] table and the concatenated record bytes, padded to the largest rank
+    table = torch.full((max_units, 2), -1, dtype=torch.int64)
+    for i, (u, r) in enumerate(zip(unit_ids, records)):
+        table[i, 0], table[i, 1] = int(u), len(r)
+    blob = np.zeros(max_bytes, dtype=np.uint8)
+    if records and sum(len(r) for r in records):
+        raw = np.concatenate([np.ascontiguousarray(r if r.dtype == dtype else r.astype(dtype)).view(np.uint8).reshape(-1)
+                              for r in records])                   # byte-wise: padding of aligned records travels too
+        blob[:raw.size] = raw
+    table, payload = table.to(device), torch.from_numpy(blob).to(device)
+    tabs = [torch.empty_like(table) for _ in range(world)] if rank == dst else None
+    pays = [torch.empty_like(payload) for _ in range(world)] if rank == dst else None
+    dist.gather(table, tabs, dst=dst, group=group)
+    dist.gather(payload, pays, dst=dst, group=group)
+    if rank != dst:
+        return None
+    found = {}
+    for t, p in zip(tabs, pays):
+        t, p = t.cpu().numpy(), p.cpu().numpy()
+        off = 0
+        for u, n in t:
+            if u < 0:
+                continue
+            if int(u) in found:
+                raise ValueError("unit %d was simulated by two ranks" % u)
+            found[int(u)] = p[off:off + int(n) * dtype.itemsize].view(dtype).copy()
+            off += int(n) * dtype.itemsize
+    ids = sorted(found)
+    return ids, [found[u] for u in ids]

@@ -72,3 +72,60 @@ def test_gather_packets_world2_gloo():
     assert got[1][0] == [100.0, 101.0, 102.0] and got[0][2] == [6.0, 7.0, 8.0]
     assert shapes == [(0, 3), (0, 3)]
     assert table[0] == [10, 11, 12] and table[1] == [81.0] * 3 and table[2] == [3.0] * 3 and table[3] == [2, 3]
+
+
+# ------------------------------------------------------------------------------------------------
+# units of a run spread over ranks, outputs reassembled in the reference's file order
+# ------------------------------------------------------------------------------------------------
+import numpy as np  # noqa: E402
+
+REC = np.dtype([("unit", "i4"), ("k", "u1"), ("t", "f8")], align=True)
+UNIT_SIZES = [40, 0, 7, 300, 12, 0, 90, 33, 5]
+
+
+def _unit_records(u):
+    """deterministic stand-in for 'simulate unit u': as many records as a third of its segments"""
+    n = UNIT_SIZES[u] // 3
+    r = np.zeros(n, dtype=REC)
+    r["unit"], r["k"], r["t"] = u, np.arange(n) % 251, np.arange(n) * 0.5 + u
+    return r
+
+
+def _unit_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = ldist.assign_units(UNIT_SIZES, world)[rank]
+    out = ldist.gather_unit_records(list(reversed(mine)), [_unit_records(u) for u in reversed(mine)], REC, dst=0)
+    if rank == 0:
+        ids, recs = out
+        got = np.concatenate(recs)
+        q.put((ids, [got[f].tolist() for f in REC.names]))
+    else:
+        assert out is None
+    none = ldist.gather_unit_records([], [], REC, dst=0)               # a run without any unit
+    if rank == 0:
+        q.put(none)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_unit_outputs_come_back_in_file_order_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 300
+    procs = [ctx.Process(target=_unit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ids, blob = q.get(timeout=120)
+    none = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ids == list(range(len(UNIT_SIZES)))
+    want = np.concatenate([_unit_records(u) for u in range(len(UNIT_SIZES))])                        # = the sequential loop's output
+    assert blob == [want[f].tolist() for f in REC.names]
+    assert none == ([], [])
+    # single process: same call, no process group
+    ids1, recs1 = ldist.gather_unit_records([4, 2, 7], [_unit_records(u) for u in (4, 2, 7)], REC)
+    assert ids1 == [2, 4, 7] and np.array_equal(np.concatenate(recs1), np.concatenate([_unit_records(u) for u in (2, 4, 7)]))
