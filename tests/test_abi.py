@@ -91,8 +91,20 @@ def test_product_has_no_cpu_fallback():
     from larndsim_b200 import quenching
     lc.load_snapshot("module0")
     if not torch.cuda.is_available():
+        seg = synth.cosmic_segments(4, lc.detector)
         with pytest.raises(RuntimeError):
-            quenching.quench[1, 256](synth.cosmic_segments(4, lc.detector), 2)
+            quenching.quench[1, 256](seg, 2)
+        # the widened stages as well: selection / batching, light window extent, table lookup
+        from larndsim_b200 import active_volume, light_sim
+        from larndsim_b200.util import batching
+        with pytest.raises(RuntimeError):
+            active_volume.select_active_volume(seg, lc.detector.TPC_BORDERS)
+        with pytest.raises(RuntimeError):
+            next(batching.TPCBatcher(seg, seg, "event_id", tpc_batch_size=1, tpc_borders=lc.detector.TPC_BORDERS))
+        import numpy as np
+        inc = np.zeros((3, 4), dtype=[("n_photons_det", "f4"), ("t0_det", "f4")])
+        with pytest.raises(RuntimeError):
+            light_sim.get_nticks(inc)
     pkg = os.path.join(ROOT, "larnd-sim_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
