@@ -18,15 +18,14 @@ from .. import active_volume as _av
 
 
 class TrackSegmentBatcher(object):
-    """Base class: an iterator that creates masks into an array of track segments."""
+    """Base class of the batchers (batching.py:6-15): holds the file's segments, the segments to batch and the name of
+    the event field; subclasses are iterators over masks into ``track_seg``."""
 
     def __init__(self, all_track_seg, track_seg, event_separator, **kwargs):
-        self.all_track_seg = all_track_seg
-        self.track_seg = track_seg
-        self.EVENT_SEPARATOR = event_separator
+        self.all_track_seg, self.track_seg, self.EVENT_SEPARATOR = all_track_seg, track_seg, event_separator
 
     def __iter__(self):
-        raise NotImplementedError
+        raise NotImplementedError("subclasses define the batching scheme")
 
 
 class TPCBatcher(TrackSegmentBatcher):
@@ -35,8 +34,7 @@ class TPCBatcher(TrackSegmentBatcher):
         self.tpc_batch_size = tpc_batch_size
         self.tpc_borders = np.sort(_av._borders(tpc_borders), axis=-1)
         self._events = np.unique(self.all_track_seg[self.EVENT_SEPARATOR])
-        self._curr_event = 0
-        self._curr_tpc = 0
+        self._next_unit = 0                     # position of the iterator: unit = event rank * n_tpc_batches + TPC group
         self._order = self._offsets = None
 
     # -- device pass --------------------------------------------------------------------
@@ -85,23 +83,20 @@ class TPCBatcher(TrackSegmentBatcher):
         for u in range(len(self._events) * nB):
             yield self._events[u // nB], src[int(self._offsets[u]):int(self._offsets[u + 1])]
 
-    # -- the reference's iterator protocol ------------------------------------------------
+    # -- the reference's iterator protocol: (event, bool mask over track_seg), event-major, single pass ----------------
     def __len__(self):
-        return len(self._events) * ceil(self.tpc_borders.shape[0] / self.tpc_batch_size)
+        return len(self._events) * self.n_tpc_batches
 
     def __iter__(self):
         return self
 
     def __next__(self):
-        if self._curr_tpc >= self.tpc_borders.shape[0]:
-            self._curr_event += 1
-            self._curr_tpc = 0
-        if self._curr_event >= len(self._events):
+        u = self._next_unit
+        if u >= len(self):
             raise StopIteration
+        self._next_unit = u + 1
         self._plan()
+        rows = self._order[int(self._offsets[u]):int(self._offsets[u + 1])]
         mask = np.zeros(self._n, dtype=bool)
-        if self.n_tpc_batches:                                   # (no TPCs: the reference still yields empty masks)
-            u = self._curr_event * self.n_tpc_batches + self._curr_tpc // self.tpc_batch_size
-            mask[self._order[int(self._offsets[u]):int(self._offsets[u + 1])]] = True
-        self._curr_tpc += self.tpc_batch_size
-        return self._events[self._curr_event], mask
+        mask[rows] = True
+        return self._events[u // self.n_tpc_batches], mask
