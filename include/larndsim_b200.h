@@ -346,6 +346,16 @@ int lsb_light_digitize(const void* signal, int32_t signal_f64, int64_t nticks, i
 int lsb_light_extent(const void* light_incidence, const lsb_linc_layout* LI, int64_t n_segments, int32_t ndet,
                      float* t0_minmax, uint8_t* active, void* stream);
 
+/* larndsim/light_sim.py:621-661 zero_suppress_waveform_truth: one 32-byte record {trigger_id i4, op_channel_id i4, tick i4,
+ * event_id i4, segment_id i8, pe_current f8} per slot of true_track_id[n_trig][n_det][n_samples][n_truth] that is not -1,
+ * in C order; op_channel[d] = channel id of column d; trigger_id = first_trigger_id + the running sum of the trigger
+ * indices of the records so far (the reference accumulates, :644).  rows: device, room for every slot; *n_rows device. */
+int64_t lsb_light_truth_ws_bytes(int64_t n_slots);
+int lsb_light_zero_suppress_truth(const int64_t* true_track_id, const double* true_photons, int64_t n_trig, int32_t n_det,
+                                  int32_t n_samples, int32_t n_truth, const int32_t* op_channel, int32_t event_id,
+                                  int32_t first_trigger_id, void* rows, int64_t* n_rows, void* ws, int64_t ws_bytes, void* stream);
+
+
 
 /* ---- active volume + batching (the callers that cut the segment array into units) ------- */
 /* larndsim/active_volume.py:4-46  select_active_volume: first_tpc[i] = lowest TPC index in [tpc_lo, tpc_hi) whose open

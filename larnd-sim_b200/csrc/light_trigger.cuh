@@ -14,6 +14,7 @@
 //                      materialised: a row map + tick offset describe them.
 #pragma once
 #include "common.cuh"
+#include "glue.cuh"
 
 template <typename TS>
 __device__ __forceinline__ double lt_group_sum(const TS* __restrict__ signal, long long nticks, int g, int cpt, long long t) {
@@ -277,5 +278,78 @@ LSB_EXPORT int lsb_light_extent(const void* light_incidence, const lsb_linc_layo
     }
     k_lt_extent_finish<<<1, 1, 0, st>>>(code);
     LSB_LAUNCH_CHECK("k_lt_extent_finish");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// zero suppression of the waveform truth: light_sim.zero_suppress_waveform_truth (:621-661)
+// The reference enumerates the [trigger][channel][sample][slot] array in Python and appends one record per slot whose
+// track id is not -1.  Here: flag -> prefix sum -> scatter, rows in the same (C-order) sequence.  The reference's running
+// `i_trig = i_trig + this_trig` (it accumulates over the entries, :644) is a second prefix sum over the kept entries.
+// ---------------------------------------------------------------------------------------
+struct LtTruthRow { int32_t trigger_id, op_channel_id, tick, event_id; long long segment_id; double pe_current; };
+static_assert(sizeof(LtTruthRow) == 32, "truth row layout");
+
+__global__ void k_lt_truth_flags(const long long* __restrict__ ids, long long n, long long per_trigger, uint32_t* __restrict__ flag,
+                                 uint32_t* __restrict__ tsum) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool keep = ids[i] != -1;
+    flag[i] = keep ? 1u : 0u;
+    tsum[i] = keep ? (uint32_t)(i / per_trigger) : 0u;
+}
+__global__ void k_lt_truth_rows(const long long* __restrict__ ids, const double* __restrict__ photons, long long n, int n_det,
+                                int n_samples, int n_truth, const int32_t* __restrict__ op_channel, int event_id, int first_trigger,
+                                const uint32_t* __restrict__ flag, const long long* __restrict__ pos, const long long* __restrict__ tpre,
+                                LtTruthRow* __restrict__ rows) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const long long per_det = (long long)n_samples * n_truth, per_trigger = per_det * n_det;
+    const long long trig = i / per_trigger, rem = i - trig * per_trigger;
+    const int det = (int)(rem / per_det), sample = (int)((rem - det * per_det) / n_truth);
+    LtTruthRow r;
+    r.trigger_id = (int32_t)(first_trigger + tpre[i] + trig);          // inclusive running sum of the trigger indices
+    r.op_channel_id = op_channel[det];
+    r.tick = sample;
+    r.event_id = event_id;
+    r.segment_id = ids[i];
+    r.pe_current = photons[i];
+    rows[pos[i]] = r;
+}
+
+LSB_EXPORT int64_t lsb_light_truth_ws_bytes(int64_t n) {
+    const size_t a4 = (((size_t)n * 4 + 15) / 16) * 16, a8 = (((size_t)n * 8 + 15) / 16) * 16;
+    return (int64_t)(2 * a4 + 2 * a8 + (size_t)(scan_num_blocks(n) + 1) * 8 + 32);
+}
+
+LSB_EXPORT int lsb_light_zero_suppress_truth(const int64_t* true_track_id, const double* true_photons, int64_t n_trig, int32_t n_det,
+                                             int32_t n_samples, int32_t n_truth, const int32_t* op_channel, int32_t event_id,
+                                             int32_t first_trigger_id, void* rows, int64_t* n_rows, void* ws, int64_t ws_bytes,
+                                             void* stream) {
+    LSB_REQUIRE(n_rows, "light_zero_suppress_truth: null pointer");
+    LSB_REQUIRE(n_trig >= 0 && n_det >= 0 && n_samples >= 0 && n_truth >= 0, "light_zero_suppress_truth: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)n_trig * n_det * n_samples * n_truth;
+    if (n == 0) { LSB_CUDA(cudaMemsetAsync(n_rows, 0, 8, st)); return 0; }
+    LSB_REQUIRE(true_track_id && true_photons && op_channel && rows, "light_zero_suppress_truth: null pointer");
+    LSB_REQUIRE(ws && ws_bytes >= lsb_light_truth_ws_bytes(n), "light_zero_suppress_truth: workspace too small");
+    const size_t a4 = (((size_t)n * 4 + 15) / 16) * 16, a8 = (((size_t)n * 8 + 15) / 16) * 16;
+    char* p = (char*)ws;
+    uint32_t* flag = (uint32_t*)p; p += a4;
+    uint32_t* tsum = (uint32_t*)p; p += a4;
+    long long* pos = (long long*)p; p += a8;
+    long long* tpre = (long long*)p; p += a8;
+    long long* bs = (long long*)p; p += (size_t)scan_num_blocks(n) * 8;
+    long long* scratch_total = (long long*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+    const long long per_trigger = (long long)n_det * n_samples * n_truth;
+    k_lt_truth_flags<<<lsb_blocks(n, 256), 256, 0, st>>>((const long long*)true_track_id, n, per_trigger, flag, tsum);
+    LSB_LAUNCH_CHECK("k_lt_truth_flags");
+    int rc = exclusive_scan<uint32_t, long long>(flag, n, pos, bs, (long long*)n_rows, st);
+    if (rc) return rc;
+    rc = exclusive_scan<uint32_t, long long>(tsum, n, tpre, bs, scratch_total, st);
+    if (rc) return rc;
+    k_lt_truth_rows<<<lsb_blocks(n, 256), 256, 0, st>>>((const long long*)true_track_id, true_photons, n, n_det, n_samples, n_truth,
+                                                       op_channel, event_id, first_trigger_id, flag, pos, tpre, (LtTruthRow*)rows);
+    LSB_LAUNCH_CHECK("k_lt_truth_rows");
     return 0;
 }

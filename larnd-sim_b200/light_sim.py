@@ -365,3 +365,41 @@ def digitize_signal(signal, signal_op_channel_idx, trigger_idx, trigger_op_chann
     _digitize(sig, f64, nticks, chan, np.arange(nsig), 0, nticks, not f64, ti, tp, M, trig_chan.reshape(ntrig, ndm), ns, False,
               dg, di, dp, M_out)
     _l.finish(dg, di, dp)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# zero suppression of the waveform truth (the compaction in front of the light HDF5 export)
+# ---------------------------------------------------------------------------------------------------------
+TRUTH_DTYPE = np.dtype([('trigger_id', 'i4'), ('op_channel_id', 'i4'), ('tick', 'i4'), ('event_id', 'i4'), ('segment_id', 'i8'),
+                        ('pe_current', 'f8')])
+
+
+def zero_suppress_waveform_truth(waveforms_true_track_id, waveforms_true_photons, i_evt, i_trig, i_mod=-1):
+    """``zero_suppress_waveform_truth(ids, photons, i_evt, i_trig, i_mod=-1)`` (light_sim.py:621-661): the truth slots that are
+    not -1, flattened to records ``['trigger_id', 'op_channel_id', 'tick', 'event_id', 'segment_id', 'pe_current']`` in the
+    reference's enumeration order (a Python loop over every slot there; flag -> prefix sum -> scatter here).  NumPy out."""
+    import torch
+    light = _consts.provider().light
+    chan = np.asarray(light.TPC_TO_OP_CHANNEL)
+    chan = (chan[(i_mod - 1) * 2:i_mod * 2] if i_mod > 0 else chan[:]).ravel()
+    ids = _l.dev(waveforms_true_track_id, want=np.int64, name="waveforms_true_track_id")
+    ph = _l.dev(waveforms_true_photons, want=np.float64, name="waveforms_true_photons")
+    if len(ids.shape) != 4 or tuple(ph.shape) != tuple(ids.shape):
+        raise ValueError("truth arrays must have shape (ntrigs, ndet, nsamples, ntruth)")
+    nt, nd, ns, M = (int(x) for x in ids.shape)
+    if nd > chan.size:
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (nd - 1, chan.size))
+    n = nt * nd * ns * M
+    lib = _l.lib()
+    lib.lsb_light_truth_ws_bytes.restype = C.c_int64
+    nws = int(lib.lsb_light_truth_ws_bytes(C.c_int64(n)))
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device="cuda")
+    rows = torch.empty((max(n, 1), TRUTH_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    cd = torch.from_numpy(np.ascontiguousarray(chan[:max(nd, 1)], dtype=np.int32)).cuda()
+    _l.check(lib.lsb_light_zero_suppress_truth(ids.c, ph.c, C.c_int64(nt), C.c_int32(nd), C.c_int32(ns), C.c_int32(M),
+                                               C.c_void_p(cd.data_ptr()), C.c_int32(int(i_evt)), C.c_int32(int(i_trig)),
+                                               C.c_void_p(rows.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                               C.c_int64(nws), _l.stream()), "light_zero_suppress_truth")
+    k = int(cnt.item())
+    return rows[:k].cpu().numpy().reshape(-1).view(TRUTH_DTYPE).copy() if k else np.empty(0, dtype=TRUTH_DTYPE)

@@ -199,3 +199,29 @@ def get_nticks(light_incidence, C):
 
 def get_active_op_channel(light_incidence):
     return np.nonzero(lit_extremes(light_incidence)[2])[0].astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# zero_suppress_waveform_truth (larndsim/light_sim.py:621-661); pinned by tools/gen_golden_light_extent.py
+# ---------------------------------------------------------------------------------------------------------
+TRUTH_DTYPE = np.dtype([("trigger_id", "i4"), ("op_channel_id", "i4"), ("tick", "i4"), ("event_id", "i4"), ("segment_id", "i8"),
+                        ("pe_current", "f8")])
+
+
+def zero_suppress_waveform_truth(true_track_id, true_photons, i_evt, i_trig, op_channel):
+    """``op_channel``: channel id of every column (TPC_TO_OP_CHANNEL of the module, flattened).  The trigger id is a running
+    sum: every kept slot adds its trigger index to it before it is recorded (:644)."""
+    nt, nd, ns, M = true_track_id.shape
+    rows = []
+    running = i_trig
+    for t in range(nt):
+        for d in range(nd):
+            for s in range(ns):
+                for m in range(M):
+                    if true_track_id[t, d, s, m] != -1:
+                        running += t
+                        rows.append((running, op_channel[d], s, i_evt, true_track_id[t, d, s, m], true_photons[t, d, s, m]))
+    out = np.empty(len(rows), dtype=TRUTH_DTYPE)
+    for k, r in enumerate(rows):
+        out[k] = r
+    return out

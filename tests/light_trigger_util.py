@@ -102,3 +102,16 @@ def extent_inputs(case, ndet=96):
     elif case == "one_entry":
         li["n_photons_det"][S // 2, 17] = 3.5
     return li
+
+
+def truth_inputs(case, ndet=96):
+    """(true_track_id i8[ntrig, ndet, nsamples, M], true_photons f8[...]) with -1 holes; 'multi' has 3 triggers"""
+    rng = np.random.default_rng(1000 + sum(map(ord, case)))
+    nt, ns, M = {"single": (1, 40, 3), "multi": (3, 25, 2), "none": (2, 10, 2), "zero_triggers": (0, 10, 2)}[case]
+    ids = rng.integers(0, 5000, (nt, ndet, ns, M)).astype(np.int64)
+    ids[rng.random(ids.shape) < (1.0 if case == "none" else 0.85)] = -1
+    ph = rng.random(ids.shape) * 20 - 2
+    return ids, ph
+
+
+TRUTH_CASES = ("single", "multi", "none", "zero_triggers")

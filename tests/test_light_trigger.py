@@ -209,3 +209,60 @@ def test_gpu_light_extent_identical(cuda, config):
     n, t0 = light_sim.get_nticks(big)
     n_ref, t0_ref = lo.get_nticks(big[[31234, 59999]], C)
     assert (n, t0) == (n_ref, t0_ref)
+
+
+# ---------------------------------------------------------------------------------------- truth zero suppression
+def _truth_case(z, case):
+    ids, ph = ltu.truth_inputs(case)
+    assert np.array_equal([float(ids.sum()), ph.sum()], z["truth_%s_sum" % case])
+    return ids, ph
+
+
+def _truth_modules(z, case):
+    return sorted(int(k.split("_m")[-1].split("_")[0]) for k in z.files if k.startswith("truth_%s_m" % case) and k.endswith("_tick"))
+
+
+def _rows_equal(rows, z, case, i_mod):
+    for f in lo.TRUTH_DTYPE.names:
+        want = z["truth_%s_m%d_%s" % (case, i_mod, f)]
+        assert rows[f].dtype == want.dtype and np.array_equal(rows[f], want), (case, i_mod, f)
+
+
+@pytest.mark.parametrize("config", ("module0", "2x2"))
+def test_oracle_truth_zero_suppression_matches_reference(config):
+    z, _ = _extent_golden(config)
+    chan_all = z["tpc_to_op_channel"]
+    for case in ltu.TRUTH_CASES:
+        ids, ph = _truth_case(z, case)
+        for i_mod in _truth_modules(z, case):
+            chan = (chan_all[(i_mod - 1) * 2:i_mod * 2] if i_mod > 0 else chan_all).ravel()
+            _rows_equal(lo.zero_suppress_waveform_truth(ids, ph, 7, 11, chan), z, case, i_mod)
+    multi = z["truth_multi_m-1_trigger_id"]
+    assert len(multi) > 1000 and multi[0] == 11 and multi[-1] > 2000 and (np.diff(multi) >= 0).all()      # the running sum
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", ("module0", "2x2"))
+def test_gpu_truth_zero_suppression_identical(cuda, config):
+    import torch
+    from larndsim_b200 import light_sim
+    z, _ = _extent_golden(config)
+    p = _provider(config)
+    assert np.array_equal(np.asarray(p.light.TPC_TO_OP_CHANNEL), z["tpc_to_op_channel"])
+    for case in ltu.TRUTH_CASES:
+        ids, ph = _truth_case(z, case)
+        for i_mod in _truth_modules(z, case):
+            rows = light_sim.zero_suppress_waveform_truth(ids, ph, 7, 11, i_mod)
+            assert isinstance(rows, np.ndarray) and rows.dtype == lo.TRUTH_DTYPE
+            _rows_equal(rows, z, case, i_mod)
+    # device inputs, many blocks: against the restatement's vectorised equivalent
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, 10**9, (4, 96, 700, 3)).astype(np.int64)
+    ids[rng.random(ids.shape) < 0.7] = -1
+    ph = rng.random(ids.shape)
+    rows = light_sim.zero_suppress_waveform_truth(torch.from_numpy(ids).cuda(), torch.from_numpy(ph).cuda(), 3, 100)
+    t, d, s, m = np.nonzero(ids != -1)
+    chan = np.asarray(p.light.TPC_TO_OP_CHANNEL).ravel()
+    assert len(rows) == len(t) and np.array_equal(rows["segment_id"], ids[t, d, s, m]) and np.array_equal(rows["pe_current"], ph[t, d, s, m])
+    assert np.array_equal(rows["tick"], s) and np.array_equal(rows["op_channel_id"], chan[d]) and (rows["event_id"] == 3).all()
+    assert np.array_equal(rows["trigger_id"], (100 + np.cumsum(t)).astype(np.int32))

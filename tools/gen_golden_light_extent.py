@@ -36,8 +36,16 @@ def run(config, path):
         out[case + "_start"] = np.asarray(t0)                       # keeps the dtype the reference returned
         out[case + "_active"] = np.asarray(ls.get_active_op_channel(inc))
         out[case + "_sum"] = np.array([inc["n_photons_det"].sum(dtype=np.float64), inc["t0_det"].sum(dtype=np.float64)])
+    for case in ltu.TRUTH_CASES:                                   # zero_suppress_waveform_truth (light_sim.py:621-661)
+        ids, ph = ltu.truth_inputs(case)
+        for i_mod in ((-1, 1) if config == "module0" else (-1, 3)):
+            rows = ls.zero_suppress_waveform_truth(ids, ph, 7, 11, i_mod)
+            for f in rows.dtype.names:
+                out["truth_%s_m%d_%s" % (case, i_mod, f)] = rows[f]
+        out["truth_%s_sum" % case] = np.array([ids.sum(), ph.sum()], dtype=np.float64)
+    out["tpc_to_op_channel"] = np.asarray(li.TPC_TO_OP_CHANNEL)
     np.savez_compressed(path, **out)
-    print(config, {k: (v.dtype.str, v.tolist() if v.size < 4 else v.shape) for k, v in out.items()})
+    print(config, {k: (v.dtype.str, v.tolist() if v.size < 4 else v.shape) for k, v in out.items() if not k.startswith("truth_") or k.endswith("trigger_id")})
 
 
 if __name__ == "__main__":
