@@ -6,7 +6,6 @@ the oracle; it is what a maintainer's driver looks like after switching the impo
     python examples/run_batches.py --config 2x2 --segments 20000 --events 4
 """
 import argparse
-import importlib
 import os
 import sys
 import time
@@ -15,12 +14,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-lsb = importlib.import_module("larnd-sim_b200")
-from importlib import import_module as _im  # noqa: E402
-
-consts, synth, active_volume = _im("larnd-sim_b200.consts"), _im("larnd-sim_b200.synth"), _im("larnd-sim_b200.active_volume")
-batching, chain_mod, packets_mod = _im("larnd-sim_b200.util.batching"), _im("larnd-sim_b200.chain"), _im("larnd-sim_b200.packets")
-fee, launch, dist_mod = _im("larnd-sim_b200.fee"), _im("larnd-sim_b200._launch"), _im("larnd-sim_b200.dist")
+from larndsim_b200 import consts, synth, active_volume, fee  # noqa: E402
+from larndsim_b200 import chain as chain_mod, packets as packets_mod, _launch as launch, dist as dist_mod  # noqa: E402
+from larndsim_b200.util import batching  # noqa: E402
 
 
 def simulate(tracks, config="2x2", event_separator="event_id", tpc_batch_size=2, rand_seed=1, event_gap_us=2.0e5, chain=None):

@@ -4,7 +4,7 @@
  * This is the drop-in boundary.  Every entry point replaces one
  * Numba `@cuda.jit` kernel (or one piece of CuPy glue) of the reference; the reference
  * file:line it replaces is cited on each declaration (paths relative to the reference
- * tree, e.g. larndsim/detsim.py).  The Python host layer in `larnd-sim_b200/` binds these
+ * tree, e.g. larndsim/detsim.py).  The Python host layer in `larndsim_b200/` binds these
  * with ctypes and re-creates the reference's `kernel[grid, block](*arrays)` call
  * surface on top; INTEGRATION.md shows the binding a larnd-sim maintainer would add.
  *

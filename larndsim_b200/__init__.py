@@ -1,10 +1,10 @@
-"""Import alias: the package directory is ``larnd-sim_b200/`` (not a valid Python identifier);
-``import larndsim_b200`` loads it from there."""
-import os as _os
+"""B200-native charge/light readout chain of larnd-sim (hot path only).
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "larnd-sim_b200")
-__path__ = [_real]
-__file__ = _os.path.join(_real, "__init__.py")
-with open(__file__) as _f:
-    exec(compile(_f.read(), __file__, "exec"))
-del _os, _f, _real
+Drop-in modules with the reference's call surface (``kernel[grid, block](*arrays)``):
+``quenching, drifting, pixels_from_track, detsim, fee, lightLUT, light_sim`` -- see INTEGRATION.md.
+All arithmetic runs in ``csrc/liblarndsim_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/larndsim_b200.h``); there is no CPU fallback.
+"""
+__version__ = "0.1.0"
+__all__ = ["consts", "quenching", "drifting", "pixels_from_track", "detsim", "fee", "lightLUT", "light_sim",
+           "chain", "rng", "synth"]

@@ -7,13 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-import importlib
-
-lsb = importlib.import_module("larnd-sim_b200")
-from importlib import import_module
-
-lconsts = import_module("larnd-sim_b200.consts")
-synth = import_module("larnd-sim_b200.synth")
+from larndsim_b200 import consts as lconsts, synth  # noqa: E402
 
 # name -> (config snapshot, n segments, record kind, tpc batch sizes, seed)
 CASES = {

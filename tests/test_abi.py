@@ -105,7 +105,7 @@ def test_product_has_no_cpu_fallback():
         inc = np.zeros((3, 4), dtype=[("n_photons_det", "f4"), ("t0_det", "f4")])
         with pytest.raises(RuntimeError):
             light_sim.get_nticks(inc)
-    pkg = os.path.join(ROOT, "larnd-sim_b200")
+    pkg = os.path.join(ROOT, "larndsim_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):

@@ -50,9 +50,8 @@ def test_oracle_unsorted_borders():
 # ------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def cuda_mods():
-    import importlib
-    av = importlib.import_module("larnd-sim_b200.active_volume")
-    bt = importlib.import_module("larnd-sim_b200.util.batching")
+    from larndsim_b200 import active_volume as av
+    from larndsim_b200.util import batching as bt
     return av, bt
 
 

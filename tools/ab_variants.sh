@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of kernel build variants on the GPU box: tools/ab_variants.sh build/v0.so build/v1.so ...
 # (each variant is copied over the product library, bench.py is run, the per-kernel times are printed)
-LIB=larnd-sim_b200/csrc/liblarndsim_b200.so
+LIB=larndsim_b200/csrc/liblarndsim_b200.so
 cp $LIB /tmp/lib_orig.so
 for v in "$@"; do
   cp "$v" $LIB

@@ -3,7 +3,7 @@
 Runs ONLY in the build container: loads the detector / pixel-layout / simulation YAML files
 through the reference's own ``larndsim.consts`` loaders (unmodified, from /root/reference) and
 writes the *derived numbers* the kernels need (TPC borders, pixel grid, timing, FEE, light and
-simulation constants) as JSON under ``larnd-sim_b200/configs/``.  The GPU box has no reference
+simulation constants) as JSON under ``larndsim_b200/configs/``.  The GPU box has no reference
 tree; ``larndsim_b200.consts.load_snapshot(name)`` reads these files there.  In a real larnd-sim
 installation the host layer reads ``larndsim.consts`` directly instead (consts.py).
 """
@@ -16,7 +16,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(__file__))
 import refharness as rh  # noqa: E402
 
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "larnd-sim_b200", "configs")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "larndsim_b200", "configs")
 
 DET = ["LAR_DENSITY", "E_FIELD", "V_DRIFT", "ELECTRON_LIFETIME", "LONG_DIFF", "TRAN_DIFF", "TEMPERATURE",
        "DRIFT_LENGTH", "TPC_BORDERS", "TIME_SAMPLING", "TIME_INTERVAL", "TIME_PADDING", "TIME_WINDOW",

@@ -2,7 +2,7 @@ import sys, time, importlib, numpy as np, torch
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import batching_util as bu
 from oracle import batching_oracle as orc
-av = importlib.import_module("larnd-sim_b200.active_volume"); bt = importlib.import_module("larnd-sim_b200.util.batching")
+av = importlib.import_module("larndsim_b200.active_volume"); bt = importlib.import_module("larndsim_b200.util.batching")
 n = 1_000_000
 seg = bu.segments("ndlar", n, "f4", 99); borders = bu.borders_of("ndlar")
 for rep in range(3):
