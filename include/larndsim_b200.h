@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define LSB_ABI_VERSION 1
+#define LSB_ABI_VERSION 2
 #define LSB_MAX_TPC 128
 
 /* dtype codes for record fields */
@@ -130,6 +130,10 @@ int64_t     lsb_profile_end(char* out, int64_t cap);
 /* numba/cuda/random.py create_xoroshiro128p_states(n, seed, subsequence_start):
  * state[i] = jump^(subsequence_start+i)(splitmix64(seed)); host-side, multithreaded. */
 int lsb_rng_create_states_host(uint64_t* states_host, int64_t n, uint64_t seed, uint64_t subsequence_start);
+/* the same states written straight into device memory by one kernel launch: the 2^64-step jump is a linear map over
+ * GF(2), state i = J^i state 0 is reached with one 128x128 bit-matrix product per set bit of i (csrc/rng.cuh).
+ * Replaces numba.cuda.random.create_xoroshiro128p_states (cli/simulate_pixels.py:96,101), bit-identical. */
+int lsb_rng_create_states(uint64_t* states_dev, int64_t n, uint64_t seed, uint64_t subsequence_start, void* stream);
 
 /* ---- per-segment kernels ----------------------------------------------------------- */
 /* larndsim/quenching.py:11-44  quench(tracks, mode) */
@@ -268,7 +272,8 @@ typedef struct lsb_chain lsb_chain;   /* opaque; owns its device workspace */
 typedef struct lsb_chain_result {
     int64_t n_segments, n_unique_pixels, max_active, max_neighbors, n_ticks;   /* S, U, maxpix, P, T */
     int64_t n_hits;                   /* adc_list entries above pedestal */
-    int64_t n_samples, n_fma;         /* MC sample points / (sample,tick) LUT reads (roofline) */
+    int64_t n_samples, n_fma;         /* MC sample points N_sp / (sample,tick) pairs that pass every test N_fma, counted on the device */
+    int64_t n_pairs;                  /* (segment,pixel) pairs that hold a pixel id (S * P-bar) */
     /* device pointers valid until the next run / destroy */
     const int32_t* unique_pix;        /* [U] */
     const int64_t* track_pixel_map;   /* [U][K] */
@@ -293,11 +298,17 @@ int        lsb_chain_set_dense(lsb_chain* h, int32_t dense);
  * summation order (bit-identical float64), exact=0 (default) evaluates the same double sum as order-free weighted
  * sums over each hit window (agrees to ~1e-15 relative; hits, timestamps and charges do not depend on it). */
 int        lsb_chain_set_exact_fractions(lsb_chain* h, int32_t exact);
+/* RNG policy of the handle.  fresh=0 (default): cli/simulate_pixels.py:92-104 maybe_create_rng_states -- one state array
+ * per handle that evolves from batch to batch, fresh states (seed = rng_seed) appended when a batch needs more.
+ * fresh=1: every batch starts from create_xoroshiro128p_states(n, seed = rng_seed); its result then depends on
+ * (records, rng_seed) only, not on which handle / rank ran it or on what ran before. */
+int        lsb_chain_set_rng_fresh(lsb_chain* h, int32_t fresh);
 /* lsb_chain_result.signals is stored sparsely by the fused chain (per row only the ticks covered by the pair's samples are
  * written; later stages never read the rest).  Call this before reading the dense f4[S, P, T] array: it zero-fills the
  * unwritten parts of the last batch on `stream` (idempotent). */
 int        lsb_chain_signals_dense(lsb_chain* h, void* stream);
-/* tracks on the device, modified in place by quench/drift like the reference */
+/* tracks on the device, modified in place by quench/drift like the reference; quench_mode < 0: the records have been
+ * quenched and drifted already (cli/simulate_pixels.py:732,742 run both over the whole file before the batch loop) */
 int lsb_chain_run(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quench_mode, uint64_t rng_seed,
                   int32_t n_events, lsb_chain_result* out, void* stream);
 /* tracks in (pinned) host memory: H2D, chain, D2H of the packet-level outputs into host buffers
@@ -432,6 +443,47 @@ int lsb_export_packets(const lsb_readout_tables* rt, int64_t U, int32_t A, int32
                        const int64_t* track_ids, const int64_t* traj_ids, const int64_t* pix_t0_ticks, const double* pix_t0_us,
                        int32_t n_trig, const double* trig_times, const int64_t* trig_event, const int32_t* trig_module,
                        int64_t cap_packets, lsb_packet* packets, void* assn_rows, int32_t n_assn, int64_t* n_packets, void* stream);
+
+
+/* ---- one rank's share of a spill / file: the batch loop itself ------------------------------ */
+/* cli/simulate_pixels.py:864-1117 (loop over the (event, TPC group) batches of larndsim/util/batching.py:40-67) +
+ * save_results :1370-1390 -> fee.export_to_hdf5 (fee.py:84-359, WRITE_BATCH_SIZE = 1: one export per batch).
+ * The runner owns `depth` chain handles (RNG policy "fresh", see lsb_chain_set_rng_fresh) that are kept in flight
+ * together, and per-rank output buffers the packets and mc_packets_assn rows of every unit are appended to on the device,
+ * unit after unit, in the order the units are passed. */
+typedef struct lsb_spill lsb_spill;
+typedef struct lsb_spill_result {
+    int64_t n_units, n_segments, n_packets;       /* n_packets: packets written (or required, on overflow) */
+    int64_t n_hits, n_unique_pixels, n_samples, n_fma;   /* sums over the units (roofline accounting) */
+    int64_t pair_ticks, pixel_ticks;              /* sum of n_pairs * T and of U * Tt over the units */
+    const lsb_packet* packets;                    /* device, [n_packets] */
+    const void* assn_rows;                        /* device, [n_packets] records of assn_row_bytes */
+    const void* records;                          /* device, the units' records (unit after unit) as the chain left them */
+    int64_t assn_row_bytes;
+    int32_t overflow, pad;
+} lsb_spill_result;
+lsb_spill* lsb_spill_create(const lsb_consts* c, const lsb_track_layout* L, const void* response, int32_t Rx, int32_t Ry,
+                            int32_t Rt, int32_t response_f64, const lsb_readout_tables* rt, int32_t n_assn, int32_t depth);
+void lsb_spill_destroy(lsb_spill* sp);
+/* serial=1: every stage of a unit is queued on one stream (no overlap of the current stage with front-end stages of other
+ * units): what per-kernel timing with events needs */
+int  lsb_spill_set_serial(lsb_spill* sp, int32_t serial);
+/* tracks_dev: the selected, quenched and drifted records of the file (device).  order_dev: row permutation written by
+ * lsb_batch_units (NULL: identity).  Unit i = rows order[unit_begin[i] .. unit_begin[i] + unit_count[i]) with event id
+ * unit_event[i], event start time unit_t0_us[i] and RNG seed unit_seed[i] (host arrays).  seg_id / traj_id: byte offset and
+ * lsb_dtype of the record fields that label the truth rows (cli/simulate_pixels.py:483-484: 'segment_id',
+ * 'file_traj_id'; offset < 0: -1 is stored).  unit_packets_host[i] receives the number of packets of unit i.
+ * Returns -2 if cap_packets was too small (out->n_packets = required capacity; nothing usable was written). */
+int lsb_spill_run(lsb_spill* sp, const void* tracks_dev, const int64_t* order_dev, int64_t n_units,
+                  const int64_t* unit_begin, const int64_t* unit_count, const int64_t* unit_event, const double* unit_t0_us,
+                  const uint64_t* unit_seed, int32_t seg_id_offset, int32_t seg_id_dtype, int32_t traj_id_offset,
+                  int32_t traj_id_dtype, int64_t cap_packets, int64_t* unit_packets_host, lsb_spill_result* out, void* stream);
+/* tracks[indices] on the device (cli/simulate_pixels.py:670): dst[r] = src[order[r]], records of `itemsize` bytes */
+int lsb_gather_records(const void* src_dev, const int64_t* order_dev, int64_t n, int32_t itemsize, void* dst_dev, void* stream);
+/* gather of variable-length blocks into one buffer (all device pointers; the three arrays are host arrays): block b =
+ * src_dev[b] .. + bytes[b] -> dst_dev + dst_off[b].  Puts the units received from all ranks into file order. */
+int lsb_copy_blocks(int64_t n_blocks, const void* const* src_dev, const int64_t* dst_off, const int64_t* bytes, void* dst_dev,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,7 @@ class LincLayout(C.Structure):
 class ChainResult(C.Structure):
     _fields_ = [("n_segments", C.c_int64), ("n_unique_pixels", C.c_int64), ("max_active", C.c_int64),
                 ("max_neighbors", C.c_int64), ("n_ticks", C.c_int64), ("n_hits", C.c_int64),
-                ("n_samples", C.c_int64), ("n_fma", C.c_int64),
+                ("n_samples", C.c_int64), ("n_fma", C.c_int64), ("n_pairs", C.c_int64),
                 ("unique_pix", C.c_void_p), ("track_pixel_map", C.c_void_p), ("adc_list", C.c_void_p),
                 ("adc_digit", C.c_void_p), ("adc_ticks_list", C.c_void_p), ("current_fractions", C.c_void_p),
                 ("signals", C.c_void_p), ("pixels_signals", C.c_void_p),
@@ -169,7 +169,7 @@ def lib():
         _lib.lsb_tracks_current_mc_workspace_bytes.restype = C.c_int64
         _lib.lsb_tracks_current_mc_last_samples.restype = C.c_int64
         _lib.lsb_chain_create.restype = C.c_void_p
-        if _lib.lsb_abi_version() != 1:
+        if _lib.lsb_abi_version() != 2:
             raise ExtensionMissing("ABI version mismatch in %s" % LIB_PATH)
     return _lib
 

@@ -20,7 +20,7 @@ class ChainResult:
         self._handle = handle
         self.n_segments, self.n_unique_pixels = int(r.n_segments), int(r.n_unique_pixels)
         self.max_active, self.max_neighbors, self.n_ticks = int(r.max_active), int(r.max_neighbors), int(r.n_ticks)
-        self.n_hits, self.n_samples = int(r.n_hits), int(r.n_samples)
+        self.n_hits, self.n_samples, self.n_fma, self.n_pairs = int(r.n_hits), int(r.n_samples), int(r.n_fma), int(r.n_pairs)
         self.stage_ms = {STAGES[i]: float(r.stage_ms[i]) for i in range(len(STAGES))}
         #: async batches: ms since the library's reference event of (front begin, front end, MC begin, MC end, FEE begin, done)
         self.timeline = [float(r.stage_ms[i]) for i in range(6)]
@@ -79,9 +79,13 @@ class ChainResult:
 class Pipeline:
     """Round-robin over `depth` chains: batch i+1 is queued while batch i is still in flight, so the
     latency-bound FEE stage of one batch runs under the MC stage of the next (each chain has a
-    high-priority stream for front/FEE work and a low-priority one for the MC kernels)."""
+    high-priority stream for front/FEE work and a low-priority one for the MC kernels).
+
+    RNG: the chains of a pipeline use the "fresh" policy (see :class:`Chain`) -- with private evolving state arrays two
+    chains seeded alike would replay the same noise on consecutive batches.  Give every batch its own ``rng_seed``."""
 
     def __init__(self, track_dtype, response, depth=2, **kw):
+        kw.setdefault("rng_fresh", True)
         self.chains = [Chain(track_dtype, response, **kw) for _ in range(depth)]
         self._inflight = []          # chains with a pending batch, oldest first
         self._next = 0
@@ -125,7 +129,12 @@ class Chain:
     """``Chain(track_dtype, response)``; ``run(tracks_dev)`` on device records, ``run_host(tracks)``
     on a (pinned) host structured array with H2D/D2H inside the call."""
 
-    def __init__(self, track_dtype, response, rng_mode="cloud", stage_timing=False, dense=False, exact_fractions=False):
+    def __init__(self, track_dtype, response, rng_mode="cloud", stage_timing=False, dense=False, exact_fractions=False,
+                 rng_fresh=False):
+        """``rng_fresh=False``: the reference's ``maybe_create_rng_states`` -- one state array per chain that evolves from
+        batch to batch (cli/simulate_pixels.py:92-104, 1015, 1079).  ``rng_fresh=True``: every batch starts from
+        ``create_xoroshiro128p_states(n, seed=rng_seed)``, so its result depends on (records, rng_seed) only -- pass a
+        different ``rng_seed`` per batch (e.g. ``rand_seed + batch number``)."""
         self._c = _consts.snapshot()
         self._L = _abi.track_layout(track_dtype)
         self.dtype = np.dtype(track_dtype)
@@ -143,6 +152,8 @@ class Chain:
             _l.check(lib.lsb_chain_set_dense(C.c_void_p(self._h), C.c_int32(1)), "chain_set_dense")
         if exact_fractions:
             _l.check(lib.lsb_chain_set_exact_fractions(C.c_void_p(self._h), C.c_int32(1)), "chain_set_exact_fractions")
+        if rng_fresh:
+            _l.check(lib.lsb_chain_set_rng_fresh(C.c_void_p(self._h), C.c_int32(1)), "chain_set_rng_fresh")
         self._K, self._A, self._Tt = int(self._c.max_tracks_per_pixel), int(self._c.max_adc_values), int(self._c.n_time_ticks)
 
     def close(self):

@@ -33,7 +33,7 @@ enum { ST_QUENCH_DRIFT = 0, ST_GET_PIXELS, ST_UNIQUE, ST_TIME_INTERVALS, ST_TRAC
        ST_GET_ADC, ST_DIGITIZE, ST_COUNT };
 
 struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int mc_overflow;
-                      long long n_hits; double sum_len; long long mc_total; };
+                      long long n_hits; double sum_len; long long mc_total; unsigned long long mc_nfma, mc_npairs; };
 
 struct lsb_chain {
     lsb_consts c;
@@ -48,6 +48,7 @@ struct lsb_chain {
     int exact_fractions;      // 1: current_fractions in the reference's summation order (bit-identical), 0: order-free weighted sums
     int dense;                // 1: materialise pixels_tracks_signals like the reference (parity / debugging)
     long long n_rng;
+    int rng_fresh;            // 1: the states are re-created from rng_seed for every batch (result independent of the batches seen before)
     int tticks_n; long long tticks_events;
     cudaEvent_t ev[ST_COUNT + 1];
     // pipelined (asynchronous) operation: front + FEE stages on a high-priority stream, the MC stage on a
@@ -105,7 +106,7 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     if (!c || !L || !response || Rx <= 0 || Ry <= 0 || Rt <= 0) { lsb_fail_arg("chain_create: bad arguments"); return nullptr; }
     lsb_chain* h = new lsb_chain();
     h->c = *c; h->L = *L; h->response = response; h->Rx = Rx; h->Ry = Ry; h->Rt = Rt; h->f64 = response_f64;
-    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->dense = 0; h->exact_fractions = 0; h->n_rng = 0; h->tticks_n = 0; h->tticks_events = -1;
+    h->rng_mode = rng_mode; h->timing = enable_stage_timing; h->dense = 0; h->exact_fractions = 0; h->n_rng = 0; h->rng_fresh = 0; h->tticks_n = 0; h->tticks_events = -1;
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -113,9 +114,10 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     cudaStreamCreateWithPriority(&h->hp, cudaStreamNonBlocking, prio_hi);
     // ONE low-priority stream for the MC stage of every handle: MC stages of different batches must run back to
     // back, not interleaved (they are L1/L2-bound and would evict each other's LUT lines)
-    static cudaStream_t s_mc_stream = nullptr;
-    if (!s_mc_stream) cudaStreamCreateWithPriority(&s_mc_stream, cudaStreamNonBlocking, prio_lo);
-    h->lp = s_mc_stream;
+    static cudaStream_t s_mc_stream[64] = {nullptr};          // per device
+    int dev = 0; cudaGetDevice(&dev); dev = (dev < 0 || dev >= 64) ? 0 : dev;
+    if (!s_mc_stream[dev]) cudaStreamCreateWithPriority(&s_mc_stream[dev], cudaStreamNonBlocking, prio_lo);
+    h->lp = s_mc_stream[dev];
     cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_mc, cudaEventDisableTiming);
@@ -135,6 +137,16 @@ LSB_EXPORT int lsb_chain_set_dense(lsb_chain* h, int32_t dense) {
 LSB_EXPORT int lsb_chain_set_exact_fractions(lsb_chain* h, int32_t exact) {
     LSB_REQUIRE(h, "chain_set_exact_fractions: null handle");
     h->exact_fractions = exact ? 1 : 0;
+    return 0;
+}
+// RNG policy.  0 (default) = the reference's maybe_create_rng_states (cli/simulate_pixels.py:92-104): the handle keeps ONE
+// evolving state array, fresh states (seed = rng_seed) are appended when a batch needs more.  1 = fresh: every batch
+// starts from create_xoroshiro128p_states(n, seed = rng_seed), made on the device (rng.cuh); the result of a batch then
+// depends on (input, rng_seed) only -- not on the handle, rank or order that processed it (SURVEY.md 8e "RNG across
+// ranks": per-unit states from (rand_seed, event, module)).
+LSB_EXPORT int lsb_chain_set_rng_fresh(lsb_chain* h, int32_t fresh) {
+    LSB_REQUIRE(h, "chain_set_rng_fresh: null handle");
+    h->rng_fresh = fresh ? 1 : 0;
     return 0;
 }
 // `signals` rows are stored sparsely by the fused MC stage (only the ticks covered by a pair's samples are written; the
@@ -166,25 +178,23 @@ LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
     delete h;
 }
 
-int lsb_rng_create_states_host_impl(uint64_t* states, int64_t n, uint64_t seed, uint64_t subsequence_start);
 cudaEvent_t lsb_reference_event();
 
-// cli/simulate_pixels.py:92-104 maybe_create_rng_states: keep evolved states, append fresh ones
+// cli/simulate_pixels.py:92-104 maybe_create_rng_states: keep evolved states, append fresh ones (made on the device)
 static int chain_grow_rng(lsb_chain* h, long long n, uint64_t seed, cudaStream_t st) {
     if (n <= h->n_rng) return 0;
-    DevBuf nb;
-    if (nb.need((size_t)n * 16)) return -1;
-    if (h->n_rng) LSB_CUDA(cudaMemcpyAsync(nb.p, h->rng.p, (size_t)h->n_rng * 16, cudaMemcpyDeviceToDevice, st));
-    long long add = n - h->n_rng;
-    uint64_t* host = (uint64_t*)malloc((size_t)add * 16);
-    if (!host) return lsb_fail_arg("chain: out of host memory for rng states");
-    lsb_rng_create_states_host_impl(host, add, seed, 0);
-    cudaError_t e = cudaMemcpyAsync((char*)nb.p + (size_t)h->n_rng * 16, host, (size_t)add * 16, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    free(host);
-    if (e != cudaSuccess) return lsb_fail_cuda(e, "rng state upload");
-    h->rng.release();
-    h->rng = nb;
+    if ((size_t)n * 16 > h->rng.cap) {
+        DevBuf nb;
+        if (nb.need((size_t)n * 16)) return -1;
+        if (h->n_rng) {
+            LSB_CUDA(cudaMemcpyAsync(nb.p, h->rng.p, (size_t)h->n_rng * 16, cudaMemcpyDeviceToDevice, st));
+            LSB_CUDA(cudaStreamSynchronize(st));              // the old buffer is freed below
+        }
+        h->rng.release();
+        h->rng = nb;
+    }
+    int rc = rng_create_states_dev((unsigned long long*)h->rng.p + 2 * h->n_rng, n - h->n_rng, seed, 0, st);
+    if (rc) return rc;
     h->n_rng = n;
     return 0;
 }
@@ -199,7 +209,16 @@ static inline void ch_trace(int i) {
     if (i > 0 && now - g_ch_trace_t0 > 1.0) fprintf(stderr, "[lsb chain trace] host %.1f ms before marker %d\n", now - g_ch_trace_t0, i);
     g_ch_trace_t0 = now;
 }
-#define CH_STAGE(i) do { ch_trace(i); if (h->timing) cudaEventRecord(h->ev[i], st); } while (0)
+// NVTX ranges with the reference's names (cli/simulate_pixels.py:917-1105 RangePush / RangePop), host side like there
+#include <nvtx3/nvToolsExt.h>
+static const char* const k_chain_range_names[ST_COUNT + 1] = {"quench+drift", "max_pixels/get_pixels", "unique_pix", "time_intervals", "tracks_current",
+                                                              "pixel_index_map/track_pixel_map", "sum_pixels_signals", "get_adc_values", "digitize", nullptr};
+struct ChainRange {
+    bool open = false;
+    void next(int i) { if (open) nvtxRangePop(); open = false; if (i >= 0 && i < ST_COUNT) { nvtxRangePushA(k_chain_range_names[i]); open = true; } }
+    ~ChainRange() { if (open) nvtxRangePop(); }
+};
+#define CH_STAGE(i) do { ch_trace(i); nvtx_range.next(i); if (h->timing) cudaEventRecord(h->ev[i], st); } while (0)
 
 // Enqueue one batch.  `st` = stream of the front and FEE stages, `st_mc` = stream of the MC stage (may be the
 // same).  Returns with everything queued; the hit count arrives in h->hs_pinned once `st` has drained.
@@ -211,6 +230,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     memset(out, 0, sizeof(*out));
     out->n_segments = S;
     if (S == 0) return 0;
+    ChainRange nvtx_range;
     const int K = c->max_tracks_per_pixel, A = c->max_adc_values, Tt = c->n_time_ticks;
     int rc;
     if ((rc = h->scal.need(sizeof(ChainScalars)))) return rc;
@@ -220,8 +240,10 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     CH_STAGE(0);
     if (st_mc != st) cudaEventRecord(h->tl[0], st);
     // ---- quench, drift (simulate_pixels.py:732,742) -------------------------------------
-    if ((rc = lsb_quench(c, L, tracks_dev, S, quench_mode, st))) return rc;
-    if ((rc = lsb_drift(c, L, tracks_dev, S, st))) return rc;
+    if (quench_mode >= 0) {                                  // < 0: the caller has quenched and drifted the records already
+        if ((rc = lsb_quench(c, L, tracks_dev, S, quench_mode, st))) return rc;
+        if ((rc = lsb_drift(c, L, tracks_dev, S, st))) return rc;
+    }
     CH_STAGE(1);
     // ---- max_radius, max_pixels (:918-928) ----------------------------------------------
     k_chain_max_tran<<<lsb_blocks(S, 256), 256, 0, st>>>(make_layout(L), (const char*)tracks_dev, S, &d_s->max_tran_bits, &d_s->sum_len);
@@ -270,17 +292,32 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     if ((rc = h->signals.need((size_t)S * P * T * 4))) return rc;
     if ((rc = h->sig_ranges.need((size_t)S * P * sizeof(int2)))) return rc;
     h->signals_dense = 0; h->last_rows = S * P; h->last_T = (int)T;
+    // states for the MC stage (index = segment + S * pixel slot, detsim.py:324) and for get_adc_values (index = pixel,
+    // fee.py:557; the reference asks for TPB * BPG = roundup128(U) of them).  Both requests are served BEFORE the MC stage
+    // is queued: it advances the states on its own stream.
     long long need_rng = S * P;
     long long need_rng2 = 128LL * ((U + 127) / 128);
-    if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
+    if (h->rng_fresh) {
+        const long long n = need_rng > need_rng2 ? need_rng : need_rng2;
+        h->n_rng = 0;
+        if ((rc = h->rng.need((size_t)n * 16))) return rc;
+        if ((rc = rng_create_states_dev((unsigned long long*)h->rng.p, need_rng, rng_seed, 0, st))) return rc;
+        if (n > need_rng && (rc = rng_create_states_dev((unsigned long long*)h->rng.p + 2 * need_rng, n - need_rng, rng_seed, 0, st))) return rc;
+        h->n_rng = n;
+    } else {
+        if ((rc = chain_grow_rng(h, need_rng, rng_seed, st))) return rc;
+        if ((rc = chain_grow_rng(h, need_rng2, rng_seed, st))) return rc;
+    }
     if (st_mc != st) { LSB_CUDA(cudaEventRecord(h->ev_front, st)); LSB_CUDA(cudaStreamWaitEvent(st_mc, h->ev_front, 0)); cudaEventRecord(h->tl[1], st); cudaEventRecord(h->tl[2], st_mc); }
     if (st_mc != st) {
         // The MC kernels re-read the response table (15.8 MB) ~2000 times per batch and need it L2-resident,
         // while the FEE stage of the previous batch streams GBs through L2 at the same time: pin the table
         // with a persisting access-policy window on the MC stream.
-        static size_t persist_max = (size_t)-1;
-        if (persist_max == (size_t)-1) {
-            int dev = 0; cudaGetDevice(&dev);
+        static size_t persist_by_dev[64]; static bool persist_init[64] = {false};
+        int dev = 0; cudaGetDevice(&dev); dev = (dev < 0 || dev >= 64) ? 0 : dev;
+        size_t& persist_max = persist_by_dev[dev];
+        if (!persist_init[dev]) {
+            persist_init[dev] = true;
             cudaDeviceProp prop; persist_max = 0;
             if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) persist_max = (size_t)prop.persistingL2CacheMaxSize;
             if (getenv("LSB_NO_L2_PERSIST")) persist_max = 0;        // tuning / A-B switch
@@ -311,7 +348,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
             if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
             if ((rc = mc_run_nosync(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
                                     h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, S, h->mc_ws.p,
-                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, (int2*)h->sig_ranges.p, st))) return rc;
+                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, (int2*)h->sig_ranges.p, &d_s->mc_nfma, &d_s->mc_npairs, st))) return rc;
         } else {
             LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
             k_ranges_full<<<lsb_blocks(S * P, 256), 256, 0, st>>>((int2*)h->sig_ranges.p, S * P, (int)T);
@@ -400,7 +437,6 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
     LSB_CUDA(cudaMemsetAsync(h->adc_ticks.p, 0, (size_t)U * A * 8, st));
     LSB_CUDA(cudaMemsetAsync(h->cf.p, 0, (size_t)U * A * K * 8, st)); LSB_MARK("memset_cf", st);
     k_fill_f64<<<lsb_blocks(U, 256), 256, 0, st>>>((double*)h->thr.p, U, c->discrimination_threshold * c->unit_e); LSB_LAUNCH_CHECK("k_fill_f64");
-    if ((rc = chain_grow_rng(h, need_rng2, rng_seed, st))) return rc;
     {
         FeeSparse sp; sp.signals = (const float*)h->signals.p; sp.T = (int)T; sp.offs = sx.offs; sp.counts = sx.counts;
         sp.sorted = sx.sorted; sp.n_entries_cap = S * P; sp.exact = h->exact_fractions;
@@ -434,6 +470,8 @@ static void chain_finish(lsb_chain* h, lsb_chain_result* out, bool with_timing) 
     if (out->unique_pix) {
         out->n_hits = h->hs_pinned->n_hits;
         if (out->n_samples < 0) out->n_samples = h->hs_pinned->mc_total;
+        out->n_fma = (int64_t)h->hs_pinned->mc_nfma;
+        out->n_pairs = (int64_t)h->hs_pinned->mc_npairs;
     }
     if (h->timing && with_timing && out->unique_pix)
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) out->stage_ms[i] = ms; }

@@ -63,6 +63,8 @@ struct McParams {
     // sync-free operation (fused chain): the sample total stays on the device; every kernel after the scan
     // returns at once if it exceeds the capacity the caller provisioned (and *overflow is raised)
     const long long* total_dev; long long cap; int* overflow;
+    unsigned long long* npairs; // device counter of (segment, pixel) pairs that hold a pixel id (S * P-bar of SURVEY 8d), or null
+    unsigned long long* nfma; // device counter of (sample, tick) pairs that pass every test of detsim.py:299,333,341-344 (N_fma of SURVEY 8d), or null
     int2* ranges;             // fused chain: rows of `signals` are stored sparsely -- only the ticks [lo, hi] covered by the pair's
                               // samples are written, and (lo, hi) is recorded here (empty: lo > hi); everything else is zero by
                               // definition and is neither written nor read (lsb_chain_signals_dense fills it in on request)
@@ -173,6 +175,10 @@ __global__ void k_mc_pairs(Layout L, const char* __restrict__ tracks, const int3
     if (n > 0xffffffffLL) n = 0xffffffffLL;
     nsamp[pr] = (uint32_t)n;
     pairs[pr] = g;
+    if (p.npairs) {
+        const unsigned m = __ballot_sync(__activemask(), pixels[(p.seg0 + itrk) * p.P + (pr % p.P)] >= 0);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(p.npairs, (unsigned long long)__popc(m));
+    }
 }
 
 __global__ void k_mc_set_offsets(McParams p, PairRec* __restrict__ pairs, const long long* __restrict__ offs, long long n) {
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
     int* out32 = offs32 + g.sample_off;
     const SampleU* in = uu + g.sample_off;
     int n_live = 0, n_irr = 0, int_lo = 0, int_hi = p.T - 1, uni_lo = p.T, uni_hi = -1;
+    unsigned long long n_fma = 0;                                    // sum of the live samples' tick counts
     const int M = d_c.mc_sample_multiplier;
     const double W = d_c.time_window, TS = d_c.time_sampling;
     const long long n = g.nstep * M;
@@ -392,6 +399,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
             if (r.shift != SHIFT_IRREGULAR) { int_lo = r.lo > int_lo ? r.lo : int_lo; int_hi = r.hi < int_hi ? r.hi : int_hi; }
             else n_irr++;
             uni_lo = r.lo < uni_lo ? r.lo : uni_lo; uni_hi = r.hi > uni_hi ? r.hi : uni_hi;
+            n_fma += (unsigned long long)(r.hi - r.lo + 1);
         }
         n_live += __popc(m);
     }
@@ -403,8 +411,10 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
         v = __shfl_xor_sync(0xffffffffu, uni_lo, o); uni_lo = v < uni_lo ? v : uni_lo;
         v = __shfl_xor_sync(0xffffffffu, uni_hi, o); uni_hi = v > uni_hi ? v : uni_hi;
         n_irr += __shfl_xor_sync(0xffffffffu, n_irr, o);
+        n_fma += __shfl_xor_sync(0xffffffffu, n_fma, o);
     }
     if (lane == 0) {
+        if (p.nfma && n_fma) atomicAdd(p.nfma, n_fma);
         PairRec* gp = pairs + pr;
         gp->n_live = n_live; gp->n_irregular = n_irr; gp->int_lo = int_lo; gp->int_hi = int_hi; gp->uni_lo = uni_lo; gp->uni_hi = uni_hi;
     }
@@ -1200,7 +1210,7 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
     g_mc_last_samples = 0;
-    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.ranges = nullptr;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.ranges = nullptr; p.nfma = nullptr; p.npairs = nullptr;
     return mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states,
                         rng_mode, p, workspace, workspace_bytes, st, 0);
 }
@@ -1212,7 +1222,8 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
 static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S, const int32_t* pixels,
                          int32_t P, float* signals, int32_t T, const void* response, int32_t Rx, int32_t Ry, int32_t Rt,
                          int32_t response_f64, uint64_t* rng_states, int64_t rng_stride, void* workspace,
-                         int64_t workspace_bytes, long long* total_out, int* overflow, int2* ranges, cudaStream_t st) {
+                         int64_t workspace_bytes, long long* total_out, int* overflow, int2* ranges, unsigned long long* nfma,
+                         unsigned long long* npairs, cudaStream_t st) {
     if (S == 0 || P == 0 || T == 0) return 0;
     if (require_current_fields(L, true)) return -1;
     int rc = lsb_upload_consts(c, st); if (rc) return rc;
@@ -1220,7 +1231,7 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
     p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
-    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.ranges = ranges;
+    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.ranges = ranges; p.nfma = nfma; p.npairs = npairs;
     rc = mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states, 0, p,
                       workspace, workspace_bytes, st, 0);
     if (rc) return rc;

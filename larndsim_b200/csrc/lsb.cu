@@ -9,8 +9,12 @@ long long g_lsb_launches = 0;
 
 static lsb_consts g_consts_host;
 static bool g_consts_valid = false;
+static int g_consts_device = -1;          // the __constant__ copy lives on ONE device: a cudaSetDevice invalidates the cache
 
 int lsb_upload_consts(const lsb_consts* c, cudaStream_t st) {
+    int dev = -1;
+    LSB_CUDA(cudaGetDevice(&dev));
+    if (dev != g_consts_device) { g_consts_valid = false; g_consts_device = dev; }
     if (g_consts_valid && memcmp(&g_consts_host, c, sizeof(lsb_consts)) == 0) return 0;
     if (c->n_tpc < 0 || c->n_tpc > LSB_MAX_TPC) return lsb_fail_arg("consts: n_tpc out of range");
     // kernels of earlier calls (any stream) may still read the old snapshot
@@ -100,7 +104,9 @@ LSB_EXPORT int64_t lsb_profile_end(char* out, int64_t cap) {
 #include "packets.cuh"
 #include "light_trigger.cuh"
 #include "batching.cuh"
+#include "rng.cuh"
 #include "chain.cuh"
+#include "spill.cuh"
 
 LSB_EXPORT int lsb_abi_version(void) { return LSB_ABI_VERSION; }
 LSB_EXPORT const char* lsb_last_error(void) { return g_lsb_error; }

@@ -236,12 +236,14 @@ __device__ __forceinline__ lsb_packet pkt_blank(int type) {
 __global__ void k_pkt_write(PktTables T, PktTrig G, long long N, int A, const Scan3* __restrict__ sc, const double* __restrict__ ticks,
                             const double* __restrict__ adc, const long long* __restrict__ pix_t0, const double* __restrict__ pix_t0_us,
                             const long long* __restrict__ event_id, const PixInfo* __restrict__ info, const long long* __restrict__ offs,
-                            long long cap, lsb_packet* __restrict__ out, long long* __restrict__ src_slot) {
+                            long long cap, lsb_packet* __restrict__ out, long long* __restrict__ src_slot,
+                            const long long* __restrict__ base_dev) {
+    // base_dev (optional): device-resident position of this call's first packet in `out` (append mode of the spill runner)
     const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (s >= N) return;
     bool evchange, ts, data; long long tt, r;
     if (pkt_slot_plan(T, G, s, A, sc, ticks, pix_t0, event_id, evchange, ts, data, tt, r) == 0) return;
-    long long o = offs[s];
+    long long o = offs[s] + (base_dev ? *base_dev : 0);
     const long long ip = s / A;
     auto put = [&](const lsb_packet& p, long long src) { if (o < cap) { out[o] = p; src_slot[o] = src; } o++; };
     if (evchange) {
@@ -296,14 +298,23 @@ __global__ void k_pkt_write(PktTables T, PktTrig G, long long N, int A, const Sc
 __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packets, const long long* __restrict__ src_slot, int A, int K, int NA,
                                                               const long long* __restrict__ event_id, const double* __restrict__ cf,
                                                               const long long* __restrict__ track_ids, const long long* __restrict__ traj_ids,
-                                                              char* __restrict__ rows) {
+                                                              char* __restrict__ rows, const long long* __restrict__ n_dev,
+                                                              const long long* __restrict__ base_dev, long long cap,
+                                                              const long long* __restrict__ seg_map, const long long* __restrict__ traj_map) {
     // one output row = the mc_packets_assn record: event_ids i8[1] | segment_ids i8[NA] | fraction f8[NA] | file_traj_ids i8[NA] |
-    // fraction_traj f8[NA]  (8 + 32 NA bytes, every field 8-byte aligned)
+    // fraction_traj f8[NA]  (8 + 32 NA bytes, every field 8-byte aligned).
+    // Append mode (spill runner): the packet count and the position of the first packet are read from the device (n_dev,
+    // base_dev; the grid is sized without knowing them and strides), and track_ids / traj_ids hold segment indices of the batch
+    // that are translated through seg_map / traj_map on the fly (cli/simulate_pixels.py:1114-1115).
     __shared__ double s_f[ASSN_WARPS][ASSN_MAXK];        // fractions in sorted order
     __shared__ long long s_t[ASSN_WARPS][ASSN_MAXK];     // trajectory ids in sorted order
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long ipk = blockIdx.x * (long long)ASSN_WARPS + w;
-    if (ipk >= n_packets) return;
+    const long long n_all = n_dev ? *n_dev : n_packets;
+    const long long base = base_dev ? *base_dev : 0;
+  for (long long ipk0 = blockIdx.x * (long long)ASSN_WARPS + w; ipk0 < n_all; ipk0 += (long long)gridDim.x * ASSN_WARPS) {
+    const long long ipk = base + ipk0;
+    if (ipk >= cap) break;
+    __syncwarp();
     const long long s = src_slot[ipk];
     char* row = rows + ipk * (8LL + 32LL * NA);
     long long* o_event = reinterpret_cast<long long*>(row);
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packet
     long long* tj = reinterpret_cast<long long*>(row + 8 + 16LL * NA); double* ftj = reinterpret_cast<double*>(row + 8 + 24LL * NA);
     for (int j = lane; j < NA; j += 32) { seg[j] = -1; fr[j] = 0.0; tj[j] = -1; ftj[j] = 0.0; }
     if (lane == 0) o_event[0] = s >= 0 ? event_id[s] : -1;
-    if (s < 0) return;
+    if (s < 0) continue;
     __syncwarp();
     const long long ip = s / A;
     const double* f = cf + s * (long long)K;
@@ -322,8 +333,11 @@ __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packet
         const double fi = f[i];
         int rank = 0;
         for (int j = 0; j < K; j++) { const double fj = f[j]; rank += (fj > fi) || (fj == fi && j > i); }
-        s_f[w][rank] = fi; s_t[w][rank] = trj[i];
-        if (rank < NA) { seg[rank] = trk[i]; fr[rank] = fi; }
+        long long tr = trj[i], sg = trk[i];
+        if (traj_map && tr >= 0) tr = traj_map[tr];
+        if (seg_map && sg >= 0) sg = seg_map[sg];
+        s_f[w][rank] = fi; s_t[w][rank] = tr;
+        if (rank < NA) { seg[rank] = sg; fr[rank] = fi; }
     }
     __syncwarp();
     // trajectories: ascending unique ids, fractions summed in sorted order, stored through float32
@@ -367,6 +381,7 @@ __global__ void __launch_bounds__(32 * ASSN_WARPS) k_pkt_assn(long long n_packet
         tj[tidx] = id;
         ftj[tidx] = (double)__double2float_rn(res);
     }
+  }
 }
 
 static int scan3_inclusive(Scan3* io, long long n, Scan3* tile_tot, cudaStream_t st) {
@@ -440,10 +455,11 @@ LSB_EXPORT int lsb_export_packets(const lsb_readout_tables* rt, int64_t U, int32
     if (n_out == 0) return 0;
     LSB_REQUIRE(packets && assn_rows && current_fractions && track_ids && traj_ids, "export_packets: null output / truth pointer");
     k_pkt_write<<<lsb_blocks(N, 256), 256, 0, st>>>(T, G, N, A, sc, adc_ticks, adc, (const long long*)pix_t0_ticks, pix_t0_us,
-                                                    (const long long*)event_id, info, offs, cap_packets, packets, src);
+                                                    (const long long*)event_id, info, offs, cap_packets, packets, src, nullptr);
     LSB_LAUNCH_CHECK("k_pkt_write");
     k_pkt_assn<<<lsb_blocks(n_out, ASSN_WARPS), 32 * ASSN_WARPS, 0, st>>>(n_out, src, A, K, n_assn, (const long long*)event_id, current_fractions,
-                                                                         (const long long*)track_ids, (const long long*)traj_ids, (char*)assn_rows);
+                                                                         (const long long*)track_ids, (const long long*)traj_ids, (char*)assn_rows, nullptr, nullptr, n_out,
+                                                                         nullptr, nullptr);
     LSB_LAUNCH_CHECK("k_pkt_assn");
     LSB_CUDA(cudaStreamSynchronize(st));      // the uploaded tables are temporaries of this call
     return 0;

@@ -74,9 +74,15 @@ def export_to_hdf5(event_id_list, adc_list, adc_ticks_list, unique_pix, current_
             import h5py                                                  # noqa: F401
             from larpix.format import hdf5format                         # noqa: F401
         except ImportError:
+            _warn_no_file(filename)
             return packets, ds
         _write_larpix_file(filename, packets, ds)
     return packets, ds
+
+
+def _warn_no_file(filename):
+    import warnings
+    warnings.warn("larpix / h5py are not importable: %r was NOT written (the packets are returned)" % (filename,), RuntimeWarning)
 
 
 def _write_larpix_file(filename, packets, ds):
@@ -185,6 +191,7 @@ def _finish_export(filename, packets, ds):
             import h5py                                                  # noqa: F401
             from larpix.format import hdf5format                         # noqa: F401
         except ImportError:
+            _warn_no_file(filename)
             return packets, ds
         _write_larpix_file(filename, packets, ds)
     return packets, ds

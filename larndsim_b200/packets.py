@@ -204,6 +204,8 @@ def export_packets(tables, event_id_list, adc_list, adc_ticks_list, unique_pix, 
             continue
         _l.check(rc, "export_packets")
         break
+    else:
+        _l.check(rc, "export_packets")
     n = int(n_out.value)
     # one D2H copy per table into pinned memory; the NumPy results are views of those buffers
     h_pk = torch.empty(n * PACKET_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)

@@ -23,8 +23,30 @@ def create_xoroshiro128p_states_host(n, seed, subsequence_start=0):
 
 
 def create_xoroshiro128p_states(n, seed, subsequence_start=0):
-    """Device array of ``n`` states, state i = jump^(subsequence_start+i)(splitmix64(seed))."""
-    return _l.DeviceRecords(host=create_xoroshiro128p_states_host(n, seed, subsequence_start))
+    """Device array of ``n`` states, state i = jump^(subsequence_start+i)(splitmix64(seed)) -- made on the device in one
+    launch (``lsb_rng_create_states``: the 2^64-step jump as a GF(2) matrix power), bit-identical to Numba's host loop."""
+    out = _l.DeviceRecords(dtype=xoroshiro128p_dtype, n=int(n))
+    if n:
+        _l.check(_l.lib().lsb_rng_create_states(C.c_void_p(out.buf.data_ptr()), C.c_int64(int(n)),
+                                                C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_uint64(int(subsequence_start)),
+                                                _l.stream()), "create_xoroshiro128p_states")
+    return out
+
+
+def _state_bytes(rng_states):
+    """uint8 CUDA tensor over any device state array (this package's, Numba's or CuPy's)."""
+    if hasattr(rng_states, "buf"):
+        return rng_states.buf
+    d = _l.dev(rng_states, name="rng_states", records=True)
+    nbytes = d.size * d.dtype.itemsize
+
+    class _H:
+        pass
+    h = _H()
+    h.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(d.ptr), False), "version": 3, "strides": None}
+    t = torch.as_tensor(h, device="cuda")
+    t._lsb_keep = rng_states
+    return t
 
 
 def maybe_create_rng_states(n, seed=0, rng_states=None):
@@ -33,7 +55,7 @@ def maybe_create_rng_states(n, seed=0, rng_states=None):
         return create_xoroshiro128p_states(n, seed=seed)
     if n > len(rng_states):
         fresh = create_xoroshiro128p_states(n - len(rng_states), seed=seed)
-        buf = torch.cat([rng_states.buf, fresh.buf])
+        buf = torch.cat([_state_bytes(rng_states), fresh.buf])
         return _l.DeviceRecords(dtype=xoroshiro128p_dtype, n=n, buf=buf)
     return rng_states
 

@@ -29,11 +29,14 @@ class TrackSegmentBatcher(object):
 
 
 class TPCBatcher(TrackSegmentBatcher):
-    def __init__(self, all_track_seg, track_seg, event_separator, tpc_batch_size=1, tpc_borders=np.empty((0, 3, 2), dtype='f4')):
+    def __init__(self, all_track_seg, track_seg, event_separator, tpc_batch_size=1, tpc_borders=np.empty((0, 3, 2), dtype='f4'),
+                 events=None):
+        """``events`` (extension): the sorted unique values of the event field, for callers whose records live on the
+        device (the reference computes ``np.unique(all_track_seg[event_separator])`` on the host, batching.py:29)."""
         super().__init__(all_track_seg, track_seg, event_separator)
         self.tpc_batch_size = tpc_batch_size
         self.tpc_borders = np.sort(_av._borders(tpc_borders), axis=-1)
-        self._events = np.unique(self.all_track_seg[self.EVENT_SEPARATOR])
+        self._events = np.unique(self.all_track_seg[self.EVENT_SEPARATOR]) if events is None else np.asarray(events)
         self._next_unit = 0                     # position of the iterator: unit = event rank * n_tpc_batches + TPC group
         self._order = self._offsets = None
 
@@ -66,8 +69,28 @@ class TPCBatcher(TrackSegmentBatcher):
                                      C.c_void_p(offsets.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_int64(nws), _l.stream()),
                  "batch_units")
         self._order_dev, self._offsets_dev = order, offsets
-        self._order, self._offsets = order.cpu().numpy(), offsets.cpu().numpy()
+        self._offsets = offsets.cpu().numpy()
+        self._order = True            # planned; the row permutation itself stays on the device until someone asks for it
+        self._order_host = None
         self._n = n
+
+    def _order_np(self):
+        self._plan()
+        if self._order_host is None:
+            self._order_host = self._order_dev.cpu().numpy()
+        return self._order_host
+
+    @property
+    def order_dev(self):
+        """int64 CUDA tensor: rows of ``track_seg`` sorted by unit (stable), the rows that belong to no unit last"""
+        self._plan()
+        return self._order_dev
+
+    @property
+    def unit_offsets(self):
+        """int64[len(self) + 1]: unit u = ``order[unit_offsets[u] : unit_offsets[u + 1]]``"""
+        self._plan()
+        return self._offsets
 
     @property
     def unit_sizes(self):
@@ -79,7 +102,7 @@ class TPCBatcher(TrackSegmentBatcher):
         """(event, ascending segment indices) per batch, in iteration order"""
         self._plan()
         nB = self.n_tpc_batches
-        src = self._order_dev if device else self._order
+        src = self._order_dev if device else self._order_np()
         for u in range(len(self._events) * nB):
             yield self._events[u // nB], src[int(self._offsets[u]):int(self._offsets[u + 1])]
 
@@ -96,7 +119,7 @@ class TPCBatcher(TrackSegmentBatcher):
             raise StopIteration
         self._next_unit = u + 1
         self._plan()
-        rows = self._order[int(self._offsets[u]):int(self._offsets[u + 1])]
+        rows = self._order_np()[int(self._offsets[u]):int(self._offsets[u + 1])]
         mask = np.zeros(self._n, dtype=bool)
         mask[rows] = True
         return self._events[u // self.n_tpc_batches], mask

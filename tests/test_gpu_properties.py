@@ -1,6 +1,7 @@
-"""Size-independent properties of the CUDA chain at the benchmark size (BASELINE.json configs[1]: module0,
-1e4 synthetic cosmic segments) where the oracle is too slow to run in full, plus the statistical agreement
-of the production ("cloud") RNG discipline with the reference's draw pattern ("replay")."""
+"""Size-independent properties of the CUDA chain at the benchmark sizes (BASELINE.json configs[1]: module0, 1e4 synthetic
+cosmic segments; 2x2 / ND-LAr beam spills of 2e4), plus the statistical agreement of the production ("cloud") RNG discipline
+with the reference's draw pattern ("replay").  The comparison of the same batches with the oracle, stage by stage, is in
+tests/test_gpu_fullsize.py (10-20 s of oracle time per batch)."""
 import numpy as np
 import pytest
 
@@ -128,24 +129,52 @@ def test_pipeline_matches_synchronous_chain(cuda):
             got.append((r.unique_pix.cpu().numpy(), r.adc_list.cpu().numpy(), r.adc_ticks_list.cpu().numpy(),
                         r.current_fractions.cpu().numpy(), r.n_hits))
     devs = [ll.DeviceRecords(host=b) for b in batches]
-    for d in devs:
+    for j, d in enumerate(devs):
         if pipe.full():
             take(pipe.collect())
-        pipe.submit(d, rng_seed=7)
+        pipe.submit(d, rng_seed=7 + j)
     while pipe._inflight:
         take(pipe.collect())
     pipe.close()
     assert len(got) == 4
-    # chain k of the pipeline sees batches k, k+2, ... with its own evolving RNG states
-    for k in range(2):
-        ch = lchain.Chain(batches[0].dtype, resp)
-        for j in (k, k + 2):
-            r = ch.run(ll.DeviceRecords(host=batches[j]), rng_seed=7)
-            ref = (r.unique_pix.cpu().numpy(), r.adc_list.cpu().numpy(), r.adc_ticks_list.cpu().numpy(),
-                   r.current_fractions.cpu().numpy(), r.n_hits)
-            for a, b in zip(got[j], ref):
-                assert np.array_equal(a, b)
-        ch.close()
+    # pipeline chains start every batch from create_xoroshiro128p_states(n, seed = rng_seed): a batch gives the same bytes
+    # whichever chain runs it and whatever ran before
+    ch = lchain.Chain(batches[0].dtype, resp, rng_fresh=True)
+    for j in (3, 0, 2, 1):
+        r = ch.run(ll.DeviceRecords(host=batches[j]), rng_seed=7 + j)
+        ref = (r.unique_pix.cpu().numpy(), r.adc_list.cpu().numpy(), r.adc_ticks_list.cpu().numpy(),
+               r.current_fractions.cpu().numpy(), r.n_hits)
+        for a, b in zip(got[j], ref):
+            assert np.array_equal(a, b)
+    ch.close()
+
+
+def test_consecutive_batches_do_not_repeat_noise(cuda):
+    """Identical input in consecutive batches must not see identical noise (round-1 advisor finding): the evolving policy
+    advances its states, the pipeline's fresh policy is given one seed per batch -- and the same seed reproduces."""
+    from larndsim_b200 import chain as lchain
+    mod = lc.load_snapshot("module0")
+    resp = synth.response_lut(mod.detector)
+    tracks = h.production_tracks(400, "module0", 21)
+
+    def table(r):
+        return r.adc_list.cpu().numpy().copy(), r.adc_ticks_list.cpu().numpy().copy()
+    ch = lchain.Chain(tracks.dtype, resp)                                      # evolving states (reference policy)
+    a = table(ch.run(ll.DeviceRecords(host=tracks.copy()), rng_seed=3))
+    b = table(ch.run(ll.DeviceRecords(host=tracks.copy()), rng_seed=3))
+    ch.close()
+    assert a[0].shape == b[0].shape and not np.array_equal(a[0], b[0])
+    pipe = lchain.Pipeline(tracks.dtype, resp, depth=2)
+    out = []
+    for seed in (3, 4, 3):
+        if pipe.full():
+            out.append(table(pipe.collect()))
+        pipe.submit(ll.DeviceRecords(host=tracks.copy()), rng_seed=seed)
+    out += [table(r) for r in pipe.drain()]
+    pipe.close()
+    assert not np.array_equal(out[0][0], out[1][0])                            # chain 0 / chain 1, different seeds
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])   # same seed, other position in the stream
+    assert np.array_equal(out[0][0], a[0])                                     # fresh(seed 3) == first batch of an evolving chain seeded 3
 
 
 @pytest.mark.parametrize("config,kind,n", [("2x2", "beam", 20000), ("ndlar", "beam", 20000)])

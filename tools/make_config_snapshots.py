@@ -35,7 +35,7 @@ LIGHT = ["LIGHT_SIMULATED", "ENABLE_LUT_SMEARING", "N_OP_CHANNEL", "OP_CHANNEL_E
          "LIGHT_DET_NOISE_SAMPLE_SPACING"]
 SIM = ["BATCH_SIZE", "EVENT_BATCH_SIZE", "EVENT_SEPARATOR", "MAX_TRACKS_PER_PIXEL", "MIN_STEP_SIZE",
        "MC_SAMPLE_MULTIPLIER", "ASSOCIATION_COUNT_TO_STORE", "MAX_ADC_VALUES", "MAX_MC_TRUTH_IDS",
-       "MC_TRUTH_THRESHOLD"]
+       "MC_TRUTH_THRESHOLD", "WRITE_BATCH_SIZE", "IS_SPILL_SIM", "SPILL_PERIOD", "MAX_EVENTS_PER_FILE"]
 PHYS = ["BOX_ALPHA", "BOX_BETA", "BIRKS_Ab", "BIRKS_kb", "W_ION", "BOX", "BIRKS", "E_CHARGE"]
 UNITS = ["e", "mV", "ns", "mus", "cm", "mm", "s"]
 
