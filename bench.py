@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the charge-readout chain (BASELINE.json metric: segments/s quench -> ADC).
+"""Benchmark of the charge-readout path (BASELINE.json metric: segments/s quench -> ADC at 1/2/4/8 B200).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = one pass of the hot path (quench -> drift -> get_pixels -> tracks_current_mc -> unique / index
-maps -> sum_pixel_signals -> get_adc_values -> digitize) over one batch of synthetic segments.  Workload at
-N=1: BASELINE.json configs[1] -- module0 geometry, 1e4 synthetic cosmic-muon segments, noise on.  For N>1
-(torchrun, one rank per GPU) every rank processes its own batch of the same size (different muons:
-independent (event, module) units), no collective inside the chain; the per-step hit
-packets are gathered to rank 0 over NCCL.  ``value`` = segments of all ranks / max-over-ranks device time.
+Workload (every N): ONE fixed synthetic ND-LAr beam spill -- ndlar config (70 TPCs), 1e6 segments in 4 events, seed 12345
+(BASELINE.json configs[4]) -- run the way the reference runs a file (cli/simulate_pixels.py:667-1117 +
+save_results -> fee.export_to_hdf5): active-volume cut -> quench -> drift -> (event, TPC pair) batches of
+larndsim/util/batching.py -> per batch get_pixels -> tracks_current_mc -> sum_pixel_signals -> get_adc_values -> digitize ->
+LArPix packets + mc_packets_assn rows.  A step = the whole spill.  With N ranks (torchrun, one per GPU) the 140 batches are
+assigned to the ranks longest-first, there is no collective inside the chain, and every rank's packets go to rank 0 over
+NCCL where they are put into file order: STRONG scaling, `value` = 1e6 segments / max-over-ranks device time per step.
 
-``--impl reference`` times the CPU implementation of the same path: the reference's kernels are Numba
-Python and cannot travel to the GPU box, so this arm runs the C restatement pinned to them
-(oracle/larnd_oracle.c, OpenMP on all host cores) on a bounded sample of the same batch.
+`value`: records resident in HBM when the timed region starts, packets left in rank 0's HBM.  `e2e`: the same call with the
+records in pinned host memory and the packets, truth rows and updated records copied back to host arrays (H2D/D2H inside).
+
+`--impl reference` times the CPU implementation of the same path: the reference's kernels are Numba Python (CUDA simulator:
+~1e3 s per segment), so this arm runs the C/OpenMP restatement pinned to them (oracle/larnd_oracle.c) with every host core on
+a bounded sample of the same spill.  The reference's own Numba-CUDA build on the same B200 is timed by
+tools/ref_numba_cuda.py (block `reference_numba_cuda` of our line).
 """
 import argparse
 import ctypes as C
@@ -29,17 +34,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CONFIG = "module0"
-N_SEGMENTS = 10000
-METRIC = "segments/s quench->ADC (module0, 1e4 synthetic cosmic-muon segments per batch)"
+CONFIG = "ndlar"
+N_SEGMENTS = int(os.environ.get("LSB_BENCH_SEGMENTS", 1_000_000))
+N_EVENTS = int(os.environ.get("LSB_BENCH_EVENTS", 4))
+SEED = 12345
+RAND_SEED = 1
+METRIC = "segments/s quench->ADC (ndlar config, synthetic beam spill of %.0e segments in %d events, (event, TPC pair) batches)" % (N_SEGMENTS, N_EVENTS)
+WORKLOAD = ("ndlar config, synthetic full beam spill (%d segments, %d events, seed %d), charge readout quench->drift->get_pixels->"
+            "tracks_current_mc->sum_pixel_signals->get_adc_values->digitize->packets, noise on, one fixed spill partitioned by "
+            "(event, TPC pair) over the GPUs") % (N_SEGMENTS, N_EVENTS, SEED)
 
 
-def make_batch(seed):
+def make_spill():
+    """(constants module, records, response table); the spill is cached under /tmp for the other arm / ranks"""
     from larndsim_b200 import consts as lc, synth
     mod = lc.load_snapshot(CONFIG)
-    tracks = synth.cosmic_segments(N_SEGMENTS, mod.detector, seed=seed)
-    response = synth.response_lut(mod.detector)
-    return mod, tracks, response
+    path = "/tmp/lsb_bench_spill_%s_%d_%d_%d.npy" % (CONFIG, N_SEGMENTS, N_EVENTS, SEED)
+    tracks = None
+    if os.path.exists(path):
+        try:
+            tracks = np.load(path)
+            if tracks.dtype != synth.segment_dtype or len(tracks) != N_SEGMENTS:
+                tracks = None
+        except Exception:
+            tracks = None
+    if tracks is None:
+        tracks = synth.beam_spill_segments(N_SEGMENTS, mod.detector, seed=SEED, n_events=N_EVENTS)
+        tracks["segment_id"] = np.arange(len(tracks))
+        tracks["file_traj_id"] = tracks["traj_id"]
+        try:
+            tmp = path + ".%d.tmp.npy" % os.getpid()
+            np.save(tmp, tracks)
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    return mod, tracks, synth.response_lut(mod.detector)
 
 
 class ClockSampler:
@@ -114,10 +143,48 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_chain(tracks, response, n_sample, rng_seed=1):
-    """The CPU restatement of the chain on the first n_sample segments; returns seconds."""
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the pinned C/OpenMP restatement (oracle/) on a bounded sample of the same spill
+# ------------------------------------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm wants every core (set before libgomp initialises, and again through its API)"""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(n))
+    except OSError:
+        pass
+    return n
+
+
+def cpu_sample(tracks, mod, n_sample):
+    """the first `n_sample` segments of the first (event, TPC pair) batch of the spill that holds that many (else of the largest
+    batch), as the loop would hand them to the chain"""
+    det = mod.detector
+    b = np.asarray(det.TPC_BORDERS, dtype=np.float64)
+    lo, hi = np.minimum(b[:, :, 0], b[:, :, 1]), np.maximum(b[:, :, 0], b[:, :, 1])
+    first = np.full(len(tracks), -1, dtype=np.int64)
+    for tpc in range(b.shape[0] - 1, -1, -1):                  # lowest TPC index that contains the start or the end point
+        for sfx in ("start", "end"):
+            ins = np.ones(len(tracks), dtype=bool)
+            for k, ax in enumerate("xyz"):
+                v = tracks["%s_%s" % (ax, sfx)].astype(np.float64)
+                ins &= (v > lo[tpc, k]) & (v < hi[tpc, k])
+            first[ins] = tpc
+    events = np.unique(tracks["event_id"])
+    n_pairs = (b.shape[0] + 1) // 2
+    unit = np.searchsorted(events, tracks["event_id"]) * n_pairs + first // 2
+    unit[first < 0] = -1
+    counts = np.bincount(unit[unit >= 0], minlength=len(events) * n_pairs)
+    big = np.nonzero(counts >= n_sample)[0]
+    u = int(big[0]) if len(big) else int(np.argmax(counts))
+    return np.ascontiguousarray(tracks[unit == u][:n_sample])
+
+
+def cpu_chain(sub, response, rng_seed=1):
+    """The CPU restatement of the chain on one batch; returns (seconds, hits)."""
     import helpers as h
-    sub = tracks[:n_sample].copy()
+    sub = sub.copy()
     orc = h.Oracle()
     t0 = time.perf_counter()
     front = h.oracle_front(sub, orc, quench_mode=orc.c.mode_birks)
@@ -130,33 +197,35 @@ def cpu_chain(tracks, response, n_sample, rng_seed=1):
     return dt, int((back["digit"] > orc.digitize(np.zeros(1))[0]).sum())
 
 
-def omp_threads():
-    n = os.environ.get("OMP_NUM_THREADS")
-    return int(n) if n else (os.cpu_count() or 1)
-
-
 def run_reference(args, rank, world):
     if rank != 0:
-        return
-    mod, tracks, response = make_batch(12345)
-    n_sample = 2048
+        return                                     # rank 0 alone runs and prints; the others exit 0 without work
+    cores = use_all_host_threads()
+    mod, tracks, response = make_spill()
+    # bounded sample: sized from a calibration run so that the K timed steps take about 90 s on this host
+    probe = cpu_sample(tracks, mod, 96)
+    cpu_chain(probe[:16], response)
+    t_probe, _ = cpu_chain(probe, response)
+    n_auto = int(len(probe) / t_probe * 90.0 / max(args.steps, 1))
+    n_sample = int(os.environ.get("LSB_BENCH_CPU_SAMPLE", max(128, min(4096, n_auto))))
+    sub = cpu_sample(tracks, mod, n_sample)
     for _ in range(args.warmup):
-        cpu_chain(tracks, response, 32)
+        cpu_chain(sub[:32], response)
     times = []
     for _ in range(args.steps):
-        dt, hits = cpu_chain(tracks, response, n_sample)
+        dt, hits = cpu_chain(sub, response)
         times.append(dt)
     total = sum(times)
-    value = n_sample * args.steps / total
-    cores = omp_threads()
+    value = len(sub) * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments), charge readout quench->ADC",
-                       "sample": "first %d of the 1e4-segment batch per step" % n_sample},
+            "config": {"workload": WORKLOAD,
+                       "sample": "per step the first %d segments of the spill's first (event, TPC pair) batch" % len(sub)},
             "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": "port",
-                             "sample": "first %d segments of the batch, CPU restatement pinned to the reference's golden vectors "
-                                       "(the reference itself is Numba Python and does not exist on the GPU box)" % n_sample},
+                             "sample": "first %d segments of the first batch of the spill per step; C/OpenMP restatement pinned to the "
+                                       "reference's golden vectors (the reference itself is Numba Python: ~1e3 s per segment under "
+                                       "the CUDA simulator)" % len(sub)},
             "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -171,6 +240,56 @@ def parse_profile(txt):
     return out
 
 
+def profile_session(lib, fn):
+    from larndsim_b200 import _launch as ll
+    import torch
+    torch.cuda.synchronize()
+    lib.lsb_profile_begin(ll.stream())
+    fn()
+    torch.cuda.synchronize()
+    buf = C.create_string_buffer(1 << 16)
+    lib.lsb_profile_end(buf, C.c_int64(len(buf)))
+    return parse_profile(buf.value.decode())
+
+
+FP32_LANES = 148 * 128                                   # B200: 148 SMs x 128 FP32 lanes (no tensor cores on this path)
+
+
+def kernel_rooflines(prof, steps, shape, peak_hbm, sm_mhz):
+    """SURVEY.md 8(d) algorithmic work per kernel x the units of the profiled launches / measured launch time.
+    `shape`: sums over the profiled batches -- n_fma, n_samples, pair_ticks (valid pairs x T), pixel_ticks (U x Tt), U, S, P."""
+    fp32_peak = FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
+    A, K = shape["A"], shape["K"]
+    alg = {
+        # 2 flop per (sample, tick) pair that passes every test: the table FMA
+        "k_mc_accumulate": ("fp32", 2.0 * shape["n_fma"]),
+        # 4 B signals read per valid (pair, tick) + 8 B per pixel tick written (sparse form: the reference's 8 B slot write per
+        # (pair, tick) into pixels_tracks_signals is not materialised, so it is not counted as work done)
+        "k_sum_pixel_signals": ("hbm", 4.0 * shape["pair_ticks"] + 8.0 * shape["pixel_ticks"]),
+        # get_adc_values: one pass over pixels_signals + the noise streams + the hit tables
+        "k_fee_trigger": ("hbm", 8.0 * shape["pixel_ticks"] + 2 * 8.0 * shape["U"] * A),
+        "k_fee_fir_pre": ("hbm", 2 * 8.0 * shape["pixel_ticks"]),
+        "k_fee_fractions_sparse": ("hbm", 4.0 * shape["pair_ticks"] + 8.0 * shape["U"] * A * K),
+        "k_mc_sampler": ("fp32", 330.0 * shape["n_samples"]),
+        "k_mc_uniforms": ("hbm", 24.0 * shape["n_samples"]),
+        "k_mc_sort": ("hbm", 4.0 * shape["n_samples"] + 16.0 * shape["n_samples"] / 3.0),
+    }
+    out = {}
+    for name, (bound, work) in alg.items():
+        if name not in prof or prof[name][1] <= 0:
+            continue
+        cnt, ms = prof[name]
+        if bound == "hbm":
+            ach = work / (ms * 1e-3) / 1e9
+            out[name] = {"bound": "hbm", "algorithmic_bytes": work, "ms": ms, "launches": cnt, "achieved": ach, "peak": peak_hbm,
+                         "unit": "GB/s", "frac": ach / peak_hbm}
+        else:
+            ach = work / (ms * 1e-3) / 1e12
+            out[name] = {"bound": "fp32", "algorithmic_flops": work, "ms": ms, "launches": cnt, "achieved": ach, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": ach / fp32_peak}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -178,370 +297,279 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
-        if os.environ.get("LSB_BENCH_BACKEND") == "gloo":       # diagnostic: control plane without NCCL (no hit gather)
-            os.environ["LSB_NO_GATHER"] = "1"
-            dist.init_process_group("gloo")
-        else:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from larndsim_b200 import _launch as ll, chain as lchain, consts as lc
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+    from larndsim_b200 import _launch as ll, chain as lchain, consts as lc, spill as lspill
     lib = ll.lib()
     lib.lsb_profile_end.restype = C.c_int64
-    # weak scaling: every rank simulates a batch of the same size AND the same content (independent detector modules seeing
-    # identical muons), so the per-rank work is exactly fixed as N grows and max-over-ranks is not a lottery over batches
-    mod, tracks, response = make_batch(12345)
+    lib.lsb_launch_count.restype = C.c_int64
+    mod, tracks, response = make_spill()
     S = len(tracks)
     itemsize = tracks.dtype.itemsize
-    ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud", stage_timing=True)
+    events = np.unique(tracks["event_id"])
+    snap = lc.snapshot()
+    A, K, Tt = int(snap.max_adc_values), int(snap.max_tracks_per_pixel), int(snap.n_time_ticks)
+    depth = int(os.environ.get("LSB_BENCH_DEPTH", 3))
+    runner = lspill.SpillRunner(tracks.dtype, response, depth=depth)
     raw = torch.from_numpy(tracks.view(np.uint8).reshape(-1).copy())
     pinned_in = raw.pin_memory()
     n_total = args.warmup + args.steps
     dev_copies = [ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda()) for _ in range(n_total)]
-    A, K = int(lc.snapshot().max_adc_values), int(lc.snapshot().max_tracks_per_pixel)
-
-    from larndsim_b200 import dist as ldist
-    gatherer = [None]
-
-    def gather_packets(res):
-        """hit table (pixel id, ADC codes, timestamps) of this batch -> rank 0 (north_star: NCCL only here);
-        one fixed-size NCCL gather per batch, no host synchronisation."""
-        if world == 1 or os.environ.get("LSB_NO_GATHER"):
-            return
-        if gatherer[0] is None:
-            from larndsim_b200 import packets as lp
-            ped = lp.ReadoutTables.from_consts()._c.adc_pedestal              # digitize(0): a hit is an ADC code above it
-            gatherer[0] = ldist.HitTableGather(2 * int(res.n_unique_pixels) + 4096, ped, "cuda")
-        gatherer[0].gather(res.unique_pix, res.adc_digit, res.adc_ticks_list)
 
     def sync():
-        if world > 1 and not os.environ.get("LSB_BENCH_NO_BARRIER"):       # (diagnostic switch)
+        if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    side = torch.cuda.Stream()
-    torch.cuda.synchronize()
-    torch.cuda.set_stream(side)          # everything below is timed with events on this (non-blocking) stream
-    # ---------------- value: device-resident inputs, three batches in flight ----------------
-    # Batches are independent, so the timed loop keeps two of them in flight (chain.Pipeline): the FEE stage of
-    # batch i (latency-bound, high-priority stream) runs under the MC stage of batch i+1 (L1-bound, low priority).
-    pipe = lchain.Pipeline(tracks.dtype, response, depth=2, rng_mode="cloud")
-    results = []
-
-    def collect(r):
-        if r is not None:
-            results.append(r)
-            gather_packets(r)
-
-    host_t = {"collect": 0.0, "submit": 0.0, "n": 0}
-
-    def step(batch):
-        w0 = time.perf_counter()
-        if pipe.full():
-            collect(pipe.collect())          # consume the oldest result before its chain is reused
-        w1 = time.perf_counter()
-        pipe.submit(batch, rng_seed=1)
-        host_t["collect"] += w1 - w0; host_t["submit"] += time.perf_counter() - w1; host_t["n"] += 1
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # ---------------- value: records resident in HBM, packets left in rank 0's HBM ----------------
     for i in range(args.warmup):
-        step(dev_copies[i])
-    while pipe._inflight:
-        collect(pipe.collect())
+        runner.simulate(dev_copies[i], events=events, rand_seed=RAND_SEED, host_output=False)
     sync()
-    results.clear()
     launches0 = lib.lsb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    host_t.update(collect=0.0, submit=0.0, n=0)
     sampler.begin()
     e0.record()
     for i in range(args.steps):
-        step(dev_copies[args.warmup + i])
-    while pipe._inflight:
-        collect(pipe.collect())
-    if gatherer[0] is not None:
-        gatherer[0].flush()                  # every hit table has reached rank 0 inside the timed region
+        last = runner.simulate(dev_copies[args.warmup + i], events=events, rand_seed=RAND_SEED, host_output=False)
     e1.record()
     sync()
     sampler.end()
     launches = lib.lsb_launch_count() - launches0
-    assert len(results) == args.steps
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    per_rank = [{"ms_per_step": ms / args.steps, "mc_sample_points": int(results[-1].n_samples)}]
+    ms_own = e0.elapsed_time(e1)
+    ms_max = max_over_ranks(ms_own)
+    value = S * args.steps / (ms_max * 1e-3)
+    st = last.stats
+    per_rank = [{"ms_per_step": ms_own / args.steps, "units": st["n_units_here"], "segments": st["n_segments_here"],
+                 "packets": st["n_packets_here"]}]
     if world > 1:
-        # every rank simulates different muons (independent units): batches differ in their number of sample points
-        rdev = "cpu" if dist.get_backend() == "gloo" else "cuda"
-        t = t.to(rdev)
-        allv = [torch.zeros(2, device=rdev, dtype=torch.float64) for _ in range(world)]
-        dist.all_gather(allv, torch.tensor([ms / args.steps, float(results[-1].n_samples)], device=rdev, dtype=torch.float64))
-        per_rank = [{"ms_per_step": float(v[0].item()), "mc_sample_points": int(v[1].item())} for v in allv]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * S * args.steps / (ms_max * 1e-3)
-    res = results[-1]
-    U, T, P_ = res.n_unique_pixels, res.n_ticks, res.max_neighbors
-    n_samples = res.n_samples
-    n_hits = res.n_hits
-
-    # ---------------- per-kernel device times: the same K steps, one batch at a time ----------------
-    # (kernels of overlapping batches would stretch each other's event intervals)
-    fresh = [ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda()) for _ in range(args.steps + 1)]
-    ch.run(fresh[0], rng_seed=1)
-    sync()
-    lib.lsb_profile_begin(ll.stream())
-    stage_acc = {}
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(args.steps):
-        r1 = ch.run(fresh[1 + i], rng_seed=1)
-        for k, v in r1.stage_ms.items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-    s1.record()
-    sync()
-    buf = C.create_string_buffer(1 << 16)
-    lib.lsb_profile_end(buf, C.c_int64(len(buf)))
-    prof = parse_profile(buf.value.decode())
-    ms_serial = s0.elapsed_time(s1) / args.steps
-
-    # ---------------- e2e: host buffers through the public chain call (pipelined the same way) ----------------
-    ucap = int(U * 1.2) + 1024
-    outs = [(torch.empty(ucap, dtype=torch.int32).pin_memory(), torch.empty((ucap, A), dtype=torch.float64).pin_memory(),
-             torch.empty((ucap, A), dtype=torch.float64).pin_memory()) for _ in range(3)]
-    host_batches = [raw.clone().pin_memory() for _ in range(3 + args.steps)]
-    for i in range(3):
-        if pipe.full():
-            pipe.collect()
-        pipe.submit_host(host_batches[i], *outs[i % 3], rng_seed=1)
-    pipe.drain()
+        v = torch.tensor([ms_own / args.steps, st["n_units_here"], st["n_segments_here"], st["n_packets_here"]], device="cuda", dtype=torch.float64)
+        allv = [torch.zeros_like(v) for _ in range(world)]
+        dist.all_gather(allv, v)
+        per_rank = [{"ms_per_step": float(a[0]), "units": int(a[1]), "segments": int(a[2]), "packets": int(a[3])} for a in allv]
+    del dev_copies
+    # ---------------- e2e: pinned host records in, packets + truth rows + updated records in host arrays out ----------------
+    host_np = pinned_in.numpy().view(tracks.dtype)
+    for _ in range(2):
+        out = runner.simulate(host_np, events=events, rand_seed=RAND_SEED, host_output=True, return_tracks=True)
     sync()
     sampler.begin()
     e0.record()
     for i in range(args.steps):
-        if pipe.full():
-            pipe.collect()
-        pipe.submit_host(host_batches[3 + i], *outs[i % 3], rng_seed=1)
-    r2 = pipe.drain()[-1]
+        out = runner.simulate(host_np, events=events, rand_seed=RAND_SEED, host_output=True, return_tracks=True)
     e1.record()
     sync()
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device="cpu" if (world > 1 and dist.get_backend() == "gloo") else "cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * args.steps / (float(t.item()) * 1e-3)
-    h2d = S * itemsize
-    d2h = S * itemsize + r2.n_unique_pixels * 4 + 2 * r2.n_unique_pixels * A * 8
-
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = S * args.steps / (ms_e2e * 1e-3)
+    if world > 1:                 # last collective of the job: rank 0 continues alone (per-kernel pass, secondary blocks)
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
-    # ---------------- next stage (SURVEY 8f rank 1): hits of one batch -> LArPix packets + truth rows ----------------
-    packets_block = None
+    n_packets = int(out.n_packets)
+    n_data = int((out.packets["packet_type"] == 0).sum())
+    h2d = S * itemsize
+    d2h = n_packets * (32 + runner.assn_dtype.itemsize) + out.n_segments * itemsize
+    unit_sizes = out.unit_sizes
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak, peak_src = measured_peaks()
+
+    # ---------------- per-kernel times: rank 0's share of the spill, one unit at a time on one stream ----------------
+    roofline = None
+    kernels = None
+    by_kernel = None
     try:
-        from larndsim_b200 import packets as lp
-        tables = lp.ReadoutTables.from_consts()
-        ev = torch.zeros((U, A), dtype=torch.int64, device="cuda")
-        tpm = res.track_pixel_map
-        traj = torch.where(tpm >= 0, tpm // 7, tpm)
-        t0s = np.array([1000.0])
-        lp.export_packets(tables, ev, res.adc_digit, res.adc_ticks_list, res.unique_pix, res.current_fractions, tpm, traj, t0s)
+        prof_runner = lspill.SpillRunner(tracks.dtype, response, depth=1, single_rank=True)      # the other ranks are done: no collective here
+        prof_runner.set_serial(True)
+        d_prof = ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda())
+        prof_runner.simulate(ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda()), events=events, rand_seed=RAND_SEED, host_output=False)
+        holder = {}
+
+        def prof_pass():
+            holder["out"] = prof_runner.simulate(d_prof, events=events, rand_seed=RAND_SEED, host_output=False)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        l0 = lib.lsb_launch_count()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            pk, ds = lp.export_packets(tables, ev, res.adc_digit, res.adc_ticks_list, res.unique_pix, res.current_fractions, tpm, traj, t0s)
+        s0.record()
+        prof = profile_session(lib, prof_pass)
+        s1.record()
         torch.cuda.synchronize()
-        pk_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-        alg_bytes = 8.0 * U * A * 3 + 8.0 * n_hits * K * 3 + len(pk) * (32 + 8 * (1 + 4 * tables.association_count))
-        packets_block = {"ms_per_batch": pk_ms, "packets_per_batch": int(len(pk)), "data_packets": int((pk["packet_type"] == 0).sum()),
-                         "packets_per_s": len(pk) / (pk_ms * 1e-3), "launches_per_batch": (lib.lsb_launch_count() - l0) / args.steps,
-                         "timed": "wall clock around the public call (device inputs, results copied to host arrays)",
-                         "algorithmic_bytes": alg_bytes, "note": "latency-bound at this size (10 launches, 2 host syncs, 2 D2H copies); not part of `value`"}
-        if not os.environ.get("LSB_BENCH_NO_CPU"):
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import packets_oracle as po
-            import packets_util as pu                     # readout tables as plain containers (tests/)
-            z = pu.load("module0")
-            nsub = min(U, 2000)
-            args_cpu = [x[:nsub].cpu().numpy() for x in (ev, res.adc_digit, res.adc_ticks_list, res.unique_pix, res.current_fractions, tpm, traj)]
-            w0 = time.perf_counter()
-            opk, _ = po.export_packets(pu.tables_from_npz(z), *args_cpu, t0s)
-            cpu_s = time.perf_counter() - w0
-            packets_block["cpu_python_restatement"] = {"packets_per_s": len(opk) / cpu_s, "sample": "first %d pixels, %.2f s, 1 core" % (nsub, cpu_s)}
-    except Exception as exc:                                   # the packet stage is an extra: never lose the headline line
-        packets_block = {"error": repr(exc)}
-    # ---------------- next stage (SURVEY 8f rank 3): light triggers + digitisation of one module's waveforms ----------------
+        ms_serial = s0.elapsed_time(s1)
+        pst = holder["out"].stats
+        kern = [(k, v) for k, v in prof.items() if not k.startswith("(")]
+        total_kernel_ms = sum(v[1] for _, v in kern)
+        top_name, (top_cnt, top_ms) = max(kern, key=lambda kv: kv[1][1])
+        shape = {"n_fma": pst["n_fma"], "n_samples": pst["n_samples"], "pair_ticks": pst["pair_ticks"], "pixel_ticks": pst["pixel_ticks"],
+                 "U": pst["n_unique_pixels"], "A": A, "K": K}
+        by_kernel = kernel_rooflines(prof, 1, shape, peak, sm_mhz)
+        traffic, ncu = None, {}
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            ncu = tj.get(top_name, {})
+            traffic = ncu.get("dram_bytes_per_launch")
+        rk = by_kernel.get(top_name, {})
+        roofline = {"kernel": top_name, "bound": rk.get("bound"), "achieved": rk.get("achieved"), "peak": rk.get("peak"), "unit": rk.get("unit"),
+                    "frac": rk.get("frac"), "traffic": traffic,
+                    "traffic_source": (tj.get("_source") if traffic else None) if os.path.exists(tpath) else None,
+                    "timed": "CUDA events on the launching stream around every launch of the kernel: the whole spill on rank 0, one "
+                             "batch at a time on one stream (%d launches)" % top_cnt,
+                    "share_of_kernel_time": top_ms / total_kernel_ms, "ms_per_launch": top_ms / max(top_cnt, 1), "launches": top_cnt,
+                    "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (non-tensor FP32: nothing on the path is a contraction)" % sm_mhz
+                                   if rk.get("bound") == "fp32" else peak_src,
+                    "work": "2 flop x N_fma; N_fma = (sample, tick) pairs that pass every test of detsim.py:299,333,341-344, counted on the "
+                            "device by the sampler (%d in these launches)" % pst["n_fma"] if top_name == "k_mc_accumulate" else "SURVEY.md 8(d)"}
+        if top_name == "k_mc_accumulate":
+            t_s = top_ms * 1e-3
+            onchip = 4.0 * pst["n_fma"] / t_s / 1e12
+            roofline["onchip"] = {"what": "table words the algorithmic formulation reads from L1 / shared memory: 4 B x N_fma", "achieved": onchip,
+                                  "peak": 148 * 128 * sm_mhz * 1e6 / 1e12, "unit": "TB/s", "frac": onchip / (148 * 128 * sm_mhz * 1e6 / 1e12),
+                                  "ncu_l1tex_throughput_pct": ncu.get("l1tex_throughput_pct"), "ncu_issue_active_pct": ncu.get("issue_active_pct")}
+            mc_ms = sum(prof[k][1] for k in ("k_mc_pairs", "k_mc_uniforms", "k_mc_sampler", "k_mc_sort", "k_mc_accumulate", "k_mc_fused") if k in prof)
+            flops = 2.0 * pst["n_fma"] + 330.0 * pst["n_samples"]
+            fp32_peak = FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
+            roofline["tracks_current_mc_stage"] = {"algorithmic_flops": flops, "ms": mc_ms, "achieved_tflops": flops / (mc_ms * 1e-3) / 1e12,
+                                                   "peak_tflops": fp32_peak, "frac": flops / (mc_ms * 1e-3) / 1e12 / fp32_peak,
+                                                   "work": "SURVEY 8(d): 2 N_fma + 330 N_sp (N_sp = %d sample points)" % pst["n_samples"]}
+        kernels = {k: {"launches": v[0], "ms": v[1], "share": v[1] / total_kernel_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}
+        kernels["_total_kernel_ms"] = total_kernel_ms
+        kernels["_wall_ms_of_the_profiled_pass"] = ms_serial
+        prof_runner.close()
+        del d_prof
+    except Exception as exc:                                   # extras never lose the headline line
+        roofline = {"error": repr(exc)}
+
+    # ---------------- secondary workload: BASELINE configs[1], module0 1e4 cosmic segments per batch (round-1 headline) ----------------
+    module0_block = None
+    try:
+        module0_block = bench_module0(lib, ll, lchain, lc, peak, sm_mhz, steps=max(3, min(args.steps, 10)))
+    except Exception as exc:
+        module0_block = {"error": repr(exc)}
+    lc.load_snapshot(CONFIG)
+    # ---------------- light path (BASELINE configs[3]) ----------------
     light_block = None
     try:
-        from larndsim_b200 import light_sim
-        import light_trigger_util as ltu
-        C_l = ltu.consts_from_npz(ltu.load("module0"))
-        sig_l, op_l, tid_l, tph_l = ltu.case_inputs("module0", C_l["OP_CHANNEL_PER_TRIG"], C_l["N_OP_CHANNEL"])
-        thr_l = ltu.thresholds(C_l, op_l)
-        sig_d = torch.from_numpy(sig_l).cuda(); tid_d = torch.from_numpy(tid_l).cuda(); tph_d = torch.from_numpy(tph_l).cuda()
-        zero_noise = np.zeros((C_l["N_OP_CHANNEL"], 33))
-        ns_l = 256
-
-        def light_once():
-            trig, chans, _ = light_sim.get_triggers(sig_d, thr_l, op_l, 0)
-            return light_sim.sim_triggers((1, 1, 1), (1, 1, 64), sig_d, op_l, tid_d, tph_d, trig, chans, ns_l, zero_noise), trig
-        light_once()
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            (dg, _, _), trig_l = light_once()
-        torch.cuda.synchronize()
-        l_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-        light_block = {"ms_per_call": l_ms, "channels": int(sig_l.shape[0]), "ticks": int(sig_l.shape[1]), "triggers": int(len(trig_l)),
-                       "digitised_samples": int(dg.numel()), "workload": "tests/light_trigger_util.py case module0 (96 channels x 9000 ticks, 2 truth slots)",
-                       "timed": "wall clock around get_triggers + sim_triggers (device inputs)",
-                       "algorithmic_bytes": 4.0 * sig_l.size + 8.0 * dg.numel() * (1 + 2 * tid_l.shape[2])}
-        if not os.environ.get("LSB_BENCH_NO_CPU"):
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import light_trigger_oracle as lo
-            w0 = time.perf_counter()
-            t_o, c_o, _ = lo.get_triggers(sig_l, thr_l, op_l, 0, C_l)
-            lo.sim_triggers(sig_l, op_l, tid_l, tph_l, t_o[:1], c_o[:1, :8], ns_l, C_l)
-            cpu_s = time.perf_counter() - w0
-            light_block["cpu_python_restatement"] = {"seconds": cpu_s, "sample": "trigger search on all channels + digitisation of 1 trigger x 8 channels (of %d x %d), 1 core" % (len(t_o), c_o.shape[1])}
+        import bench_light
+        light_block = bench_light.run(peak, steps=3)
     except Exception as exc:
         light_block = {"error": repr(exc)}
-    # ---------------- BASELINE metric, second half: the deterministic tracks_current kernel (detsim.py:351-453) ----------------
-    # (not called by the CLI; a bounded sample of the same batch: SAMPLED_POINTS^2 x z_steps rho evaluations per pair and tick slab)
-    tc_block = None
-    try:
-        import helpers as hh
-        from larndsim_b200 import detsim, quenching, drifting, pixels_from_track as pft
-        n_tc = 128
-        sub = tracks[:n_tc].copy()
-        d_sub = ll.DeviceRecords(host=sub)
-        quenching.quench[1, 1](d_sub, int(lc.snapshot().mode_birks))
-        drifting.drift[1, 1](d_sub)
-        fr = hh.oracle_front(sub.copy(), hh.Oracle(lc.snapshot()))         # pixel lists / tick count of the sample (host)
-        neigh = torch.from_numpy(fr["neigh"]).cuda()
-        sig_tc = torch.zeros((n_tc, fr["P"], fr["T"]), dtype=torch.float32, device="cuda")
-        resp_d = torch.from_numpy(response).cuda()
-        detsim.tracks_current[1, 1](sig_tc, neigh, d_sub, resp_d)
-        torch.cuda.synchronize()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sig_tc.zero_()
-        t0e.record()
-        detsim.tracks_current[1, 1](sig_tc, neigh, d_sub, resp_d)
-        t1e.record()
-        torch.cuda.synchronize()
-        tc_ms = t0e.elapsed_time(t1e)
-        live_pairs = int((sig_tc != 0).any(dim=2).sum().item())
-        live_ticks = int((sig_tc != 0).sum().item())
-        sp = int(mod.detector.SAMPLED_POINTS)
-        n_rho = float(live_pairs) * sp * sp * sp                              # z_steps >= SAMPLED_POINTS: a lower bound
-        flops = 110.0 * n_rho + 2.0 * sp * sp * sp * live_ticks                # SURVEY 8(d): 110 N_rho + 2 N_rho T_act
-        sm_clk_tc = 1965.0
-        tc_block = {"segments": n_tc, "ms": tc_ms, "segments_per_s": n_tc / (tc_ms * 1e-3), "live_pairs": live_pairs,
-                    "flops_lower_bound": flops, "achieved_tflops_lower_bound": flops / (tc_ms * 1e-3) / 1e12,
-                    "fp32_peak_tflops": 148 * 128 * 2 * sm_clk_tc * 1e6 / 1e12, "frac_of_fp32_peak_lower_bound": flops / (tc_ms * 1e-3) / (148 * 128 * 2 * sm_clk_tc * 1e6),
-                    "note": "the kernel evaluates rho (erf, exp, log) and the table products in float64 like the reference, so its own ceiling is the "
-                            "FP64 / transcendental rate, not FP32 FFMA; flops count the algorithmic formulation with z_steps = SAMPLED_POINTS"}
-    except Exception as exc:
-        tc_block = {"error": repr(exc)}
-    # ---------------- roofline of the dominant kernel ----------------
-    peak, peak_src = measured_peaks()
-    Tt = int(lc.snapshot().n_time_ticks)
-    kern = [(k, v) for k, v in prof.items() if not k.startswith("(")]
-    total_kernel_ms = sum(v[1] for _, v in kern)
-    top_name, (top_cnt, top_ms) = max(kern, key=lambda kv: kv[1][1])
-    per_launch_ms = top_ms / max(top_cnt, 1)
-    launches_per_step = top_cnt / args.steps
-    # algorithmic HBM bytes per launch (DESIGN.md section 4).  n_valid = (segment,pixel) pairs with a pixel,
-    # T_act = ticks with time >= 0 actually written (about half of T for uniformly distributed drift times)
-    n_valid = 0.61 * S * P_
-    alg = {
-        # out: the ticks of signals the samples cover (rows are stored sparsely, about half of T per valid pair); in: group
-        # records (16 B, ~1 per 3 samples), sample records for the edge ticks (24 B), pair records
-        "k_mc_accumulate": 4.0 * n_valid * T * 0.5 + 24.0 * n_samples + 16.0 * n_samples / 3.0 + 160.0 * S * P_,
-        "k_fee_trigger": 8.0 * U * Tt + 4.0 * U * 4480 + 2 * 8.0 * U * A,
-        "k_sum_pixel_signals": 4.0 * n_valid * T + 2 * 8.0 * U * Tt,
-        "k_mc_sampler": 24.0 * n_samples + 28.0 * n_samples,
-        "k_mc_uniforms": 24.0 * n_samples,
-        "k_mc_sort": 4.0 * n_samples + 16.0 * n_samples / 3.0,
-    }
-    traffic = None
-    ncu = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        ncu = tj.get(top_name, {})
-        traffic = ncu.get("dram_bytes")
-    bytes_per_launch = alg.get(top_name)
-    roofline = {"kernel": top_name, "bound": "hbm", "timed": "CUDA events on the launching stream, same K steps run one batch at a time",
-                "share_of_kernel_time": top_ms / total_kernel_ms, "ms_per_launch": per_launch_ms, "launches_per_step": launches_per_step,
-                "achieved": (bytes_per_launch / (per_launch_ms * 1e-3) / 1e9) if bytes_per_launch else None,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": traffic,
-                "traffic_source": tj.get("_source") if traffic else None}
-    roofline["frac"] = roofline["achieved"] / peak if roofline["achieved"] else None
-    if top_name == "k_mc_accumulate":
-        # This kernel is not HBM-bound (the table is L2/L1-resident): its limiter is the L1TEX data pipe.  The HBM figures
-        # above are reported because the contract asks for them; these explain the kernel.  Algorithmic work (SURVEY 8d):
-        # N_fma sample-tick pairs, one table word and one add each; the grouped path serves them with ~1 aligned LDG.128
-        # per 2.4 pairs x 32 lanes and a count-weighted FFMA per distinct offset.
-        n_fma = 32.0 * 9.19e8 * (S * P_ / 180000.0)      # sample-tick pairs per launch (ncu count of the one-load-per-pair kernel)
-        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
-        mc_ms = sum(prof[k][1] for k in ("k_mc_pairs", "k_mc_uniforms", "k_mc_sampler", "k_mc_sort", "k_mc_accumulate") if k in prof) / args.steps
-        fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
-        roofline["limiter"] = {"what": "L1TEX data pipe (table gather, table L2-resident)",
-                               "sample_tick_pairs_per_launch": n_fma, "pairs_per_s": n_fma / (per_launch_ms * 1e-3),
-                               "l1_wavefront_peak_per_s": 148 * sm_clk * 1e6,
-                               "ncu_l1tex_throughput_pct": ncu.get("l1tex_throughput_pct"),
-                               "ncu_l1_global_load_requests": ncu.get("l1_global_load_requests"),
-                               "ncu_issue_active_pct": ncu.get("issue_active_pct")}
-        # BASELINE metric, second half: tracks_current_mc against the FP32 peak, algorithmic FLOPs of SURVEY 8(d)
-        flops = 2.0 * n_fma + 330.0 * n_samples
-        roofline["tracks_current_mc_fp32"] = {"algorithmic_flops_per_batch": flops, "stage_ms": mc_ms,
-                                              "achieved_tflops": flops / (mc_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                                              "frac": flops / (mc_ms * 1e-3) / 1e12 / fp32_peak,
-                                              "peak_source": "148 SM x 128 lanes x 2 x SM clock (no tensor cores: nothing is a contraction)"}
-    kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
-               sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
-
-    # ---------------- CPU baseline (bounded sample) ----------------
+    lc.load_snapshot(CONFIG)
+    # ---------------- CPU baseline (bounded sample) + the reference's own Numba-CUDA build on this GPU ----------------
     cpu = None
-    if world == 1 and not os.environ.get("LSB_BENCH_NO_CPU"):     # (the switch is for kernel A/B runs, tools/ab_variants.sh)
-        n_cpu = 4096
-        cpu_chain(tracks, response, 16)
-        cpu_s, _ = cpu_chain(tracks, response, n_cpu)
-        cpu = {"value": n_cpu / cpu_s, "unit": "segments/s", "cores": omp_threads(), "kind": "port",
-               "sample": "first %d segments of the same batch, %.1f s; C/OpenMP restatement of the reference kernels (oracle/), "
-                         "pinned to the reference's golden vectors" % (n_cpu, cpu_s)}
+    ref_cuda = None
+    if world == 1 and not os.environ.get("LSB_BENCH_NO_CPU"):
+        cores = use_all_host_threads()
+        sub = cpu_sample(tracks, mod, 2048)
+        cpu_chain(sub[:16], response)
+        cpu_s, _ = cpu_chain(sub, response)
+        cpu = {"value": len(sub) / cpu_s, "unit": "segments/s", "cores": cores, "kind": "port",
+               "sample": "first %d segments of the spill's first (event, TPC pair) batch, %.1f s; C/OpenMP restatement of the reference "
+                         "kernels (oracle/), pinned to the reference's golden vectors" % (len(sub), cpu_s)}
+        try:
+            runner.close()
+            torch.cuda.empty_cache()
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_numba_cuda.py"), "--config", "module0", "--segments", "10000"],
+                               capture_output=True, text=True, timeout=300)
+            ref_cuda = json.loads(p.stdout.strip().split("\n")[-1])
+            ref_cuda.pop("traceback", None)
+        except Exception as exc:
+            ref_cuda = {"unavailable": repr(exc)}
 
     line = {"metric": METRIC, "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 index/gating + f32 LUT accumulation (signals f32, pixel sums f64)", "data": "synthetic",
-            "config": {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments), charge readout quench->ADC, noise on",
-                       "segments_per_batch": S, "pixels_per_segment_row": P_, "unique_pixels": U, "ticks": T, "hits": n_hits,
-                       "mc_sample_points": n_samples, "rng": "cloud (one sample cloud per segment x pixel)",
-                       "l2": "per-step working set (signals %.2f GB dense-equivalent, per-segment pixel waveforms %.2f GB) >> 126 MB L2; fresh input copy each step"
-                             % (4.0 * S * P_ * T / 1e9, 8.0 * U * Tt * K / 1e9),
-                       "pipeline": "2 batches in flight per GPU (FEE stage of batch i under the MC stage of batch i+1)",
-                       "parallelism": "1 batch stream per rank (identical batch on every rank), no collective in the chain; NCCL gather of the compacted hit packets to rank 0" if world > 1 else "single GPU"},
+            "config": {"workload": WORKLOAD, "segments": S, "events": int(len(events)), "batches": int(len(unit_sizes)),
+                       "batch_segments_min_mean_max": [int(unit_sizes.min()), float(unit_sizes.mean()), int(unit_sizes.max())],
+                       "packets": n_packets, "data_packets": n_data, "hits": st["n_hits"] if world == 1 else None,
+                       "rng": "cloud (one sample cloud per segment x pixel); per-batch states = create_xoroshiro128p_states(seed = rand_seed + batch number)",
+                       "l2": "per-step working set (152 MB of records, ~1 GB of sparse waveforms per batch in flight, %.2f GB of packets + truth rows) >> 126 MB L2; "
+                             "fresh device copy of the records each step" % (d2h / 1e9),
+                       "pipeline": "%d batches in flight per GPU (front-end stage of one batch under the current stage of the next)" % depth,
+                       "parallelism": ("%d ranks, batches assigned longest-first, no collective in the chain; NCCL send/recv of the packets + truth rows to rank 0, "
+                                       "file order restored on the device" % world) if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(t.item()) / args.steps},
-            "gpu_launches": int(launches), "per_rank": per_rank, "host_ms_per_step": {"wait_for_oldest_batch": 1e3 * host_t["collect"] / max(host_t["n"], 1),
-                                                              "submit_next_batch": 1e3 * host_t["submit"] / max(host_t["n"], 1)},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "packets": packets_block, "light_triggers": light_block, "tracks_current": tc_block,
-            "ms_per_step_unpipelined": ms_serial,
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()}, "kernels": kernels}
+                    "ms_per_step": ms_e2e / args.steps,
+                    "what": "SpillRunner.simulate(host records) -> host packets, mc_packets_assn rows and updated records (what fee.export_to_hdf5 "
+                            "and the segments dataset receive)"},
+            "gpu_launches": int(launches), "per_rank": per_rank, "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel,
+            "cpu_baseline": cpu, "reference_numba_cuda": ref_cuda, "module0_1e4": module0_block, "light": light_block, "kernels": kernels}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def bench_module0(lib, ll, lchain, lc, peak, sm_mhz, steps):
+    """BASELINE configs[1]: module0, 1e4 synthetic cosmic-muon segments per batch, quench -> digitize (no packets), two batches in
+    flight; plus the per-kernel rooflines on that batch shape."""
+    import torch
+    from larndsim_b200 import synth
+    mod = lc.load_snapshot("module0")
+    tracks = synth.cosmic_segments(10000, mod.detector, seed=12345)
+    response = synth.response_lut(mod.detector)
+    S = len(tracks)
+    snap = lc.snapshot()
+    A, K, Tt = int(snap.max_adc_values), int(snap.max_tracks_per_pixel), int(snap.n_time_ticks)
+    raw = torch.from_numpy(tracks.view(np.uint8).reshape(-1).copy()).pin_memory()
+    warm = 3
+    copies = [ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=raw.cuda()) for _ in range(warm + steps)]
+    pipe = lchain.Pipeline(tracks.dtype, response, depth=2, rng_mode="cloud")
+    results = []
+
+    def step(i):
+        if pipe.full():
+            results.append(pipe.collect())
+        pipe.submit(copies[i], rng_seed=RAND_SEED + i)
+    for i in range(warm):
+        step(i)
+    results += pipe.drain()
+    torch.cuda.synchronize()
+    results.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warm + i)
+    results += pipe.drain()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pipe.close()
+    # per-kernel, one batch at a time
+    ch = lchain.Chain(tracks.dtype, response, rng_mode="cloud", stage_timing=True)
+    fresh = [ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=raw.cuda()) for _ in range(steps + 1)]
+    r1 = ch.run(fresh[0], rng_seed=1)
+    acc = {"n_fma": 0, "n_samples": 0, "pair_ticks": 0, "pixel_ticks": 0, "U": 0, "A": A, "K": K}
+    stage_acc = {}
+
+    def passes():
+        for i in range(steps):
+            r = ch.run(fresh[1 + i], rng_seed=1)
+            acc["n_fma"] += r.n_fma; acc["n_samples"] += r.n_samples; acc["pair_ticks"] += r.n_pairs * r.n_ticks
+            acc["pixel_ticks"] += r.n_unique_pixels * Tt; acc["U"] += r.n_unique_pixels
+            for k, v in r.stage_ms.items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+    prof = profile_session(lib, passes)
+    ch.close()
+    by_kernel = kernel_rooflines(prof, steps, acc, peak, sm_mhz)
+    return {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments per batch), quench->digitize, 2 batches in flight, noise on",
+            "segments_per_s": S / (ms * 1e-3), "ms_per_batch": ms, "unique_pixels": r1.n_unique_pixels, "ticks": r1.n_ticks, "hits": r1.n_hits,
+            "n_fma_per_batch": acc["n_fma"] / steps, "mc_sample_points_per_batch": acc["n_samples"] / steps,
+            "stage_ms_per_batch": {k: v / steps for k, v in stage_acc.items()},
+            "kernel_ms_per_batch": {k: v[1] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
+            "roofline_by_kernel": by_kernel}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -274,6 +274,7 @@ typedef struct lsb_chain_result {
     int64_t n_hits;                   /* adc_list entries above pedestal */
     int64_t n_samples, n_fma;         /* MC sample points N_sp / (sample,tick) pairs that pass every test N_fma, counted on the device */
     int64_t n_pairs;                  /* (segment,pixel) pairs that hold a pixel id (S * P-bar) */
+    int64_t n_groups, n_edge, n_irregular;   /* MC diagnostics: group records of the grouped gather, (sample,tick) pairs on edge ticks, samples on the exact path */
     /* device pointers valid until the next run / destroy */
     const int32_t* unique_pix;        /* [U] */
     const int64_t* track_pixel_map;   /* [U][K] */

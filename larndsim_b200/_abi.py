@@ -76,7 +76,7 @@ class LincLayout(C.Structure):
 class ChainResult(C.Structure):
     _fields_ = [("n_segments", C.c_int64), ("n_unique_pixels", C.c_int64), ("max_active", C.c_int64),
                 ("max_neighbors", C.c_int64), ("n_ticks", C.c_int64), ("n_hits", C.c_int64),
-                ("n_samples", C.c_int64), ("n_fma", C.c_int64), ("n_pairs", C.c_int64),
+                ("n_samples", C.c_int64), ("n_fma", C.c_int64), ("n_pairs", C.c_int64), ("n_groups", C.c_int64), ("n_edge", C.c_int64), ("n_irregular", C.c_int64),
                 ("unique_pix", C.c_void_p), ("track_pixel_map", C.c_void_p), ("adc_list", C.c_void_p),
                 ("adc_digit", C.c_void_p), ("adc_ticks_list", C.c_void_p), ("current_fractions", C.c_void_p),
                 ("signals", C.c_void_p), ("pixels_signals", C.c_void_p),

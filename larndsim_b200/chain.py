@@ -21,6 +21,7 @@ class ChainResult:
         self.n_segments, self.n_unique_pixels = int(r.n_segments), int(r.n_unique_pixels)
         self.max_active, self.max_neighbors, self.n_ticks = int(r.max_active), int(r.max_neighbors), int(r.n_ticks)
         self.n_hits, self.n_samples, self.n_fma, self.n_pairs = int(r.n_hits), int(r.n_samples), int(r.n_fma), int(r.n_pairs)
+        self.n_groups, self.n_edge, self.n_irregular = int(r.n_groups), int(r.n_edge), int(r.n_irregular)
         self.stage_ms = {STAGES[i]: float(r.stage_ms[i]) for i in range(len(STAGES))}
         #: async batches: ms since the library's reference event of (front begin, front end, MC begin, MC end, FEE begin, done)
         self.timeline = [float(r.stage_ms[i]) for i in range(6)]

@@ -33,12 +33,13 @@ enum { ST_QUENCH_DRIFT = 0, ST_GET_PIXELS, ST_UNIQUE, ST_TIME_INTERVALS, ST_TRAC
        ST_GET_ADC, ST_DIGITIZE, ST_COUNT };
 
 struct ChainScalars { long long max_pixels; unsigned long long max_tran_bits; long long n_unique; long long t_max; int max_dist; int mc_overflow;
-                      long long n_hits; double sum_len; long long mc_total; unsigned long long mc_nfma, mc_npairs; };
+                      long long n_hits; double sum_len; long long mc_total; unsigned long long mc_nfma, mc_npairs, mc_diag[3]; };
 
 struct lsb_chain {
     lsb_consts c;
     lsb_track_layout L;
     const void* response; int Rx, Ry, Rt, f64, rng_mode, timing;
+    DevBuf response_split;    // phase-split copy of the table (RESPONSE_SAMPLING = TIME_SAMPLING / 2), see current.cuh
     DevBuf sig_ranges;        // int2 per (segment, pixel) row of `signals`: ticks that hold data (rows are stored sparsely)
     int signals_dense;        // the rows of the last batch have been zero-filled outside their ranges
     long long last_rows; int last_T;
@@ -127,6 +128,11 @@ LSB_EXPORT lsb_chain* lsb_chain_create(const lsb_consts* c, const lsb_track_layo
     cudaMallocHost((void**)&h->hs_pinned, sizeof(ChainScalars));
     h->pending_valid = 0;
     h->arena.base = nullptr; h->arena.cap = h->arena.off = h->arena.high_water = h->arena.overflow = 0;
+    if (rng_mode == 0 && mc_wants_split(c, response_f64)) {
+        cudaStream_t st = h->hp;
+        if (h->response_split.need((size_t)Rx * Ry * Rt * 4) || mc_build_split(response, Rx, Ry, Rt, (float*)h->response_split.p, st) ||
+            cudaStreamSynchronize(st) != cudaSuccess) { lsb_chain_destroy(h); return nullptr; }
+    }
     return h;
 }
 LSB_EXPORT int lsb_chain_set_dense(lsb_chain* h, int32_t dense) {
@@ -163,7 +169,7 @@ LSB_EXPORT int lsb_chain_signals_dense(lsb_chain* h, void* stream) {
 }
 LSB_EXPORT void lsb_chain_destroy(lsb_chain* h) {
     if (!h) return;
-    h->sig_ranges.release();
+    h->sig_ranges.release(); h->response_split.release();
     DevBuf* all[] = {&h->tracks, &h->scal, &h->active, &h->neigh, &h->nrad, &h->npl, &h->uniq, &h->uniq_ws, &h->starts, &h->signals,
                      &h->mc_ws, &h->pim, &h->tpm, &h->psig, &h->pts, &h->oflow, &h->tticks, &h->integral, &h->adc_digit,
                      &h->adc_ticks, &h->cf, &h->thr, &h->rng, &h->nhits, &h->sx_slot, &h->sx_counts, &h->sx_cursor, &h->sx_raw,
@@ -329,7 +335,7 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
         if (persist_max) {
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof(attr));
-            attr.accessPolicyWindow.base_ptr = const_cast<void*>(h->response);
+            attr.accessPolicyWindow.base_ptr = h->response_split.p ? h->response_split.p : const_cast<void*>(h->response);
             attr.accessPolicyWindow.num_bytes = lut_bytes;
             attr.accessPolicyWindow.hitRatio = lut_bytes <= persist_max ? 1.0f : (float)((double)persist_max / (double)lut_bytes);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -347,8 +353,8 @@ static int chain_enqueue(lsb_chain* h, void* tracks_dev, int64_t S, int32_t quen
             long long wsb = lsb_tracks_current_mc_workspace_bytes(S, (int32_t)P, (long long)bound_d);
             if ((size_t)wsb > h->mc_ws.cap) { if ((rc = h->mc_ws.need((size_t)wsb))) return rc; }
             if ((rc = mc_run_nosync(c, L, tracks_dev, S, (const int32_t*)h->neigh.p, (int32_t)P, (float*)h->signals.p, (int32_t)T,
-                                    h->response, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, S, h->mc_ws.p,
-                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, (int2*)h->sig_ranges.p, &d_s->mc_nfma, &d_s->mc_npairs, st))) return rc;
+                                    h->response, h->response_split.p, h->Rx, h->Ry, h->Rt, h->f64, (uint64_t*)h->rng.p, S, h->mc_ws.p,
+                                    (int64_t)h->mc_ws.cap, &d_s->mc_total, &d_s->mc_overflow, (int2*)h->sig_ranges.p, &d_s->mc_nfma, &d_s->mc_npairs, d_s->mc_diag, st))) return rc;
         } else {
             LSB_CUDA(cudaMemsetAsync(h->signals.p, 0, (size_t)S * P * T * 4, st)); LSB_MARK("memset_signals", st);
             k_ranges_full<<<lsb_blocks(S * P, 256), 256, 0, st>>>((int2*)h->sig_ranges.p, S * P, (int)T);
@@ -472,6 +478,7 @@ static void chain_finish(lsb_chain* h, lsb_chain_result* out, bool with_timing) 
         if (out->n_samples < 0) out->n_samples = h->hs_pinned->mc_total;
         out->n_fma = (int64_t)h->hs_pinned->mc_nfma;
         out->n_pairs = (int64_t)h->hs_pinned->mc_npairs;
+        out->n_groups = (int64_t)h->hs_pinned->mc_diag[0]; out->n_edge = (int64_t)h->hs_pinned->mc_diag[1]; out->n_irregular = (int64_t)h->hs_pinned->mc_diag[2];
     }
     if (h->timing && with_timing && out->unique_pix)
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) out->stage_ms[i] = ms; }
@@ -515,7 +522,9 @@ LSB_EXPORT int lsb_chain_wait(lsb_chain* h, lsb_chain_result* out) {
     chain_finish(h, &h->pending, false);
     if (h->pending.unique_pix) {
         // timeline of this batch in ms since the library's reference event: front begin/end, MC begin/end, FEE begin, done
+        // (the markers are only recorded when the MC stage ran on its own stream)
         for (int i = 0; i < 6; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, lsb_reference_event(), h->tl[i]) == cudaSuccess) h->pending.stage_ms[i] = ms; }
+        (void)cudaGetLastError();
     }
     *out = h->pending;
     h->pending_valid = 0;

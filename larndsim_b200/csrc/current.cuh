@@ -60,9 +60,14 @@ struct McParams {
     long long rng_stride;     // ntrk of detsim.py:324
     int P, T, Rx, Ry, Rt;
     int stride;               // TIME_SAMPLING / RESPONSE_SAMPLING if integral, else 0
+    int split, split_len;     // split == 2: the accumulate kernel reads a PHASE-SPLIT copy of the table (every row stored as
+                              // [even samples | odd samples], split_len = ceil(Rt / 2) = start of the odd half), which turns the
+                              // stride-2 gather LUT[row + 2 tick + shift] into the unit-stride gather
+                              // split[row + (shift & 1) * split_len + (shift >> 1) + tick] of the grouped path
     // sync-free operation (fused chain): the sample total stays on the device; every kernel after the scan
     // returns at once if it exceeds the capacity the caller provisioned (and *overflow is raised)
     const long long* total_dev; long long cap; int* overflow;
+    unsigned long long* diag;   // optional device counters {group records, edge (sample, tick) pairs, irregular samples}
     unsigned long long* npairs; // device counter of (segment, pixel) pairs that hold a pixel id (S * P-bar of SURVEY 8d), or null
     unsigned long long* nfma; // device counter of (sample, tick) pairs that pass every test of detsim.py:299,333,341-344 (N_fma of SURVEY 8d), or null
     int2* ranges;             // fused chain: rows of `signals` are stored sparsely -- only the ticks [lo, hi] covered by the pair's
@@ -379,11 +384,18 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
                     if (p.stride > 0) {
                         long long klo = resp_k(tick_time(g.t_start, lo), t0), khi = resp_k(tick_time(g.t_start, hi), t0);
                         long long sh = klo - (long long)p.stride * lo;
-                        if (khi == (long long)p.stride * hi + sh) shift = (int)sh;
+                        long long last = khi;                                   // table index (within the row) read at tick hi
+                        if (khi == (long long)p.stride * hi + sh) {
+                            if (p.split == 2) {                                  // phase-split table: unit stride from here on
+                                sh = (sh & 1) * (long long)p.split_len + (sh >> 1);
+                                last = sh + hi;
+                            }
+                            shift = (int)sh;
+                        }
                         // the grouped accumulate path reads the table in aligned 4-word blocks: a sample that reaches
                         // the last complete block of the table (or the partial one after it) takes the exact path
                         const long long L4 = (((long long)p.Rx * p.Ry * p.Rt) & ~(long long)(ACC_GW - 1)) - ACC_GW;
-                        if ((long long)s.rowoff + khi >= L4) shift = SHIFT_IRREGULAR;
+                        if ((long long)s.rowoff + last >= L4) shift = SHIFT_IRREGULAR;
                     }
                     r.t0 = t0; r.rowoff = s.rowoff; r.shift = shift; r.lo = lo; r.hi = hi;
                     keep = true;
@@ -574,7 +586,16 @@ __global__ void __launch_bounds__(32 * SORT_WARPS, SORT_MINB) k_mc_sort(McParams
             else ng += warp_sort_group<16>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
         }
     }
-    if (lane == 0) gp->n_groups = ng;
+    if (lane == 0) {
+        gp->n_groups = ng;
+        if (p.diag) {
+            atomicAdd(p.diag, (unsigned long long)ng);
+            const int interior = gp->int_lo <= gp->int_hi && n_reg > 0 ? gp->int_hi - gp->int_lo + 1 : 0;
+            const int uni = gp->uni_hi >= gp->uni_lo ? gp->uni_hi - gp->uni_lo + 1 : 0;
+            atomicAdd(p.diag + 1, (unsigned long long)(uni - interior) * (unsigned long long)n_live);
+            atomicAdd(p.diag + 2, (unsigned long long)gp->n_irregular);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -796,7 +817,10 @@ template <typename TL, int STRIDE, bool FAST>
 __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
                                                            const SampleRec* __restrict__ samples,
                                                            const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
-                                                           const TL* __restrict__ lut, float* __restrict__ signals) {
+                                                           const TL* __restrict__ lut, float* __restrict__ signals,
+                                                           const TL* __restrict__ lut_exact) {
+    // lut: the table the affine samples index with `rowoff + shift + STRIDE * tick` (the phase-split copy when p.split == 2);
+    // lut_exact: the table as the caller passed it, read by the exact per-tick path of the irregular samples
     MC_GUARD(p);
     long long pr = blockIdx.x;
     const PairRec* gp = pairs + pr;
@@ -1003,7 +1027,7 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
                     if (tick < 0) continue;
                     if (!(r.t0 < tick && tick < r.t0 + W)) continue;
                     long long k = __double2ll_rn((tick - r.t0) / d_c.response_sampling);
-                    if (0 <= k && k < p.Rt) { sum += (double)lut[(long long)r.rowoff + k]; any = true; }
+                    if (0 <= k && k < p.Rt) { sum += (double)lut_exact[(long long)r.rowoff + k]; any = true; }
                 }
             }
             if (active && any) out[it] = __double2float_rn((double)out[it] + charge * sum);
@@ -1102,33 +1126,58 @@ LSB_EXPORT int32_t lsb_mc_get_grouped(void) {
 }
 
 template <typename TL>
-static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut, float* signals, cudaStream_t st) {
+static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut, const TL* lut_split, float* signals, cudaStream_t st) {
     unsigned grid = (unsigned)(p.S * p.P);
-    if (p.stride == 1) {
+    if (p.stride == 1 || p.split == 2) {
         if constexpr (sizeof(TL) == 4) {
-            if (lsb_mc_get_grouped() && ((uintptr_t)lut & (4 * ACC_GW - 1)) == 0) {
+            const TL* table = p.split == 2 ? lut_split : lut;
+            if (lsb_mc_get_grouped() && ((uintptr_t)table & (4 * ACC_GW - 1)) == 0) {
                 // grouped path: equal / adjacent offsets must be neighbours
                 // group records reuse the uniforms buffer (dead after k_mc_sampler; 24 bytes per sample >= one 16-byte record)
                 GroupRecT* groups = reinterpret_cast<GroupRecT*>(w.uu);
                 k_mc_sort<<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                 LSB_LAUNCH_CHECK("k_mc_sort");
-                k_mc_accumulate<TL, 1, true><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, lut, signals);
+                k_mc_accumulate<TL, 1, true><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
+                LSB_LAUNCH_CHECK("k_mc_accumulate");
+                return 0;
+            }
+            if (p.split == 2) {
+                k_mc_accumulate<TL, 1, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, table, signals, lut);
                 LSB_LAUNCH_CHECK("k_mc_accumulate");
                 return 0;
             }
         }
-        k_mc_accumulate<TL, 1, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals);
-    } else if (p.stride == 2) k_mc_accumulate<TL, 2, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals);
-    else k_mc_accumulate<TL, 0, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals);
+        k_mc_accumulate<TL, 1, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
+    } else if (p.stride == 2) k_mc_accumulate<TL, 2, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
+    else k_mc_accumulate<TL, 0, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
     LSB_LAUNCH_CHECK("k_mc_accumulate");
     return 0;
+}
+
+// phase-split copy of a float table sampled at half the tick length (RESPONSE_SAMPLING = TIME_SAMPLING / 2, e.g. ndlar-module.yaml):
+// every row [Rt] becomes [even samples (ceil(Rt/2)) | odd samples (floor(Rt/2))]
+__global__ void k_lut_phase_split(const float* __restrict__ src, float* __restrict__ dst, long long rows, int Rt) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= rows * Rt) return;
+    const long long row = i / Rt; const int k = (int)(i - row * Rt);
+    const int half = (Rt + 1) >> 1;
+    dst[row * Rt + (k & 1) * half + (k >> 1)] = src[i];
+}
+static int mc_build_split(const void* response, int Rx, int Ry, int Rt, float* dst, cudaStream_t st) {
+    const long long rows = (long long)Rx * Ry;
+    k_lut_phase_split<<<lsb_blocks(rows * Rt, 256), 256, 0, st>>>((const float*)response, dst, rows, Rt);
+    LSB_LAUNCH_CHECK("k_lut_phase_split");
+    return 0;
+}
+static inline bool mc_wants_split(const lsb_consts* c, int f64) {
+    return !f64 && c->time_sampling / c->response_sampling == 2.0 && lsb_mc_get_grouped();
 }
 
 // statistics of the last call (roofline accounting)
 static long long g_mc_last_samples = 0;
 
 static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixels, float* signals, const void* response,
-                        int f64, unsigned long long* rng, int mode, McParams p, void* ws, long long ws_bytes,
+                        const void* response_split, int f64, unsigned long long* rng, int mode, McParams p, void* ws, long long ws_bytes,
                         cudaStream_t st, int depth) {
     McWs w;
     long long npair = p.S * p.P;
@@ -1155,9 +1204,9 @@ static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixe
             if (depth > 40) return lsb_fail_arg("tracks_current_mc: workspace split too deep");
             McParams a = p, b = p;
             a.S = p.S / 2; b.S = p.S - a.S; b.seg0 = p.seg0 + a.S;
-            rc = mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, a, ws, ws_bytes, st, depth + 1);
+            rc = mc_run_range(L, tracks, pixels, signals, response, response_split, f64, rng, mode, a, ws, ws_bytes, st, depth + 1);
             if (rc) return rc;
-            return mc_run_range(L, tracks, pixels, signals, response, f64, rng, mode, b, ws, ws_bytes, st, depth + 1);
+            return mc_run_range(L, tracks, pixels, signals, response, response_split, f64, rng, mode, b, ws, ws_bytes, st, depth + 1);
         }
         g_mc_last_samples += total;
         if (total == 0) return 0;
@@ -1175,8 +1224,8 @@ static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixe
     LSB_LAUNCH_CHECK("k_mc_uniforms");
     k_mc_sampler<<<lsb_blocks(npair, SMP_WARPS), 32 * SMP_WARPS, 0, st>>>(p, w.pairs, w.uu, w.samples, w.offs32);
     LSB_LAUNCH_CHECK("k_mc_sampler");
-    if (f64) return mc_launch_accumulate<double>(p, w, (const double*)response, signals, st);
-    return mc_launch_accumulate<float>(p, w, (const float*)response, signals, st);
+    if (f64) return mc_launch_accumulate<double>(p, w, (const double*)response, nullptr, signals, st);
+    return mc_launch_accumulate<float>(p, w, (const float*)response, (const float*)response_split, signals, st);
 }
 
 LSB_EXPORT int64_t lsb_tracks_current_mc_last_samples(void) { return g_mc_last_samples; }
@@ -1210,8 +1259,16 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
     g_mc_last_samples = 0;
-    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.ranges = nullptr; p.nfma = nullptr; p.npairs = nullptr;
-    return mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states,
+    p.total_dev = nullptr; p.cap = 0; p.overflow = nullptr; p.ranges = nullptr; p.nfma = nullptr; p.npairs = nullptr; p.diag = nullptr;
+    p.split = 0; p.split_len = 0;
+    TmpPool pool(st);
+    float* split = nullptr;
+    if (rng_mode == 0 && mc_wants_split(c, response_f64)) {          // 31.6 MB re-laid out per call (~20 us); the chain keeps its copy
+        LSB_CUDA(pool.get(&split, (long long)Rx * Ry * Rt));
+        if ((rc = mc_build_split(response, Rx, Ry, Rt, split, st))) return rc;
+        p.split = 2; p.split_len = (Rt + 1) >> 1;
+    }
+    return mc_run_range(make_layout(L), tracks, pixels, signals, response, split, response_f64, (unsigned long long*)rng_states,
                         rng_mode, p, workspace, workspace_bytes, st, 0);
 }
 
@@ -1220,10 +1277,10 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
 // is raised -- and nothing is written -- if the bound was wrong.  Cloud mode only.  `signals` is stored sparsely: row e
 // holds data in ticks ranges[e].x .. ranges[e].y only (see McParams::ranges); the caller does not pre-fill it.
 static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S, const int32_t* pixels,
-                         int32_t P, float* signals, int32_t T, const void* response, int32_t Rx, int32_t Ry, int32_t Rt,
+                         int32_t P, float* signals, int32_t T, const void* response, const void* response_split, int32_t Rx, int32_t Ry, int32_t Rt,
                          int32_t response_f64, uint64_t* rng_states, int64_t rng_stride, void* workspace,
                          int64_t workspace_bytes, long long* total_out, int* overflow, int2* ranges, unsigned long long* nfma,
-                         unsigned long long* npairs, cudaStream_t st) {
+                         unsigned long long* npairs, unsigned long long* diag, cudaStream_t st) {
     if (S == 0 || P == 0 || T == 0) return 0;
     if (require_current_fields(L, true)) return -1;
     int rc = lsb_upload_consts(c, st); if (rc) return rc;
@@ -1231,8 +1288,9 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
     p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
     double ratio = c->time_sampling / c->response_sampling;
     p.stride = (ratio == 1.0) ? 1 : (ratio == 2.0 ? 2 : 0);
-    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.ranges = ranges; p.nfma = nfma; p.npairs = npairs;
-    rc = mc_run_range(make_layout(L), tracks, pixels, signals, response, response_f64, (unsigned long long*)rng_states, 0, p,
+    p.total_dev = nullptr; p.cap = 0; p.overflow = overflow; p.ranges = ranges; p.nfma = nfma; p.npairs = npairs; p.diag = diag;
+    p.split = response_split ? 2 : 0; p.split_len = (Rt + 1) >> 1;
+    rc = mc_run_range(make_layout(L), tracks, pixels, signals, response, response_split, response_f64, (unsigned long long*)rng_states, 0, p,
                       workspace, workspace_bytes, st, 0);
     if (rc) return rc;
     McWs w;

@@ -68,15 +68,17 @@ class SpillOutput:
 
 
 class SpillRunner:
-    def __init__(self, track_dtype, response, depth=3, tpc_batch_size=None, event_separator=None, group=None, provider=None):
+    def __init__(self, track_dtype, response, depth=3, tpc_batch_size=None, event_separator=None, group=None, provider=None,
+                 single_rank=False):
+        """``single_rank=True``: ignore the process group and simulate every unit here (e.g. to check a distributed run)."""
         self._prov = provider or _consts.provider()
         p = self._prov
         self.dtype = np.dtype(track_dtype)
         self.sep = event_separator or getattr(p.sim, "EVENT_SEPARATOR", "event_id")
         self.tpc_batch_size = int(tpc_batch_size or getattr(p.sim, "EVENT_BATCH_SIZE", 2))
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() and not single_rank else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() and not single_rank else 0
         self._c = _consts.snapshot(p)
         self._L = _abi.track_layout(self.dtype)
         self._resp = _l.dev(response, name="response")

@@ -249,6 +249,41 @@ def oracle_back(orc, front, signals, states, n_events=1):
     return dict(pim=pim, tpm=tpm, ps=ps, pts=pts, overflow=of, adc=adc, ticks=ticks, cf=cf, digit=orc.digitize(adc))
 
 
+def oracle_back_chunked(orc, front, signals, states, n_events=1, chunk=2048):
+    """`oracle_back` with bounded memory: the reference's dense pixels_tracks_signals is [U, Tt, K] float64 (0.8 MB per pixel for
+    module0, 1.3 MB for ND-LAr), so the pixels are processed `chunk` at a time -- pixels are independent in sum_pixel_signals and
+    get_adc_values (RNG state index = pixel, fee.py:557), the results are identical to one dense call."""
+    c = orc.c
+    K, A, Tt = c.max_tracks_per_pixel, c.max_adc_values, c.n_time_ticks
+    uniq = front["uniq"]
+    U = len(uniq)
+    pim = orc.pixel_index_map(front["neigh"], uniq)
+    tpm = orc.track_pixel_map2(uniq, front["neigh"], front["nrad"], int(front["nrad"].max()) + 1, K)
+    time_ticks = np.linspace(0, n_events * c.time_interval[1], Tt + 1)
+    ps = np.zeros((U, Tt)); of = np.zeros(U)
+    adc = np.zeros((U, A)); ticks = np.zeros((U, A)); cf = np.zeros((U, A, K))
+    for u0 in range(0, U, chunk):
+        u1 = min(U, u0 + chunk)
+        sel = (pim >= u0) & (pim < u1)
+        pim_c = np.where(sel, pim - u0, -1)
+        ps_c, pts_c, of_c = orc.sum_pixel_signals(signals, front["starts"], pim_c, np.ascontiguousarray(tpm[u0:u1]), Tt)
+        thr = np.full(u1 - u0, c.discrimination_threshold * c.unit_e)
+        st_c = np.ascontiguousarray(states[u0:u1])
+        adc_c, ticks_c, cf_c = orc.get_adc_values(ps_c, pts_c, time_ticks, A, 0.0, st_c, thr)
+        states[u0:u1] = st_c
+        ps[u0:u1], of[u0:u1], adc[u0:u1], ticks[u0:u1], cf[u0:u1] = ps_c, of_c, adc_c, ticks_c, cf_c
+        del pts_c
+    return dict(pim=pim, tpm=tpm, ps=ps, overflow=of, adc=adc, ticks=ticks, cf=cf, digit=orc.digitize(adc))
+
+
+def rel_err_rows(a, b, rows=256):
+    """`rel_err` over the leading axis in slabs (bounded temporaries for GB-sized waveform arrays)"""
+    worst = 0.0
+    for i in range(0, a.shape[0], rows):
+        worst = max(worst, rel_err(a[i:i + rows], b[i:i + rows]))
+    return worst
+
+
 #: The oracle evaluates exp/log/erf with glibc, the CUDA kernels with libdevice (what the reference's
 #: Numba-CUDA build calls): both are <= 1 ulp but not bit-identical, exactly like the reference's own GPU
 #: and CUDA-simulator builds.  float64 record fields that go through a transcendental are therefore

@@ -132,3 +132,17 @@ def test_device_rng_states_match_host(cuda):
         ll.check(lib.lsb_rng_create_states(C.c_void_p(dev.data_ptr()), C.c_int64(n), C.c_uint64(seed), C.c_uint64(start), ll.stream()), "rng")
         got = dev.cpu().numpy().view(np.uint64).reshape(n, 2)
         assert np.array_equal(got[:, 0], host["s0"]) and np.array_equal(got[:, 1], host["s1"])
+
+
+def test_partitioned_spill_equals_single_rank(cuda):
+    """2 ranks over NCCL (needs 2 GPUs): rank 0 ends up with exactly the single-rank bytes, in file order"""
+    import os
+    import subprocess
+    import sys
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(root, "tests", "spill_dist_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "output == single-rank output: True" in r.stdout

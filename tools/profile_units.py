@@ -1,0 +1,36 @@
+"""One module0 batch (1e4 cosmics) and one ND-LAr (event, TPC pair) unit of the bench spill through the chain, for ncu captures
+and MC diagnostics (samples per group record, share of edge ticks).   python tools/profile_units.py [module0|ndlar|both]"""
+import os, sys, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from larndsim_b200 import consts as lc, synth, chain as lchain, _launch as ll
+
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+reps = int(os.environ.get("REPS", 2))
+out = {}
+if which in ("module0", "both"):
+    mod = lc.load_snapshot("module0")
+    tr = synth.cosmic_segments(10000, mod.detector, seed=12345)
+    ch = lchain.Chain(tr.dtype, synth.response_lut(mod.detector), stage_timing=True)
+    for _ in range(reps):
+        r = ch.run(ll.DeviceRecords(host=tr.copy()), rng_seed=1)
+    out["module0"] = dict(S=r.n_segments, P=r.max_neighbors, U=r.n_unique_pixels, T=r.n_ticks, n_samples=r.n_samples, n_fma=r.n_fma,
+                          n_pairs=r.n_pairs, n_groups=r.n_groups, n_edge=r.n_edge, n_irregular=r.n_irregular, stage_ms=r.stage_ms)
+    ch.close()
+if which in ("ndlar", "both"):
+    mod, tracks, resp = bench.make_spill()
+    sub = bench.cpu_sample(tracks, mod, 7000)
+    ch = lchain.Chain(sub.dtype, resp, stage_timing=True)
+    for _ in range(reps):
+        r = ch.run(ll.DeviceRecords(host=sub.copy()), rng_seed=1)
+    out["ndlar"] = dict(S=r.n_segments, P=r.max_neighbors, U=r.n_unique_pixels, T=r.n_ticks, n_samples=r.n_samples, n_fma=r.n_fma,
+                        n_pairs=r.n_pairs, n_groups=r.n_groups, n_edge=r.n_edge, n_irregular=r.n_irregular, stage_ms=r.stage_ms)
+    ch.close()
+for k, v in out.items():
+    v["samples_per_group"] = v["n_samples"] / max(v["n_groups"], 1)
+    v["edge_share_of_fma"] = v["n_edge"] / max(v["n_fma"], 1)
+    v["fma_per_segment"] = v["n_fma"] / v["S"]
+print(json.dumps(out, indent=1))
