@@ -193,6 +193,12 @@ int64_t lsb_tracks_current_mc_last_samples(void);
  * 0 = generic gather stream.  Same results to 1e-5; the default can also be set with LSB_MC_GROUPED=0/1. */
 void lsb_mc_set_grouped(int32_t on);
 int32_t lsb_mc_get_grouped(void);
+/* consecutive ticks a lane owns in the grouped path: 4 (default; 8-word windows, two LDG.128 per group and 128 ticks of a warp)
+ * or 8 (12-word windows, three LDG.128 per 256 ticks: fewer table words per tick but more registers -- measured slower on
+ * B200); also LSB_ACC_LANE_TICKS=4/8.  Tables sampled at half the tick
+ * length (RESPONSE_SAMPLING = TIME_SAMPLING / 2, ND-LAr) take the same path on a phase-split copy of the table. */
+void lsb_mc_set_lane_ticks(int32_t n);
+int32_t lsb_mc_get_lane_ticks(void);
 /* larndsim/detsim.py:351-453  tracks_current(signals, pixels, tracks, response) */
 int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
                        const int32_t* pixels, int32_t P, float* signals, int32_t T,

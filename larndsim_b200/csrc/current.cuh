@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
                         }
                         // the grouped accumulate path reads the table in aligned 4-word blocks: a sample that reaches
                         // the last complete block of the table (or the partial one after it) takes the exact path
-                        const long long L4 = (((long long)p.Rx * p.Ry * p.Rt) & ~(long long)(ACC_GW - 1)) - ACC_GW;
+                        const long long L4 = (((long long)p.Rx * p.Ry * p.Rt) & ~(long long)(ACC_GW - 1)) - 2 * ACC_GW;   // 12-word windows (8-tick lanes)
                         if ((long long)s.rowoff + last >= L4) shift = SHIFT_IRREGULAR;
                     }
                     r.t0 = t0; r.rowoff = s.rowoff; r.shift = shift; r.lo = lo; r.hi = hi;
@@ -755,6 +755,60 @@ __device__ __forceinline__ void acc_gather(const float4* __restrict__ lut4, int 
     }
 }
 
+// ---- lane = 8 consecutive ticks on the 4-word groups (FAST == 2) -----------------------------------------------------------
+// The window of a group grows from 8 to 12 table words per lane (three aligned LDG.128) but serves twice the ticks: 1.5 words
+// per tick instead of 2, and the per-group overhead (record, count unpacking, branches) is paid once per 256 ticks of a warp.
+__device__ __forceinline__ void acc_apply_t8(const int4& rec, const float4& a, const float4& b, const float4& c, float (&acc)[8]) {
+    const float w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    const float2 c01 = __half22float2(*reinterpret_cast<const __half2*>(&rec.y));
+    const float2 c23 = __half22float2(*reinterpret_cast<const __half2*>(&rec.z));
+    if (c01.x != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(c01.x, w[j], acc[j]);
+    }
+    if (c01.y != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(c01.y, w[j + 1], acc[j]);
+    }
+    if (c23.x != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(c23.x, w[j + 2], acc[j]);
+    }
+    if (c23.y != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = __fmaf_rn(c23.y, w[j + 3], acc[j]);
+    }
+}
+__device__ __forceinline__ void acc_gather_t8(const float4* __restrict__ lut4, int n4m3, const GroupRec* __restrict__ grp, int ng, int Qb,
+                                              double (&dacc)[8]) {
+    // record g+1 and its window are in flight while group g is applied; float32 partial sums (<= 8 terms) are folded into
+    // float64 every second group, as in the 4-tick path
+    const int4* recs = reinterpret_cast<const int4*>(grp);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    int4 rec = __ldg(recs);
+    const float4* w = lut4 + min(Qb + rec.x, n4m3);
+    float4 a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+    for (int g = 0; g < ng; g++) {
+        int4 nrec = rec;
+        float4 na = a, nb = b, nc = c;
+        if (g + 1 < ng) {
+            nrec = __ldg(recs + g + 1);
+            const float4* w1 = lut4 + min(Qb + nrec.x, n4m3);
+            na = __ldg(w1); nb = __ldg(w1 + 1); nc = __ldg(w1 + 2);
+        }
+        acc_apply_t8(rec, a, b, c, acc);
+        if (g & 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { dacc[j] += (double)acc[j]; acc[j] = 0.f; }
+        }
+        rec = nrec; a = na; b = nb; c = nc;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) dacc[j] += (double)acc[j];
+}
+
 // ---- 8-word groups: lane = 8 consecutive ticks, 16-word window fetched with two 256-bit loads ------------------------
 struct __align__(32) float8 { float v[8]; };
 __device__ __forceinline__ float8 ldg256(const float* p) {
@@ -813,16 +867,14 @@ __device__ __forceinline__ void acc_gather8(const float* __restrict__ lut, int n
     for (int j = 0; j < 8; j++) dacc[j] += (double)acc[j];
 }
 
-template <typename TL, int STRIDE, bool FAST>
-__global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
-                                                           const SampleRec* __restrict__ samples,
-                                                           const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
-                                                           const TL* __restrict__ lut, float* __restrict__ signals,
-                                                           const TL* __restrict__ lut_exact) {
+template <typename TL, int STRIDE, int FAST>
+__device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long pr, const PairRec* __restrict__ pairs,
+                                                   const SampleRec* __restrict__ samples,
+                                                   const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
+                                                   const TL* __restrict__ lut, float* __restrict__ signals,
+                                                   const TL* __restrict__ lut_exact) {
     // lut: the table the affine samples index with `rowoff + shift + STRIDE * tick` (the phase-split copy when p.split == 2);
     // lut_exact: the table as the caller passed it, read by the exact per-tick path of the irregular samples
-    MC_GUARD(p);
-    long long pr = blockIdx.x;
     const PairRec* gp = pairs + pr;
     if (!gp->valid) {
         if (p.ranges && threadIdx.x == 0) p.ranges[(p.seg0 + pr / p.P) * p.P + (pr % p.P)] = make_int2(0, -1);
@@ -848,7 +900,7 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
 
     // ---- interior ticks, grouped path ------------------------------------------------
     // Tick blocks are dealt round-robin to the warps; warps run independently (no barrier).
-    if constexpr (FAST) {
+    if constexpr (FAST == 1) {
         constexpr int NW = ACC_TPB / 32;
         const int lane = tid & 31, warp = tid >> 5;
         const int ng = gp->n_groups;
@@ -894,6 +946,32 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
                 }
         }
 #endif
+    }
+    if constexpr (FAST == 2) {
+        // lane = 8 consecutive ticks, warp = 256 ticks, 4-word groups
+        constexpr int NW = ACC_TPB / 32;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int ng = gp->n_groups;
+        const float4* lut4 = reinterpret_cast<const float4*>(lut);
+        const int n4m3 = (int)(((long long)p.Rx * p.Ry * p.Rt) >> 2) - 3;
+        const GroupRec* grp = reinterpret_cast<const GroupRec*>(groups) + soff;
+        for (int tb = int_lo + 256 * warp; tb <= int_hi; tb += 256 * NW) {
+            double dacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) dacc[j] = 0.0;
+            acc_gather_t8(lut4, n4m3, grp, ng, ((tb - int_lo) >> 2) + 2 * lane, dacc);
+            const int it0 = tb + 8 * lane;
+            if (it0 + 7 <= int_hi && ((reinterpret_cast<uintptr_t>(out + it0) & 15) == 0)) {
+                *reinterpret_cast<float4*>(out + it0) = make_float4(__double2float_rn(charge * dacc[0]), __double2float_rn(charge * dacc[1]),
+                                                                    __double2float_rn(charge * dacc[2]), __double2float_rn(charge * dacc[3]));
+                *reinterpret_cast<float4*>(out + it0 + 4) = make_float4(__double2float_rn(charge * dacc[4]), __double2float_rn(charge * dacc[5]),
+                                                                        __double2float_rn(charge * dacc[6]), __double2float_rn(charge * dacc[7]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (it0 + j <= int_hi) out[it0 + j] = __double2float_rn(charge * dacc[j]);
+            }
+        }
     }
     // ---- interior ticks, generic path: unconditional gather stream ---------------------
     if (STRIDE > 0 && !FAST) {
@@ -1035,6 +1113,18 @@ __global__ void __launch_bounds__(ACC_TPB, FAST ? ACC_MINB : 8) k_mc_accumulate(
     }
 }
 
+// one CTA per (segment, pixel) pair.  (A persistent grid fetching pairs from a device counter was measured on B200: 3.6 % slower
+// alone -- an atomic and two barriers per pair -- and no better with three batches in flight, profiles/r02_spill_pipeline.md.)
+template <typename TL, int STRIDE, int FAST>
+__global__ void __launch_bounds__(ACC_TPB, FAST == 1 ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
+                                                           const SampleRec* __restrict__ samples,
+                                                           const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
+                                                           const TL* __restrict__ lut, float* __restrict__ signals,
+                                                           const TL* __restrict__ lut_exact) {
+    MC_GUARD(p);
+    mc_accumulate_pair<TL, STRIDE, FAST>(p, (long long)blockIdx.x, pairs, samples, offs32, groups, lut, signals, lut_exact);
+}
+
 // replay mode: literal reference order, one thread per pair (detsim.py:324-348)
 template <typename TL>
 __global__ void k_mc_replay(McParams p, const PairRec* __restrict__ pairs, const TL* __restrict__ lut,
@@ -1125,6 +1215,16 @@ LSB_EXPORT int32_t lsb_mc_get_grouped(void) {
     return g_mc_grouped;
 }
 
+// ticks per lane of the grouped interior path: 4 (8-word windows; default) or 8 (12-word windows: 1.5 instead of 2 table words per
+// tick, but 64 registers / 32 warps per SM -- measured slower on B200: 7.39 against 6.26 ms per module0 batch, 12.9 against 11.0 ms per
+// ND-LAr unit, profiles/r02_spill_pipeline.md); LSB_ACC_LANE_TICKS / lsb_mc_set_lane_ticks
+static int g_mc_lane_ticks = -1;
+LSB_EXPORT void lsb_mc_set_lane_ticks(int32_t n) { g_mc_lane_ticks = n == 8 ? 8 : 4; }
+LSB_EXPORT int32_t lsb_mc_get_lane_ticks(void) {
+    if (g_mc_lane_ticks < 0) { const char* e = getenv("LSB_ACC_LANE_TICKS"); g_mc_lane_ticks = (e && atoi(e) == 8) ? 8 : 4; }
+    return g_mc_lane_ticks;
+}
+
 template <typename TL>
 static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut, const TL* lut_split, float* signals, cudaStream_t st) {
     unsigned grid = (unsigned)(p.S * p.P);
@@ -1137,19 +1237,20 @@ static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut,
                 GroupRecT* groups = reinterpret_cast<GroupRecT*>(w.uu);
                 k_mc_sort<<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                 LSB_LAUNCH_CHECK("k_mc_sort");
-                k_mc_accumulate<TL, 1, true><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
+                if (lsb_mc_get_lane_ticks() == 8) k_mc_accumulate<TL, 1, 2><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
+                else k_mc_accumulate<TL, 1, 1><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
                 LSB_LAUNCH_CHECK("k_mc_accumulate");
                 return 0;
             }
             if (p.split == 2) {
-                k_mc_accumulate<TL, 1, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, table, signals, lut);
+                k_mc_accumulate<TL, 1, 0><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, table, signals, lut);
                 LSB_LAUNCH_CHECK("k_mc_accumulate");
                 return 0;
             }
         }
-        k_mc_accumulate<TL, 1, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
-    } else if (p.stride == 2) k_mc_accumulate<TL, 2, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
-    else k_mc_accumulate<TL, 0, false><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
+        k_mc_accumulate<TL, 1, 0><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
+    } else if (p.stride == 2) k_mc_accumulate<TL, 2, 0><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
+    else k_mc_accumulate<TL, 0, 0><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, nullptr, lut, signals, lut);
     LSB_LAUNCH_CHECK("k_mc_accumulate");
     return 0;
 }

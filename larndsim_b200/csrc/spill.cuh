@@ -249,6 +249,8 @@ LSB_EXPORT int lsb_spill_run(lsb_spill* sp, const void* tracks_dev, const int64_
     cudaEvent_t prev_export = nullptr;
     long long off = 0;
     lsb_chain_result done;
+    FILE* timeline = getenv("LSB_SPILL_TIMELINE") ? fopen(getenv("LSB_SPILL_TIMELINE"), "a") : nullptr;     // diagnostics (tools/timeline.py)
+    if (timeline) fprintf(timeline, "# run\n");
     auto collect = [&](int k) -> int {
         lsb_chain* h = sp->ch[k];
         if (!h->pending_valid) return 0;
@@ -257,6 +259,9 @@ LSB_EXPORT int lsb_spill_run(lsb_spill* sp, const void* tracks_dev, const int64_
         out->n_hits += done.n_hits; out->n_unique_pixels += done.n_unique_pixels;
         if (done.n_samples > 0) out->n_samples += done.n_samples;
         out->n_fma += done.n_fma;
+        if (timeline && done.unique_pix)        // ms since the library's reference event: front begin/end, MC begin/end, FEE begin, done
+            fprintf(timeline, "%lld %lld %.4f %.4f %.4f %.4f %.4f %.4f\n", (long long)done.n_segments, (long long)done.n_unique_pixels, done.stage_ms[0],
+                    done.stage_ms[1], done.stage_ms[2], done.stage_ms[3], done.stage_ms[4], done.stage_ms[5]);
         out->pair_ticks += done.n_pairs * done.n_ticks; out->pixel_ticks += done.n_unique_pixels * (long long)sp->c.n_time_ticks;
         return 0;
     };
@@ -276,7 +281,8 @@ LSB_EXPORT int lsb_spill_run(lsb_spill* sp, const void* tracks_dev, const int64_
         h->pending_valid = 1;
         off += n;
     }
-    for (int k = 0; k < sp->depth; k++) if ((rc = collect(k))) return rc;
+    for (int k = 0; k < sp->depth; k++) if ((rc = collect(k))) { if (timeline) fclose(timeline); return rc; }
+    if (timeline) fclose(timeline);
     // every handle has drained (lsb_chain_wait synchronises on its last event): the table is final
     LSB_CUDA(cudaMemcpyAsync(sp->host_table, sp->unit_table.p, (size_t)n_units * 16, cudaMemcpyDeviceToHost, st));
     LSB_CUDA(cudaMemcpyAsync(sp->host_table + 2 * n_units, sp->cursor.p, 16, cudaMemcpyDeviceToHost, st));
