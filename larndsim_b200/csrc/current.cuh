@@ -1441,11 +1441,20 @@ __device__ __forceinline__ void rho_prepare(TcPair& g) {
     g.r_two_a_Dr = 2 * a * Dr;
     g.r_four_a = 4 * a;
 }
+// erf(hi) - erf(lo), lo <= hi (detsim.py:149-151 writes -erf(lo) + erf(hi)): taken between the complementary functions when both
+// arguments lie on the same side of zero, where the reference's form cancels (grid points beyond the ends of the segment) and a
+// one-ulp difference between two erf implementations would change the waveform at the 1e-5..1 level; identical to rounding wherever
+// the reference's form is well-conditioned.  The oracle (oracle/larnd_oracle.c erf_diff) does the same.
+__device__ __forceinline__ double erf_diff(double lo, double hi) {
+    if (lo >= 0.0) return erfc(lo) - erfc(hi);
+    if (hi <= 0.0) return erfc(-hi) - erfc(-lo);
+    return erf(hi) - erf(lo);
+}
 __device__ __forceinline__ double rho_fast(double x, double y, double z, const TcPair& g) {
     const double dx = x - g.start[0], dy = y - g.start[1], dz = z - g.start[2];
     double b = -(dx / g.r_d0 * g.r_ux + dy / g.r_d1 * g.r_uy + dz / g.r_d2 * g.r_uz);
     double delta = dx * dx / g.r_e0 + dy * dy / g.r_e1 + dz * dz / g.r_e2;
-    double integral = sqrt(M_PI) * (-erf(b / g.r_sqrt_a_2) + erf((b + g.r_two_a_Dr) / g.r_sqrt_a_2)) / g.r_sqrt_a_2;
+    double integral = sqrt(M_PI) * erf_diff(b / g.r_sqrt_a_2, (b + g.r_two_a_Dr) / g.r_sqrt_a_2) / g.r_sqrt_a_2;
     double expo = 0;
     if (g.r_factor != 0 && integral != 0) expo = exp(b * b / g.r_four_a - delta + g.r_log_factor + log(integral));
     return expo;
@@ -1466,7 +1475,7 @@ __device__ double rho_dev(const double* pt, const TcPair& g) {
                  (z - start[2]) / R32(sig[2] * sig[2], s32) * uz);
     double delta = (x - start[0]) * (x - start[0]) / (2 * sig[0] * sig[0]) + (y - start[1]) * (y - start[1]) / (2 * sig[1] * sig[1]) +
                    (z - start[2]) * (z - start[2]) / (2 * sig[2] * sig[2]);
-    double integral = sqrt(M_PI) * (-erf(b / sqrt_a_2) + erf((b + 2 * a * Dr) / sqrt_a_2)) / sqrt_a_2;
+    double integral = sqrt(M_PI) * erf_diff(b / sqrt_a_2, (b + 2 * a * Dr) / sqrt_a_2) / sqrt_a_2;
     double expo = 0;
     if (factor != 0 && integral != 0) expo = exp(b * b / (4 * a) - delta + log(factor) + log(integral));
     return expo;

@@ -527,6 +527,18 @@ ORC_API int orc_count_mc_work(const lsb_consts* c, const lsb_track_layout* L, co
 /* ------------------------------------------------------------------------------------ */
 static inline double sgn(double x) { return x >= 0 ? 1.0 : -1.0; }     /* :455-466 */
 /* rho :120-159 with _b :114-118.  sigmas float32-typed when s32 (products of two float32 stay float32). */
+/* erf(hi) - erf(lo), lo <= hi, of rho (detsim.py:149-151).  The reference writes -erf(lo) + erf(hi): when both arguments
+ * lie on the same side of zero beyond ~4 (grid points past the ends of the segment) both terms are +-1 to within 1e-8 and
+ * the difference keeps few or no digits -- a one-ulp difference between two libm's erf then changes the result at the
+ * 1e-5..1 level (and the reference returns 0 when it cancels completely).  The same difference is taken here between the
+ * complementary functions on that side, which keeps full relative precision; wherever the reference's form is
+ * well-conditioned the two agree to rounding.  The CUDA kernel (csrc/current.cuh rho_fast / rho_dev) does the same. */
+static inline double erf_diff(double lo, double hi) {
+    if (lo >= 0.0) return erfc(lo) - erfc(hi);
+    if (hi <= 0.0) return erfc(-hi) - erfc(-lo);
+    return erf(hi) - erf(lo);
+}
+
 static double rho(const double* pt, double q, const double* start, const double* sig, const double* seg, int s32, int c32) {
     /* Numba typing: segment/start float32 (c32), sigmas float32 (s32), point float64; an int literal
      * times a float32 is float64 (2*sigma), float32*float32 stays float32, x**2 keeps the base type. */
@@ -545,7 +557,7 @@ static double rho(const double* pt, double q, const double* start, const double*
     double delta = (x - start[0]) * (x - start[0]) / (2 * sig[0] * sig[0]) +
                    (y - start[1]) * (y - start[1]) / (2 * sig[1] * sig[1]) +
                    (z - start[2]) * (z - start[2]) / (2 * sig[2] * sig[2]);
-    double integral = sqrt(M_PI) * (-erf(b / sqrt_a_2) + erf((b + 2 * a * Dr) / sqrt_a_2)) / sqrt_a_2;
+    double integral = sqrt(M_PI) * erf_diff(b / sqrt_a_2, (b + 2 * a * Dr) / sqrt_a_2) / sqrt_a_2;
     double expo = 0;
     if (factor != 0 && integral != 0)
         expo = exp(b * b / (4 * a) - delta + log(factor) + log(integral));

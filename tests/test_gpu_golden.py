@@ -104,7 +104,9 @@ def test_current_sum_fee_golden(cuda, label):
     ref_tc = g["tc:signals"]
     sig = np.zeros_like(ref_tc)
     detsim.tracks_current[(1, P_, T), (1, 1, 1)](sig, nb[:1], g["tracks"][:1], lut)
-    assert np.array_equal(sig != 0, ref_tc != 0) and h.rel_err_peak(sig, ref_tc) < 1e-4     # erf cancellation, see test_gpu_kernels
+    # against the reference's own output: 1e-5 relative wherever the reference's -erf(a) + erf(b) is well-conditioned (the kernel
+    # takes the difference through erfc beyond the segment ends, where the reference's form loses its digits: < 1e-6 of the peak)
+    assert np.array_equal(sig != 0, ref_tc != 0) and h.rel_err_peak(sig, ref_tc) < 1e-6
 
 
 @pytest.mark.parametrize("n_true", [0, 2])

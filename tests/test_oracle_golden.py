@@ -214,6 +214,6 @@ def test_light_chain(n_true):
 def test_abi_struct_sizes_match_header():
     """The ctypes mirror must agree with the C structs the oracle was compiled against."""
     lib = h.oracle_lib()
-    assert lib.orc_abi_version() == 1
+    assert lib.orc_abi_version() == 2
     c = lc.snapshot(lc.load_snapshot("module0"))
     assert c.n_tpc == 2 and c.n_pixels[0] == 140 and abs(c.tpc_borders[5] - (-0.15875)) < 1e-9
