@@ -199,6 +199,25 @@ __global__ void k_widen_idx(const int32_t* __restrict__ idx, long long n, long l
 
 static inline long long rs_tiles(long long n) { return (n + RS_TILE - 1) / RS_TILE; }
 
+// stable sort of (key, index) pairs by the low `bits` bits of the key; the sorted arrays end up in *keyA / *idxA (the pointers are
+// swapped per pass); scratch from `pool`
+static int rs_sort_pairs(uint32_t** keyA, uint32_t** keyB, int32_t** idxA, int32_t** idxB, long long n, int bits, TmpPool& pool, cudaStream_t st) {
+    const long long nt = rs_tiles(n), nh = 256 * nt;
+    uint32_t* hist; long long* base; long long* bs; long long* total;
+    LSB_CUDA(pool.get(&hist, nh)); LSB_CUDA(pool.get(&base, nh)); LSB_CUDA(pool.get(&bs, scan_num_blocks(nh) + 1)); LSB_CUDA(pool.get(&total, 1));
+    for (int shift = 0; shift < bits; shift += 8) {
+        k_rs_hist<<<(unsigned)nt, RS_TPB, 0, st>>>(*keyA, n, shift, nt, hist);
+        LSB_LAUNCH_CHECK("k_rs_hist");
+        int rc = exclusive_scan<uint32_t, long long>(hist, nh, base, bs, total, st);
+        if (rc) return rc;
+        k_rs_scatter<<<(unsigned)nt, RS_TPB, 0, st>>>(*keyA, *idxA, n, shift, nt, base, *keyB, *idxB);
+        LSB_LAUNCH_CHECK("k_rs_scatter");
+        uint32_t* tk = *keyA; *keyA = *keyB; *keyB = tk;
+        int32_t* ti = *idxA; *idxA = *idxB; *idxB = ti;
+    }
+    return 0;
+}
+
 LSB_EXPORT int64_t lsb_batch_units_ws_bytes(int64_t n) {
     const long long nt = rs_tiles(n), nh = 256 * nt;
     return (int64_t)(4 * align16((size_t)n * 4) + align16((size_t)nh * 4) + align16((size_t)nh * 8) +

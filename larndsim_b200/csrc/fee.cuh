@@ -16,6 +16,7 @@
 #pragma once
 #include "common.cuh"
 #include "pixelmap.cuh"
+#include "rng.cuh"
 
 #define FEE_MAX_TAPS 256
 
@@ -101,6 +102,29 @@ __global__ void k_fee_rng_normals(const float2* __restrict__ uu, float* __restri
     float a = sqrtf(__fmul_rn(-2.0f, logf(u.x)));              // == rng_normal_f32
     float b = cosf(__fmul_rn(6.283185307179586f, u.y));
     nrm[i] = __fmul_rn(a, b);
+}
+
+// The same normals and snapshots in ONE pass with (pixel, chunk) parallelism: thread (g, pixel) jumps the pixel's stream to draw
+// RNG_STEP_UNIT * g (rng.cuh: one GF(2) matrix product per set bit of g; the matrices are shared by the warp, g is warp-uniform),
+// records the snapshot, and turns its 64 uniform pairs into normals.  Pixels are the fast index, so stores are coalesced; the
+// 8-byte uniform pairs never reach HBM.  (k_fee_rng_uniforms walked each stream sequentially with one thread per pixel --
+// 15 000 threads on a 300 000-thread machine -- and k_fee_rng_normals re-read its 0.8 GB of output.)
+static_assert(RNG_STEP_UNIT == 2 * FEE_SNAP, "one chunk = FEE_SNAP normals");
+__global__ void __launch_bounds__(128) k_fee_rng_chunks(const RngStepTable* __restrict__ tab, const unsigned long long* __restrict__ rng_states,
+                                                        long long U, int n_chunks, float* __restrict__ nrm, ulonglong2* __restrict__ snaps) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= U * n_chunks) return;
+    const int g = (int)(idx / U);
+    const long long ip = idx - (long long)g * U;
+    unsigned long long s0 = rng_states[2 * ip], s1 = rng_states[2 * ip + 1];
+    for (int k = 0, bits = g; bits; k++, bits >>= 1)
+        if (bits & 1) rng_matvec_dev(reinterpret_cast<const ulonglong2*>(tab->col[k]), s0, s1);
+    snaps[(long long)g * U + ip] = make_ulonglong2(s0, s1);
+    Rng r; r.s0 = s0; r.s1 = s1;
+    float* out = nrm + (long long)g * FEE_SNAP * U + ip;
+#pragma unroll 4
+    for (int i = 0; i < FEE_SNAP; i++) out[(long long)i * U] = rng_normal_f32(r);
+    if (g == n_chunks - 1) snaps[(long long)n_chunks * U + ip] = make_ulonglong2(r.s0, r.s1);
 }
 
 struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2* snaps; int NMAX; };
@@ -623,17 +647,28 @@ static int fee_run(const lsb_consts* c, const double* pixels_signals, const doub
         const double pre_bytes = (double)U * ((double)nmax * 12.0 + (double)Tq * 8.0);
         FeePre pre; pre.q_pre = nullptr; pre.Tq = Tq; pre.nrm = nullptr; pre.snaps = nullptr; pre.NMAX = (int)nmax;
         if (pre_bytes < 12e9 && nmax < 2000000) {
-            double* q_pre; float2* uu; float* nrm; ulonglong2* snaps;
+            double* q_pre; float* nrm; ulonglong2* snaps;
             LSB_CUDA(tp.get(&q_pre, U * (long long)Tq));
-            LSB_CUDA(tp.get(&uu, U * nmax));
             LSB_CUDA(tp.get(&nrm, U * nmax));
             LSB_CUDA(tp.get(&snaps, U * (nmax / FEE_SNAP + 1)));
             k_fee_fir_pre<<<lsb_blocks(U * (long long)Tq, 256), 256, 0, st>>>(fp, pixels_signals, U, Tt, Tq, q_pre);
             LSB_LAUNCH_CHECK("k_fee_fir_pre");
-            k_fee_rng_uniforms<<<lsb_blocks(U, 64), 64, 0, st>>>((const unsigned long long*)rng_states, U, (int)nmax, uu, snaps);
-            LSB_LAUNCH_CHECK("k_fee_rng_uniforms");
-            k_fee_rng_normals<<<lsb_blocks(U * nmax, 256), 256, 0, st>>>(uu, nrm, U * nmax);
-            LSB_LAUNCH_CHECK("k_fee_rng_normals");
+            const int n_chunks = (int)(nmax / FEE_SNAP);
+            const RngStepTable* step_tab = (fp.reset_noise != 0.0 || fp.unc_noise != 0.0 || fp.disc_noise != 0.0) && n_chunks < (1 << RNG_STEP_LEVELS)
+                                               ? rng_step_table_dev() : nullptr;
+            static int chunked = -1;
+            if (chunked < 0) { const char* e = getenv("LSB_FEE_RNG_CHUNKED"); chunked = (e && e[0] == '0') ? 0 : 1; }
+            if (step_tab && chunked) {
+                k_fee_rng_chunks<<<lsb_blocks(U * (long long)n_chunks, 128), 128, 0, st>>>(step_tab, (const unsigned long long*)rng_states, U, n_chunks, nrm, snaps);
+                LSB_LAUNCH_CHECK("k_fee_rng_chunks");
+            } else {
+                float2* uu;
+                LSB_CUDA(tp.get(&uu, U * nmax));
+                k_fee_rng_uniforms<<<lsb_blocks(U, 64), 64, 0, st>>>((const unsigned long long*)rng_states, U, (int)nmax, uu, snaps);
+                LSB_LAUNCH_CHECK("k_fee_rng_uniforms");
+                k_fee_rng_normals<<<lsb_blocks(U * nmax, 256), 256, 0, st>>>(uu, nrm, U * nmax);
+                LSB_LAUNCH_CHECK("k_fee_rng_normals");
+            }
             pre.q_pre = q_pre; pre.nrm = nrm; pre.snaps = snaps;
             k_fee_trigger<true><<<lsb_blocks(U, FEE_TRIG_PIX), FEE_TRIG_TPB, 0, st>>>(fp, pre, pixels_signals, U, Tt, time_ticks, n_time_ticks, adc_list,
                                                                  adc_ticks_list, A, time_padding, (unsigned long long*)rng_states,

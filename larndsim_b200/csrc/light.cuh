@@ -11,6 +11,8 @@
 // (scintillation model / SiPM impulse) are evaluated once per call on the host in float64.
 #pragma once
 #include "common.cuh"
+#include "glue.cuh"
+#include "batching.cuh"
 
 // lightLUT.py:65-136, thread per (segment, channel)
 __global__ void k_light_incidence(Layout L, const char* __restrict__ tracks, long long S, const char* __restrict__ lut,
@@ -79,6 +81,55 @@ __global__ void k_light_gather_segs(Layout L, const char* __restrict__ segments,
 
 #define LT_TPB 128
 #define LT_CHUNK 128
+// one segment's contribution to one tick (light_sim.py:84-129), reference add order and roundings
+__device__ __forceinline__ void light_add_segment(const LightSeg& g, const char* __restrict__ lut, const lsb_lut_layout& LL,
+                                                  double start_tick_time, double end_tick_time, double prof_len, float& acc,
+                                                  long long* __restrict__ true_id, double* __restrict__ true_ph, long long tbase, int n_true) {
+    if (!(g.nph > 0.f)) return;
+    const double track_time = g.t0;
+    const double track_end_time = track_time + prof_len;
+    if (track_end_time < start_tick_time || track_time > end_tick_time) return;
+    const char* lrec = lut + g.lut_off;
+    if (d_c.enable_lut_smearing) {
+        // profile_time is non-decreasing in ip: only the bins around (tick start - t0) / 1 ns can pass the strict test below; the
+        // window is taken with a margin of two bins on either side and every bin in it is tested exactly, in ascending order
+        const double step = d_c.unit_ns / d_c.unit_mus;
+        const double first = floor((start_tick_time - track_time) / step) - 2.0;
+        const double last = ceil((end_tick_time - track_time) / step) + 2.0;
+        const int ip_lo = first > 0.0 ? (first < (double)LL.n_time_dist ? (int)first : LL.n_time_dist) : 0;
+        const int ip_hi = last < (double)(LL.n_time_dist - 1) ? (last >= 0.0 ? (int)last : -1) : LL.n_time_dist - 1;
+        for (int ip = ip_lo; ip <= ip_hi; ip++) {
+            double profile_time = track_time + (double)ip * d_c.unit_ns / d_c.unit_mus;
+            if (profile_time < end_tick_time && profile_time > start_tick_time) {
+                float tp = *(const float*)(lrec + LL.off_time_dist + 4 * ip);
+                double photons = (double)__fmul_rn(g.nph, tp) / d_c.light_tick_size;
+                acc = __double2float_rn((double)acc + photons);
+                if (photons > d_c.mc_truth_threshold) {
+                    for (int q = 0; q < n_true; q++) {
+                        long long* tid = true_id + tbase + q;
+                        if (*tid == -1 || *tid == g.track_id) { *tid = g.track_id; true_ph[tbase + q] += photons; break; }
+                    }
+                }
+            }
+        }
+    } else {
+        float ta = *(const float*)(lrec + LL.off_t0_avg);
+        double t0_avg = (double)ta * d_c.unit_ns / d_c.unit_mus;
+        double profile_time = track_time + t0_avg;
+        if (profile_time < end_tick_time && profile_time > start_tick_time) {
+            double photons = (double)g.nph / d_c.light_tick_size;
+            acc = __double2float_rn((double)acc + photons);
+            if (photons > d_c.mc_truth_threshold) {
+                for (int q = 0; q < n_true; q++) {
+                    long long* tid = true_id + tbase + q;
+                    if (*tid == -1 || *tid == g.track_id) { *tid = g.track_id; true_ph[tbase + q] += photons; break; }
+                }
+            }
+        }
+    }
+}
+
+// brute force (the reference's formulation: every tick walks every segment; CTA-wide early-out): kept for A/B (LSB_LIGHT_BINNED=0)
 __global__ void __launch_bounds__(LT_TPB) k_sum_light_signals(const LightSeg* __restrict__ segs, long long n_sorted,
                                                               const char* __restrict__ lut, lsb_lut_layout LL, double start_time,
                                                               float* __restrict__ lsi, int ndet, int nticks,
@@ -105,42 +156,69 @@ __global__ void __launch_bounds__(LT_TPB) k_sum_light_signals(const LightSeg* __
         for (int s = 0; s < nc; s++) {
             const LightSeg g = s_seg[s];
             if (!(g.nph > 0.f)) continue;
-            double track_time = g.t0;
-            double track_end_time = track_time + prof_len;
-            if (track_end_time < cta_lo || track_time > cta_hi) continue;          // uniform early-out (superset of the next test)
-            if (track_end_time < start_tick_time || track_time > end_tick_time) continue;
-            const char* lrec = lut + g.lut_off;
-            if (d_c.enable_lut_smearing) {
-                for (int ip = 0; ip < LL.n_time_dist; ip++) {
-                    double profile_time = track_time + (double)ip * d_c.unit_ns / d_c.unit_mus;
-                    if (profile_time < end_tick_time && profile_time > start_tick_time) {
-                        float tp = *(const float*)(lrec + LL.off_time_dist + 4 * ip);
-                        double photons = (double)__fmul_rn(g.nph, tp) / d_c.light_tick_size;
-                        acc = __double2float_rn((double)acc + photons);
-                        if (photons > d_c.mc_truth_threshold) {
-                            for (int q = 0; q < n_true; q++) {
-                                long long* tid = true_id + tbase + q;
-                                if (*tid == -1 || *tid == g.track_id) { *tid = g.track_id; true_ph[tbase + q] += photons; break; }
-                            }
-                        }
-                    }
-                }
-            } else {
-                float ta = *(const float*)(lrec + LL.off_t0_avg);
-                double t0_avg = (double)ta * d_c.unit_ns / d_c.unit_mus;
-                double profile_time = track_time + t0_avg;
-                if (profile_time < end_tick_time && profile_time > start_tick_time) {
-                    double photons = (double)g.nph / d_c.light_tick_size;
-                    acc = __double2float_rn((double)acc + photons);
-                    if (photons > d_c.mc_truth_threshold) {
-                        for (int q = 0; q < n_true; q++) {
-                            long long* tid = true_id + tbase + q;
-                            if (*tid == -1 || *tid == g.track_id) { *tid = g.track_id; true_ph[tbase + q] += photons; break; }
-                        }
-                    }
-                }
-            }
+            if (g.t0 + prof_len < cta_lo || g.t0 > cta_hi) continue;          // uniform early-out (superset of the per-tick test)
+            light_add_segment(g, lut, LL, start_tick_time, end_tick_time, prof_len, acc, true_id, true_ph, tbase, n_true);
         }
+    }
+    if (active) lsi[(long long)idet * nticks + itick] = acc;
+}
+
+// ---- binned form ---------------------------------------------------------------------------------------------------
+// A segment lights a channel for t0_profile_length ns: a few dozen of the 16 000 ticks.  Every (channel, segment) entry with
+// photons is expanded to the blocks of LT_TPB ticks it can touch (a superset computed with a margin; the exact per-tick test
+// stays in the kernel), the (block, entry) pairs are sorted by block with the package's STABLE radix sort, so each block's list is
+// in `sorted_indices` order -- the order in which the reference adds, which the float32 accumulator depends on -- and a CTA walks
+// only its own list: O(entries) instead of O(ndet * nticks * S).
+__global__ void k_light_block_ranges(const LightSeg* __restrict__ segs, long long n_entries, double start_time, double prof_len,
+                                     int nticks, int2* __restrict__ range, uint32_t* __restrict__ count) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const LightSeg g = segs[e];
+    int2 r = make_int2(0, -1);
+    if (g.nph > 0.f) {
+        const double lo = floor((g.t0 - start_time) / d_c.light_tick_size) - 2.0;
+        const double hi = ceil((g.t0 + prof_len - start_time) / d_c.light_tick_size) + 2.0;
+        if (hi >= 0.0 && lo <= (double)(nticks - 1)) {
+            const int il = lo < 0.0 ? 0 : (int)lo, ih = hi > (double)(nticks - 1) ? nticks - 1 : (int)hi;
+            r = make_int2(il / LT_TPB, ih / LT_TPB);
+        }
+    }
+    range[e] = r;
+    count[e] = r.y >= r.x ? (uint32_t)(r.y - r.x + 1) : 0u;
+}
+__global__ void k_light_expand(const int2* __restrict__ range, const long long* __restrict__ offs, long long n_entries, long long n_sorted,
+                               int n_blocks, uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const int2 r = range[e];
+    const long long idet = e / n_sorted;
+    long long o = offs[e];
+    for (int b = r.x; b <= r.y; b++, o++) { keys[o] = (uint32_t)(idet * n_blocks + b); idx[o] = (int32_t)e; }
+}
+__global__ void __launch_bounds__(LT_TPB) k_sum_light_signals_binned(const LightSeg* __restrict__ segs, const int32_t* __restrict__ idx,
+                                                                     const long long* __restrict__ bucket, const char* __restrict__ lut,
+                                                                     lsb_lut_layout LL, double start_time, float* __restrict__ lsi, int ndet,
+                                                                     int nticks, long long* __restrict__ true_id, double* __restrict__ true_ph,
+                                                                     int n_true, double t0_profile_length) {
+    __shared__ LightSeg s_seg[LT_CHUNK];
+    const int idet = blockIdx.y;
+    const long long key = (long long)idet * gridDim.x + blockIdx.x;
+    const long long e0 = bucket[key], e1 = bucket[key + 1];
+    if (e0 >= e1) return;                                   // nothing reaches this block: the caller's values stay
+    const int itick = blockIdx.x * LT_TPB + threadIdx.x;
+    const bool active = itick < nticks;
+    const double start_tick_time = (double)itick * d_c.light_tick_size + start_time;
+    const double end_tick_time = start_tick_time + d_c.light_tick_size;
+    const double prof_len = t0_profile_length * d_c.unit_ns / d_c.unit_mus;
+    float acc = active ? lsi[(long long)idet * nticks + itick] : 0.f;
+    const long long tbase = ((long long)idet * nticks + itick) * n_true;
+    for (long long c0 = e0; c0 < e1; c0 += LT_CHUNK) {
+        const int nc = (int)(e1 - c0 < LT_CHUNK ? e1 - c0 : LT_CHUNK);
+        __syncthreads();
+        if ((int)threadIdx.x < nc) s_seg[threadIdx.x] = segs[idx[c0 + threadIdx.x]];
+        __syncthreads();
+        if (!active) continue;
+        for (int s = 0; s < nc; s++) light_add_segment(s_seg[s], lut, LL, start_tick_time, end_tick_time, prof_len, acc, true_id, true_ph, tbase, n_true);
     }
     if (active) lsi[(long long)idet * nticks + itick] = acc;
 }
@@ -301,9 +379,40 @@ LSB_EXPORT int lsb_sum_light_signals(const lsb_consts* c, const lsb_track_layout
         ndet_inc, op_channel, *LL, (const long long*)sorted_indices, n_sorted, ndet, segs);
     LSB_LAUNCH_CHECK("k_light_gather_segs");
     dim3 grid((unsigned)((nticks + LT_TPB - 1) / LT_TPB), (unsigned)ndet);
-    k_sum_light_signals<<<grid, LT_TPB, 0, st>>>(segs, n_sorted, (const char*)lut, *LL, start_time, light_sample_inc, ndet, nticks,
-                                                (long long*)true_track_id, true_photons, n_true, t0_profile_length);
-    LSB_LAUNCH_CHECK("k_sum_light_signals");
+    static int binned = -1;
+    if (binned < 0) { const char* e = getenv("LSB_LIGHT_BINNED"); binned = (e && e[0] == '0') ? 0 : 1; }
+    const long long n_entries = (long long)ndet * n_sorted, n_buckets = (long long)ndet * grid.x;
+    if (!binned || n_entries >= (1ll << 31) || n_buckets >= (1ll << 31)) {
+        k_sum_light_signals<<<grid, LT_TPB, 0, st>>>(segs, n_sorted, (const char*)lut, *LL, start_time, light_sample_inc, ndet, nticks,
+                                                    (long long*)true_track_id, true_photons, n_true, t0_profile_length);
+        LSB_LAUNCH_CHECK("k_sum_light_signals");
+        return 0;
+    }
+    int2* range; uint32_t* count; long long* offs; long long* bs; long long* total;
+    LSB_CUDA(tp.get(&range, n_entries)); LSB_CUDA(tp.get(&count, n_entries)); LSB_CUDA(tp.get(&offs, n_entries));
+    LSB_CUDA(tp.get(&bs, scan_num_blocks(n_entries) + 1)); LSB_CUDA(tp.get(&total, 1));
+    k_light_block_ranges<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(segs, n_entries, start_time, t0_profile_length * c->unit_ns / c->unit_mus,
+                                                                    nticks, range, count);
+    LSB_LAUNCH_CHECK("k_light_block_ranges");
+    if ((rc = exclusive_scan<uint32_t, long long>(count, n_entries, offs, bs, total, st))) return rc;
+    long long E = 0;
+    LSB_CUDA(cudaMemcpyAsync(&E, total, 8, cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
+    if (E == 0) return 0;
+    LSB_REQUIRE(E < (1ll << 31), "sum_light_signals: more than 2^31 (block, segment) pairs");
+    uint32_t *keyA, *keyB; int32_t *idxA, *idxB; long long* bucket;
+    LSB_CUDA(tp.get(&keyA, E)); LSB_CUDA(tp.get(&keyB, E)); LSB_CUDA(tp.get(&idxA, E)); LSB_CUDA(tp.get(&idxB, E));
+    LSB_CUDA(tp.get(&bucket, n_buckets + 1));
+    k_light_expand<<<lsb_blocks(n_entries, 256), 256, 0, st>>>(range, offs, n_entries, n_sorted, (int)grid.x, keyA, idxA);
+    LSB_LAUNCH_CHECK("k_light_expand");
+    int bits = 0;
+    while ((n_buckets >> bits) != 0) bits++;
+    if ((rc = rs_sort_pairs(&keyA, &keyB, &idxA, &idxB, E, bits, tp, st))) return rc;
+    k_unit_offsets<<<lsb_blocks(n_buckets + 1, 256), 256, 0, st>>>(keyA, E, n_buckets, bucket);
+    LSB_LAUNCH_CHECK("k_unit_offsets");
+    k_sum_light_signals_binned<<<grid, LT_TPB, 0, st>>>(segs, idxA, bucket, (const char*)lut, *LL, start_time, light_sample_inc, ndet, nticks,
+                                                       (long long*)true_track_id, true_photons, n_true, t0_profile_length);
+    LSB_LAUNCH_CHECK("k_sum_light_signals_binned");
     return 0;
 }
 
@@ -336,6 +445,9 @@ static int light_fir(int mode, const lsb_consts* c, const float* in, const int64
             wh[tt] = imp;
         }
     }
+    // taps beyond the last non-zero weight add w * in = 0 to the accumulator (and never pass the truth threshold): the SiPM impulse is
+    // 256 samples long while the reference loops over the whole light window
+    while (nw > 1 && wh[nw - 1] == 0.0) nw--;
     TmpPool tp(st);
     double* wd;
     cudaError_t e = tp.get(&wd, nw);

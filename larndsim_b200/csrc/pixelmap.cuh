@@ -216,6 +216,8 @@ __global__ void k_sum_sort(const long long* __restrict__ pim, const int* __restr
 
 #define SUM_TPB 256
 #define SUM_CHUNK 64
+#define SUM_R 4             // ticks per thread (t, t + TPB, ...): four independent loads per entry in flight -- with one tick per thread
+                            // the kernel was latency-bound at 0.26 of the HBM peak (2048 threads x 4 B in flight per SM)
 // FRESH: pixels_signals holds no earlier contributions (fused chain): it is written without being read or pre-zeroed
 template <bool WITH_PTS, bool FRESH>
 __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restrict__ pixels_signals, long long U, int Tt,
@@ -226,28 +228,46 @@ __global__ void __launch_bounds__(SUM_TPB) k_sum_pixel_signals(double* __restric
     __shared__ SumEntry s_e[SUM_CHUNK];
     const long long p = blockIdx.x;
     const int n = counts[p];
-    const int t = blockIdx.y * SUM_TPB + threadIdx.x;
-    const bool active = t < Tt;
-    if (n == 0) { if (FRESH && active) pixels_signals[p * Tt + t] = 0.0; return; }
+    const int t0 = blockIdx.y * (SUM_TPB * SUM_R) + threadIdx.x;
+    double* out = pixels_signals + p * Tt;
+    if (n == 0) {
+        if (FRESH) {
+#pragma unroll
+            for (int r = 0; r < SUM_R; r++) { const int t = t0 + r * SUM_TPB; if (t < Tt) out[t] = 0.0; }
+        }
+        return;
+    }
     const SumEntry* L = sorted + offs[p];
-    double acc = (active && !FRESH) ? pixels_signals[p * Tt + t] : 0.0;
-    double* prow = pts + (p * Tt + (active ? t : 0)) * (long long)K;
+    double acc[SUM_R];
+#pragma unroll
+    for (int r = 0; r < SUM_R; r++) { const int t = t0 + r * SUM_TPB; acc[r] = (t < Tt && !FRESH) ? out[t] : 0.0; }
+    const int cta_lo = blockIdx.y * (SUM_TPB * SUM_R), cta_hi = cta_lo + SUM_TPB * SUM_R - 1;
     for (int c0 = 0; c0 < n; c0 += SUM_CHUNK) {
         int nc = n - c0 < SUM_CHUNK ? n - c0 : SUM_CHUNK;
         __syncthreads();
         if ((int)threadIdx.x < nc) s_e[threadIdx.x] = L[c0 + threadIdx.x];
         __syncthreads();
-        if (!active) continue;
         for (int i = 0; i < nc; i++) {
-            long long itick = (long long)t - s_e[i].start_tick;
-            if (itick < s_e[i].lo || itick > s_e[i].hi) continue;
-            float s = __ldg(signals + (long long)s_e[i].e * T + itick);
-            if (s == 0.f) continue;                            // x + 0 == x: skipping is exact
-            acc += (double)s;
-            if (WITH_PTS) prow[s_e[i].slot] += (double)s;
+            const SumEntry e = s_e[i];
+            // ticks of this entry: start_tick + [lo, hi]; skip the entry for the whole CTA if it misses its tick block
+            if (e.start_tick + e.hi < cta_lo || e.start_tick + e.lo > cta_hi) continue;
+            const float* row = signals + (long long)e.e * T;
+            float v[SUM_R];
+#pragma unroll
+            for (int r = 0; r < SUM_R; r++) {
+                const long long itick = (long long)(t0 + r * SUM_TPB) - e.start_tick;
+                v[r] = (itick >= e.lo && itick <= e.hi && t0 + r * SUM_TPB < Tt) ? __ldg(row + itick) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < SUM_R; r++) {
+                if (v[r] == 0.f) continue;                         // x + 0 == x: skipping is exact
+                acc[r] += (double)v[r];
+                if (WITH_PTS) pts[(p * Tt + t0 + r * SUM_TPB) * (long long)K + e.slot] += (double)v[r];
+            }
         }
     }
-    if (active) pixels_signals[p * Tt + t] = acc;
+#pragma unroll
+    for (int r = 0; r < SUM_R; r++) { const int t = t0 + r * SUM_TPB; if (t < Tt) out[t] = acc[r]; }
 }
 
 // tick ranges of sparsely stored rows -> entries (thread per pixel)
@@ -283,7 +303,7 @@ static int sum_run(const SumCtx& x, double* pixels_signals, long long U, int Tt,
                    cudaStream_t st, bool fresh = false) {
     if (Tt <= 0) return 0;
     if (T <= 0) { if (fresh) LSB_CUDA(cudaMemsetAsync(pixels_signals, 0, (size_t)U * Tt * 8, st)); return 0; }
-    dim3 grid((unsigned)U, (unsigned)((Tt + SUM_TPB - 1) / SUM_TPB));
+    dim3 grid((unsigned)U, (unsigned)((Tt + SUM_TPB * SUM_R - 1) / (SUM_TPB * SUM_R)));
     if (pts) k_sum_pixel_signals<true, false><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, pts);
     else if (fresh) k_sum_pixel_signals<false, true><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, nullptr);
     else k_sum_pixel_signals<false, false><<<grid, SUM_TPB, 0, st>>>(pixels_signals, U, Tt, signals, T, x.offs, x.counts, x.sorted, K, nullptr);

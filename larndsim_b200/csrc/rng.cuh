@@ -92,6 +92,57 @@ __global__ void k_rng_create_states(const RngJumpTable* __restrict__ tab, unsign
     states[2 * i] = s0; states[2 * i + 1] = s1;
 }
 
+// ---- stepping a stream ahead: T^(RNG_STEP_UNIT * 2^k), T = one next() -------------------------------------------------------------
+// A stream that has to be consumed from many positions at once (the per-pixel noise of get_adc_values: ~13 000 draws per pixel,
+// strictly sequential in the reference) is cut into chunks of RNG_STEP_UNIT draws; the state at the start of chunk g is
+// T^(RNG_STEP_UNIT * g) state 0, one bit-matrix product per set bit of g.
+#define RNG_STEP_UNIT 128            // draws per chunk = 64 Box-Muller normals
+#define RNG_STEP_LEVELS 20
+struct RngStepTable { uint64_t col[RNG_STEP_LEVELS][128][2]; };
+static const RngStepTable* rng_step_table_host() {
+    static RngStepTable* T = nullptr;
+    if (T) return T;
+    T = new RngStepTable();
+    uint64_t cur[128][2], nxt[128][2];
+    for (int b = 0; b < 128; b++) {                                   // T itself
+        uint64_t v[2] = {0, 0};
+        v[b >> 6] = 1ULL << (b & 63);
+        rngj_next(v);
+        cur[b][0] = v[0]; cur[b][1] = v[1];
+    }
+    for (int sq = 0; (1 << sq) < RNG_STEP_UNIT; sq++) {               // T^(2^sq) -> T^RNG_STEP_UNIT
+        for (int b = 0; b < 128; b++) rngj_matvec(cur, cur[b], nxt[b]);
+        memcpy(cur, nxt, sizeof(cur));
+    }
+    memcpy(T->col[0], cur, sizeof(cur));
+    for (int k = 1; k < RNG_STEP_LEVELS; k++)
+        for (int b = 0; b < 128; b++) rngj_matvec(T->col[k - 1], T->col[k - 1][b], T->col[k][b]);
+    return T;
+}
+static const RngStepTable* rng_step_table_dev() {
+    static const RngStepTable* dev_tab[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!dev_tab[dev]) {
+        RngStepTable* d = nullptr;
+        if (cudaMalloc((void**)&d, sizeof(RngStepTable)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, rng_step_table_host(), sizeof(RngStepTable), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+        dev_tab[dev] = d;
+    }
+    return dev_tab[dev];
+}
+__device__ __forceinline__ void rng_matvec_dev(const ulonglong2* __restrict__ col, unsigned long long& s0, unsigned long long& s1) {
+    unsigned long long a = 0, b = 0;
+#pragma unroll 4
+    for (int bit = 0; bit < 64; bit++) {
+        const ulonglong2 c0 = __ldg(col + bit), c1 = __ldg(col + 64 + bit);
+        const unsigned long long m0 = 0ULL - ((s0 >> bit) & 1ULL), m1 = 0ULL - ((s1 >> bit) & 1ULL);
+        a ^= (c0.x & m0) ^ (c1.x & m1);
+        b ^= (c0.y & m0) ^ (c1.y & m1);
+    }
+    s0 = a; s1 = b;
+}
+
 static int rng_create_states_dev(unsigned long long* states_dev, long long n, uint64_t seed, uint64_t start, cudaStream_t st) {
     if (n <= 0) return 0;
     LSB_REQUIRE(start + (uint64_t)n < (1ULL << RNG_JUMP_LEVELS), "rng_create_states: subsequence index beyond 2^48");

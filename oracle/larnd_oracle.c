@@ -928,6 +928,7 @@ ORC_API int orc_sum_light_signals(const lsb_consts* c, const lsb_track_layout* L
                                   int64_t* true_id, double* true_ph, int32_t n_true,
                                   const int64_t* sorted_indices, int64_t n_sorted, double t0_profile_length) {
     (void)S;
+#pragma omp parallel for collapse(2) schedule(dynamic, 256)
     for (int32_t idet = 0; idet < ndet; idet++)
         for (int32_t itick = 0; itick < nticks; itick++) {
             double start_tick_time = itick * c->light_tick_size + start_time;

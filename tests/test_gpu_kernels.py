@@ -365,3 +365,54 @@ def test_light_chain_medium_vs_oracle(cuda):
     resp = np.zeros_like(inc)
     light_sim.calc_light_detector_response[(nd, 19), (1, 64)](ref_disc, empty_i, empty_f, resp, empty_i.copy(), empty_f.copy())
     assert np.array_equal(resp, ref_resp)
+
+
+def test_light_chain_2x2_module_shape_full_taps(cuda):
+    """Light chain at the 2x2 shape (BASELINE configs[3]): one module's 96 optical channels x 16 000 ticks of 1 ns, beam-spill
+    segments, LUT smearing on, the FULL 16 000-tap scintillation / response windows -- float32 waveforms bit for bit
+    (reference add order), through the binned sum_light_signals and the FIRs with trimmed zero taps."""
+    from larndsim_b200 import lightLUT, light_sim, rng
+    mod = lc.load_snapshot("2x2")
+    li = mod.light
+    li.ENABLE_LUT_SMEARING = True
+    assert tuple(li.LIGHT_WINDOW) == (0, 16) and li.LIGHT_TICK_SIZE == 0.001
+    tr = synth.beam_spill_segments(1500, mod.detector, seed=8, n_events=1)
+    orc = h.Oracle()
+    orc.quench(tr, 2); orc.drift(tr)
+    lut = synth.light_lut((14, 26, 8, 48), 40)
+    ol = h.OracleLight()
+    ndet = int(li.N_OP_CHANNEL)
+    eff = np.asarray(li.OP_CHANNEL_EFFICIENCY, dtype=np.float64)
+    tpc = np.asarray(li.OP_CHANNEL_TO_TPC, dtype=np.int64)
+    linc_ref, vox_ref = ol.light_incidence(tr, lut, ndet, eff, tpc)
+    linc = np.zeros_like(linc_ref); vox = np.zeros_like(vox_ref)
+    lightLUT.calculate_light_incidence[6, 256](tr, lut, linc, vox)
+    assert np.array_equal(vox, vox_ref) and np.array_equal(linc["n_photons_det"], linc_ref["n_photons_det"])
+    nticks, t_start = light_sim.get_nticks(linc)
+    assert nticks == 16000
+    op_channel = np.asarray(li.TPC_TO_OP_CHANNEL)[:2].ravel().astype(np.int32)         # the module's 96 channels (mod2mod mode)
+    nd = len(op_channel)
+    sorted_idx = np.stack([np.argsort(linc["n_photons_det"][:, ch], kind="stable")[::-1] for ch in op_channel]).astype(np.int64)
+    seg_ids = np.arange(len(tr), dtype=np.int64)
+    empty_i = np.zeros((nd, nticks, 0), dtype=np.int64); empty_f = np.zeros((nd, nticks, 0))
+    ref_inc, _, _ = ol.sum_light_signals(tr, vox, seg_ids, linc, op_channel, lut, t_start, nticks, 0, sorted_idx, 40)
+    inc = np.zeros((nd, nticks), dtype=np.float32)
+    BPG, TPB = (nd, (nticks + 63) // 64), (1, 64)
+    light_sim.sum_light_signals[BPG, TPB](tr, vox, seg_ids, linc, op_channel, lut, t_start, inc, empty_i, empty_f, sorted_idx, 40.0)
+    assert (ref_inc != 0).sum() > 1000 and np.array_equal(inc, ref_inc)
+    ref_sc, _, _ = ol.scintillation(ref_inc, empty_i, empty_f)
+    sc = np.zeros_like(inc)
+    light_sim.calc_scintillation_effect[BPG, TPB](inc, empty_i, empty_f, sc, empty_i.copy(), empty_f.copy())
+    assert np.array_equal(sc, ref_sc)
+    st = h.rng_states(nd * nticks, 5)
+    ref_disc = ol.stat_fluctuations(ref_sc, st)
+    disc = np.zeros_like(inc)
+    states = rng.create_xoroshiro128p_states(nd * nticks, 5)
+    light_sim.calc_stat_fluctuations[BPG, TPB](sc, disc, states)
+    assert (disc != ref_disc).mean() < 1e-4
+    assert np.array_equal(states.copy_to_host().view(np.uint64).reshape(-1, 2), st)
+    gain = np.asarray(li.LIGHT_GAIN, dtype=np.float64).reshape(-1)
+    ref_resp, _, _ = ol.detector_response(ref_disc, empty_i, empty_f, gain, np.asarray(li.IMPULSE_MODEL, dtype=np.float64))
+    resp = np.zeros_like(inc)
+    light_sim.calc_light_detector_response[BPG, TPB](ref_disc, empty_i, empty_f, resp, empty_i.copy(), empty_f.copy())
+    assert (ref_resp != 0).sum() > 1000 and np.array_equal(resp, ref_resp)
