@@ -269,6 +269,8 @@ def kernel_rooflines(prof, steps, shape, peak_hbm, sm_mhz):
         # get_adc_values: one pass over pixels_signals + the noise streams + the hit tables
         "k_fee_trigger": ("hbm", 8.0 * shape["pixel_ticks"] + 2 * 8.0 * shape["U"] * A),
         "k_fee_fir_pre": ("hbm", 2 * 8.0 * shape["pixel_ticks"]),
+        # noise stream of every pixel: two float32 normals per tick written once (+ hold-delay draws)
+        "k_fee_rng_chunks": ("hbm", 2 * 4.0 * shape["pixel_ticks"]),
         "k_fee_fractions_sparse": ("hbm", 4.0 * shape["pair_ticks"] + 8.0 * shape["U"] * A * K),
         "k_mc_sampler": ("fp32", 330.0 * shape["n_samples"]),
         "k_mc_uniforms": ("hbm", 24.0 * shape["n_samples"]),
