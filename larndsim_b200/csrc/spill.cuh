@@ -316,10 +316,15 @@ struct BlockCopy { const char* src; long long dst_off; long long bytes; };
 __global__ void k_copy_blocks(const BlockCopy* __restrict__ blocks, char* __restrict__ dst) {
     const BlockCopy b = blocks[blockIdx.y];
     char* d = dst + b.dst_off;
-    if ((((uintptr_t)b.src | (uintptr_t)d | (uintptr_t)b.bytes) & 15) == 0) {
+    const uintptr_t align = (uintptr_t)b.src | (uintptr_t)d | (uintptr_t)b.bytes;
+    if ((align & 15) == 0) {
         const long long n = b.bytes >> 4;
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
             reinterpret_cast<int4*>(d)[i] = __ldg(reinterpret_cast<const int4*>(b.src) + i);
+    } else if ((align & 7) == 0) {                       // mc_packets_assn rows: 8 + 32 n bytes, 8-byte aligned
+        const long long n = b.bytes >> 3;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            reinterpret_cast<long long*>(d)[i] = __ldg(reinterpret_cast<const long long*>(b.src) + i);
     } else {
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < b.bytes; i += (long long)gridDim.x * blockDim.x) d[i] = b.src[i];
     }

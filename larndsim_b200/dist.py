@@ -98,7 +98,9 @@ class HitTableGather:
 
     def unpack(self, buf):
         """(pixel ids i4[n], ADC codes f8[n], timestamps f8[n]) of one received buffer"""
-        n = min(int(buf[0, 0].item()), self.cap)
+        n = int(buf[0, 0].item())
+        if n > self.cap:
+            raise OverflowError("HitTableGather: %d hits in a batch, capacity %d (size `cap` from U * MAX_ADC_VALUES to make this impossible)" % (n, self.cap))
         return buf[1:n + 1, 0].to(torch.int32), buf[1:n + 1, 1], buf[1:n + 1, 2]
 
 

@@ -105,6 +105,11 @@ def test_product_has_no_cpu_fallback():
         inc = np.zeros((3, 4), dtype=[("n_photons_det", "f4"), ("t0_det", "f4")])
         with pytest.raises(RuntimeError):
             light_sim.get_nticks(inc)
+        from larndsim_b200 import spill, chain
+        with pytest.raises(RuntimeError):
+            spill.SpillRunner(seg.dtype, synth.response_lut(lc.detector))
+        with pytest.raises(RuntimeError):
+            chain.Chain(seg.dtype, synth.response_lut(lc.detector))
     pkg = os.path.join(ROOT, "larndsim_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:

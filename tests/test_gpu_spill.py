@@ -2,6 +2,9 @@
 the drop-in modules, i.e. the reference's own sequence (cli/simulate_pixels.py:667-671, 727-742, 864-1117, save_results ->
 fee.export_to_hdf5): active volume cut, quench, drift, TPCBatcher masks, one chain call per (event, TPC group) batch, one
 export per batch, the between-event packets in between.  Packets and mc_packets_assn rows must agree byte for byte."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -20,59 +23,8 @@ def cuda():
     return torch
 
 
-def call_by_call(tracks, mod, resp, rand_seed, tpc_batch_size):
-    """The loop with one drop-in call per reference call."""
-    import torch
-    from larndsim_b200 import active_volume, quenching, drifting, chain as lchain, packets as lp, fee
-    from larndsim_b200.util import batching
-    det = mod.detector
-    keep = active_volume.select_active_volume(tracks, det.TPC_BORDERS)
-    tracks = np.ascontiguousarray(tracks[keep])
-    quenching.quench[1, 1](tracks, mod.physics.BIRKS)
-    drifting.drift[1, 1](tracks)
-    segment_ids = tracks["segment_id"].astype(np.int64)
-    trajectory_ids = tracks["file_traj_id"].astype(np.int64)
-    events = np.unique(tracks["event_id"])
-    event_times = (events.astype(np.int64) % mod.sim.MAX_EVENTS_PER_FILE) * float(mod.sim.SPILL_PERIOD)
-    tables = lp.ReadoutTables.from_consts(mod)
-    ch = lchain.Chain(tracks.dtype, resp, rng_fresh=True)
-    period = det.CLOCK_RESET_PERIOD * det.CLOCK_CYCLE
-    sync_start = event_times[0] // period * period + period
-    packets, rows, sizes = [], [], []
-    last_event = None
-    nB = None
-    for u, (ievd, mask) in enumerate(batching.TPCBatcher(tracks, tracks, "event_id", tpc_batch_size=tpc_batch_size, tpc_borders=det.TPC_BORDERS)):
-        t0 = float(event_times[int(np.searchsorted(events, ievd))])
-        if last_event is None or ievd > last_event:                            # :868-887
-            if t0 - sync_start >= 0:
-                sync_times = np.arange(sync_start, t0 + 1, period)
-                if len(sync_times):
-                    p, r = fee.export_sync_to_hdf5(None, np.full(sync_times.shape, period))
-                    packets.append(p); rows.append(r)
-                    sync_start = sync_times[-1] + period
-            p, r = fee.export_timestamp_trigger_to_hdf5(None, [t0])
-            packets.append(p); rows.append(r)
-        last_event = ievd
-        sub = np.ascontiguousarray(tracks[mask])
-        sizes.append(len(sub))
-        if len(sub) == 0:
-            continue
-        res = ch.run(ll.DeviceRecords(host=sub), quench_mode=-1, rng_seed=rand_seed + u, n_events=1)
-        if res.n_unique_pixels == 0:
-            continue
-        tpm = res.track_pixel_map
-        seg_of, trj_of = torch.from_numpy(segment_ids[mask]).cuda(), torch.from_numpy(trajectory_ids[mask]).cuda()
-        safe = tpm.clamp(min=0)
-        track_ids = torch.where(tpm >= 0, seg_of[safe], tpm)
-        traj_ids = torch.where(tpm >= 0, trj_of[safe], tpm)
-        ev = np.full(tuple(res.adc_digit.shape), int(ievd), dtype=np.int64)
-        # charge-only run: one light trigger per event at t0, module 1 (cli/simulate_pixels.py:222-226)
-        p, r = lp.export_packets(tables, ev, res.adc_digit, res.adc_ticks_list, res.unique_pix, res.current_fractions, track_ids,
-                                 traj_ids, np.array([t0]), light_trigger_times=np.zeros(1), light_trigger_event_id=np.array([int(ievd)]),
-                                 light_trigger_modules=np.ones(1))
-        packets.append(p); rows.append(r)
-    ch.close()
-    return np.concatenate(packets), np.concatenate(rows), tracks, np.array(sizes)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+from reference_loop import call_by_call  # noqa: E402  (the loop with one drop-in call per reference call)
 
 
 @pytest.mark.parametrize("config,n,n_events,tbs", [("2x2", 6000, 3, 2), ("ndlar", 12000, 2, 2), ("module0", 3000, 2, 1)])
@@ -146,3 +98,25 @@ def test_partitioned_spill_equals_single_rank(cuda):
                         "--master-port", "29611", os.path.join(root, "tests", "spill_dist_worker.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "output == single-rank output: True" in r.stdout
+
+
+def test_verbatim_batch_body_equals_fused_chain(cuda):
+    """cli/simulate_pixels.py:907-1102 statement by statement with the drop-in kernels (examples/reference_loop.py
+    batch_body_verbatim: dense pixels_tracks_signals, the S-iteration index-map loop, ...) == the fused chain on the same batch"""
+    from reference_loop import batch_body_verbatim
+    from larndsim_b200 import chain as lchain, quenching, drifting
+    mod = lc.load_snapshot("2x2")
+    resp = synth.response_lut(mod.detector)
+    tracks = synth.beam_spill_segments(500, mod.detector, seed=77, n_events=1)
+    quenching.quench[2, 256](tracks, mod.physics.BIRKS)
+    drifting.drift[2, 256](tracks)
+    out = batch_body_verbatim(tracks.copy(), resp, rand_seed=4, ievd=0, mod=mod)
+    ch = lchain.Chain(tracks.dtype, resp, rng_fresh=True, exact_fractions=True)
+    res = ch.run(ll.DeviceRecords(host=tracks.copy()), quench_mode=-1, rng_seed=4)
+    assert cuda.equal(out["unique_pix"].to(cuda.int32), res.unique_pix)
+    assert cuda.equal(out["track_pixel_map"], res.track_pixel_map)
+    assert cuda.equal(out["pixels_signals"], res.pixels_signals)
+    assert cuda.equal(out["integral_list"], res.adc_list) and cuda.equal(out["adc_tot_ticks"], res.adc_ticks_list)
+    assert cuda.equal(out["adc_tot"], res.adc_digit) and cuda.equal(out["current_fractions"], res.current_fractions)
+    assert int((out["adc_tot"] > 0).sum()) > 100 and not bool(out["overflow_flag"].any())
+    ch.close()
