@@ -138,7 +138,8 @@ def batch_body_verbatim(selected_tracks, response, rand_seed, ievd, mod, rng_sta
     overflow_flag = torch.zeros(len(unique_pix), dtype=torch.float64, device=dev)
     detsim.sum_pixel_signals[BPG, TPB](pixels_signals, signals, track_starts, pixel_index_map, track_pixel_map, pixels_tracks_signals, overflow_flag)
     # get_adc_values (:1070-1102)
-    time_ticks = torch.linspace(0, len(unique_eventIDs) * detector.TIME_INTERVAL[1], pixels_signals.shape[1] + 1, dtype=torch.float64, device=dev)
+    # cp.linspace follows numpy's formula (start + i * step, last element = stop); torch.linspace does not
+    time_ticks = torch.from_numpy(np.linspace(0, len(unique_eventIDs) * detector.TIME_INTERVAL[1], pixels_signals.shape[1] + 1)).to(dev)
     integral_list = torch.zeros((pixels_signals.shape[0], sim.MAX_ADC_VALUES), dtype=torch.float64, device=dev)
     adc_ticks_list = torch.zeros((pixels_signals.shape[0], sim.MAX_ADC_VALUES), dtype=torch.float64, device=dev)
     current_fractions = torch.zeros((pixels_signals.shape[0], sim.MAX_ADC_VALUES, track_pixel_map.shape[1]), dtype=torch.float64, device=dev)
