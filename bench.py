@@ -560,7 +560,54 @@ def bench_module0(lib, ll, lchain, lc, peak, sm_mhz, steps):
     prof = profile_session(lib, passes)
     ch.close()
     by_kernel = kernel_rooflines(prof, steps, acc, peak, sm_mhz)
-    return {"workload": "module0 config, synthetic cosmic-muon segments (1e4 segments per batch), quench->digitize, 2 batches in flight, noise on",
+    # the deterministic tracks_current kernel (detsim.py:351-453; not called by the CLI): bounded sample of the same batch, inputs
+    # made with the drop-in kernels (quench, drift, max_pixels, get_pixels, time_intervals)
+    tc = None
+    try:
+        from math import ceil
+        from larndsim_b200 import detsim, quenching, drifting, pixels_from_track as pft
+        n_tc = 128
+        sub = tracks[:n_tc].copy()
+        quenching.quench[1, 128](sub, int(snap.mode_birks))
+        drifting.drift[1, 128](sub)
+        radius = ceil(max(sub["tran_diff"]) * 5 / mod.detector.PIXEL_PITCH)
+        mp = np.array([0])
+        pft.max_pixels[1, 128](sub, mp)
+        P_tc = int((2 * radius + 1) * mp[0] + (1 + 2 * radius) * radius * 2)
+        d_sub = ll.DeviceRecords(host=sub)
+        act = torch.full((n_tc, int(mp[0])), -1, dtype=torch.int32, device="cuda")
+        neigh = torch.full((n_tc, P_tc), -1, dtype=torch.int32, device="cuda")
+        nrad = torch.full((n_tc, P_tc), -1, dtype=torch.int32, device="cuda")
+        npl = torch.zeros(n_tc, dtype=torch.float64, device="cuda")
+        pft.get_pixels[1, 128](d_sub, act, neigh, nrad, npl, radius)
+        ml = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ts = torch.empty(n_tc, dtype=torch.float64, device="cuda")
+        detsim.time_intervals[1, 128](ts, ml, d_sub)
+        T_tc = int(ml.item())
+        sig_tc = torch.zeros((n_tc, P_tc, T_tc), dtype=torch.float32, device="cuda")
+        resp_d = torch.from_numpy(response).cuda()
+        detsim.tracks_current[1, 1](sig_tc, neigh, d_sub, resp_d)
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sig_tc.zero_()
+        t0e.record()
+        detsim.tracks_current[1, 1](sig_tc, neigh, d_sub, resp_d)
+        t1e.record()
+        torch.cuda.synchronize()
+        tc_ms = t0e.elapsed_time(t1e)
+        live_pairs = int((sig_tc != 0).any(dim=2).sum().item())
+        live_ticks = int((sig_tc != 0).sum().item())
+        sp = int(mod.detector.SAMPLED_POINTS)
+        flops = 110.0 * live_pairs * sp ** 3 + 2.0 * sp ** 3 * live_ticks          # 110 N_rho + 2 N_rho T_act, z_steps >= SAMPLED_POINTS
+        fp32_peak = FP32_LANES * 2 * sm_mhz * 1e6
+        tc = {"segments": n_tc, "ms": tc_ms, "segments_per_s": n_tc / (tc_ms * 1e-3), "live_pairs": live_pairs, "sampled_points": sp,
+              "algorithmic_flops_lower_bound": flops, "achieved_tflops_lower_bound": flops / (tc_ms * 1e-3) / 1e12,
+              "frac_of_fp32_peak_lower_bound": flops / (tc_ms * 1e-3) / fp32_peak,
+              "note": "rho (erfc, exp, log) and the table products are float64 like the reference: its own ceiling is the FP64 / transcendental "
+                      "rate, not FP32 FFMA"}
+    except Exception as exc:
+        tc = {"error": repr(exc)}
+    return {"tracks_current": tc, "workload": "module0 config, synthetic cosmic-muon segments (1e4 segments per batch), quench->digitize, 2 batches in flight, noise on",
             "segments_per_s": S / (ms * 1e-3), "ms_per_batch": ms, "unique_pixels": r1.n_unique_pixels, "ticks": r1.n_ticks, "hits": r1.n_hits,
             "n_fma_per_batch": acc["n_fma"] / steps, "mc_sample_points_per_batch": acc["n_samples"] / steps,
             "stage_ms_per_batch": {k: v / steps for k, v in stage_acc.items()},

@@ -717,7 +717,8 @@ __device__ __forceinline__ void acc_window(const float4* __restrict__ lut4, int 
     for (int r = 0; r < R; r++) {
         const float4* w = lut4 + min(Qb[r] + q, n4m2);
         lo[r] = __ldg(w);
-        hi[r] = __ldg(w + 1);
+        hi[r] = __ldg(w + 1);       // (skipping this load for groups whose samples all sit at 4q was measured: the warp-uniform test in
+                                    // front of the loads costs more than the ~8 % of wavefronts it saves -- 1374 against 1202 ms per spill)
     }
 }
 template <int R>
