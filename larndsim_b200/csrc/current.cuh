@@ -756,6 +756,29 @@ __device__ __forceinline__ void acc_gather(const float4* __restrict__ lut4, int 
     }
 }
 
+// ---- TMA variant of the grouped interior path (FAST == 3) ---------------------------------------------------------------------------
+// The 32 lanes of a warp read, for one group record and one 128-tick block, the CONTIGUOUS table words [4(Qb0 + q), + 132): one
+// `cp.async.bulk` (TMA, 1-D; UBLKCP in SASS) per group brings them into a per-warp ring of shared-memory stages, completion is
+// signalled on an mbarrier per stage, and every lane then takes its 8-word window with two LDS.128.  A/B against the LDG.128 path:
+// profiles/r02_spill_pipeline.md (LSB_ACC_TMA=1 selects it).
+#define ACC_TMA_STAGES 4
+#define ACC_TMA_WORDS 136                       // 132 used; stage stride 544 B (16-byte aligned)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 // ---- lane = 8 consecutive ticks on the 4-word groups (FAST == 2) -----------------------------------------------------------
 // The window of a group grows from 8 to 12 table words per lane (three aligned LDG.128) but serves twice the ticks: 1.5 words
 // per tick instead of 2, and the per-group overhead (record, count unpacking, branches) is paid once per 256 ticks of a warp.
@@ -947,6 +970,67 @@ __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long 
                 }
         }
 #endif
+    }
+    if constexpr (FAST == 3) {
+        constexpr int NW = ACC_TPB / 32, NS = ACC_TMA_STAGES;
+        __shared__ __align__(128) float s_win[NW][NS][ACC_TMA_WORDS];
+        __shared__ __align__(8) unsigned long long s_bar[NW][NS];
+        const int lane = tid & 31, warp = tid >> 5;
+        const int ng = gp->n_groups;
+        const long long n_words4 = ((long long)p.Rx * p.Ry * p.Rt) & ~3LL;     // whole 16-byte words of the table
+        const float* table = reinterpret_cast<const float*>(lut);
+        const int4* recs = reinterpret_cast<const int4*>(reinterpret_cast<const GroupRec*>(groups) + soff);
+        if (lane == 0) {
+#pragma unroll
+            for (int s2 = 0; s2 < NS; s2++) mbar_init(smem_u32(&s_bar[warp][s2]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        unsigned it = 0;                                    // copies consumed so far by this warp (stage = it % NS, parity = (it / NS) & 1)
+        unsigned issued = 0;
+        for (int tb = int_lo + 128 * warp; tb <= int_hi && ng > 0; tb += 128 * NW) {
+            const long long base4 = (long long)(tb - int_lo);              // first table word of the block's window, relative to 4q
+            auto issue = [&](int g) {
+                if (lane == 0) {
+                    const int q = __ldg(&recs[g].x);
+                    long long w0 = 4LL * q + base4;
+                    long long nw = n_words4 - w0;
+                    if (nw > 132) nw = 132;
+                    if (nw < 4) { nw = 4; w0 = n_words4 - 4; }              // (never needed by a stored tick)
+                    const unsigned st = issued % NS;
+                    const uint32_t bar = smem_u32(&s_bar[warp][st]);
+                    mbar_expect_tx(bar, (uint32_t)nw * 4u);
+                    tma_load_1d(smem_u32(&s_win[warp][st][0]), table + w0, (uint32_t)nw * 4u, bar);
+                }
+                issued++;
+            };
+            const int pre = ng < NS - 1 ? ng : NS - 1;
+            for (int g = 0; g < pre; g++) issue(g);
+            double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+            float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+            for (int g = 0; g < ng; g++) {
+                const int4 rec = __ldg(recs + g);
+                const unsigned st = it % NS;
+                mbar_wait(smem_u32(&s_bar[warp][st]), (it / NS) & 1u);
+                float4 lo[1], hi[1];
+                const float4* w = reinterpret_cast<const float4*>(&s_win[warp][st][0]) + lane;
+                lo[0] = w[0]; hi[0] = w[1];
+                it++;
+                __syncwarp();                                               // every lane has read the stage the next copy overwrites
+                if (g + NS - 1 < ng) issue(g + NS - 1);
+                acc_apply<1>(rec, lo, hi, acc);
+                if (g & 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { dacc[j] += (double)acc[0][j]; acc[0][j] = 0.f; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                dacc[j] += (double)acc[0][j];
+                const int it2 = tb + 4 * lane + j;
+                if (it2 <= int_hi) out[it2] = __double2float_rn(charge * dacc[j]);
+            }
+        }
     }
     if constexpr (FAST == 2) {
         // lane = 8 consecutive ticks, warp = 256 ticks, 4-word groups
@@ -1238,7 +1322,10 @@ static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut,
                 GroupRecT* groups = reinterpret_cast<GroupRecT*>(w.uu);
                 k_mc_sort<<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                 LSB_LAUNCH_CHECK("k_mc_sort");
-                if (lsb_mc_get_lane_ticks() == 8) k_mc_accumulate<TL, 1, 2><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
+                static int use_tma = -1;
+                if (use_tma < 0) { const char* e = getenv("LSB_ACC_TMA"); use_tma = (e && e[0] == '1') ? 1 : 0; }
+                if (use_tma) k_mc_accumulate<TL, 1, 3><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
+                else if (lsb_mc_get_lane_ticks() == 8) k_mc_accumulate<TL, 1, 2><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
                 else k_mc_accumulate<TL, 1, 1><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
                 LSB_LAUNCH_CHECK("k_mc_accumulate");
                 return 0;
