@@ -120,3 +120,31 @@ def test_verbatim_batch_body_equals_fused_chain(cuda):
     assert cuda.equal(out["adc_tot"], res.adc_digit) and cuda.equal(out["current_fractions"], res.current_fractions)
     assert int((out["adc_tot"] > 0).sum()) > 100 and not bool(out["overflow_flag"].any())
     ch.close()
+
+
+def test_spill_runner_empty_and_ragged_inputs(cuda):
+    """no segment at all; every segment outside the TPCs; an event whose batches are all empty; one tiny batch"""
+    from larndsim_b200 import spill
+    mod = lc.load_snapshot("2x2")
+    resp = synth.response_lut(mod.detector)
+    tracks = synth.beam_spill_segments(900, mod.detector, seed=3, n_events=3)
+    tracks["segment_id"] = np.arange(len(tracks)); tracks["file_traj_id"] = tracks["traj_id"]
+    runner = spill.SpillRunner(tracks.dtype, resp, depth=2)
+    none = runner.simulate(tracks[:0].copy(), rand_seed=1)
+    assert none.n_segments == 0 and len(none.packets) == 0 and len(none.packets_mc_ds) == 0
+    far = tracks.copy()
+    for f in ("x_start", "x_end", "x"):
+        far[f] += 1.0e5
+    out = runner.simulate(far, rand_seed=1)
+    assert out.n_segments == 0 and (out.packets["packet_type"] == 0).sum() == 0
+    # event 1 entirely outside: its batches are empty, the other events are unaffected
+    part = tracks.copy()
+    sel = part["event_id"] == 1
+    for f in ("x_start", "x_end", "x"):
+        part[f][sel] += 1.0e5
+    a = runner.simulate(part, rand_seed=1)
+    ref_pk, ref_rows, _, _ = call_by_call(part.copy(), mod, resp, rand_seed=1, tpc_batch_size=runner.tpc_batch_size)
+    assert a.packets.tobytes() == ref_pk.tobytes() and a.packets_mc_ds.tobytes() == ref_rows.tobytes()
+    one = runner.simulate(tracks[:3].copy(), rand_seed=1)
+    assert one.n_segments == 3 and len(one.packets) >= 2
+    runner.close()
