@@ -458,6 +458,15 @@ def run_ours(args, rank, world, local_rank):
     except Exception as exc:
         module0_block = {"error": repr(exc)}
     lc.load_snapshot(CONFIG)
+    try:        # the same kernel on the round-1 workload, for comparison (coarser table: 4.1 instead of 1.75 samples per group record)
+        m0 = module0_block["roofline_by_kernel"]["k_mc_accumulate"]
+        t_s = m0["ms"] * 1e-3
+        l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
+        roofline["same_kernel_on_module0_1e4"] = {"frac_of_fp32_peak": m0["frac"], "achieved_tflops": m0["achieved"],
+                                                  "onchip_TBs": 2.0 * m0["algorithmic_flops"] / t_s / 1e12,
+                                                  "onchip_frac": 2.0 * m0["algorithmic_flops"] / t_s / 1e12 / l1_peak}
+    except Exception:
+        pass
     # ---------------- light path (BASELINE configs[3]) ----------------
     light_block = None
     try:

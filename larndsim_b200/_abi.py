@@ -145,7 +145,8 @@ def linc_layout(dtype):
 
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "csrc", "liblarndsim_b200.so")
+#: LSB_LIB_PATH selects another build of the same library (kernel A/B variants, tools/ab_variants.sh)
+LIB_PATH = os.environ.get("LSB_LIB_PATH") or os.path.join(_PKG_DIR, "csrc", "liblarndsim_b200.so")
 _lib = None
 
 
