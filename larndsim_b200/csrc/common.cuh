@@ -151,9 +151,11 @@ __device__ __forceinline__ unsigned long long rng_next(Rng& r) {
     return result;
 }
 __device__ __forceinline__ float rng_uniform_f32(Rng& r) {
+    // float32((x >> 11) * 2^-53) (numba/cuda/random.py uint64_to_unit_float32): the 53-bit integer is exact in float64 and the
+    // scaling is a power of two, so the only rounding is the one to float32 -- taken here straight from the integer (I2F.F32.U64,
+    // round to nearest even) followed by the exact scaling; bit-identical, and off the FP64 pipe
     unsigned long long x = rng_next(r);
-    double d = (double)(x >> 11) * (1.0 / 9007199254740992.0);
-    return __double2float_rn(d);
+    return __fmul_rn(__ull2float_rn(x >> 11), 1.1102230246251565e-16f);
 }
 __device__ __forceinline__ float rng_normal_f32(Rng& r) {
     float u1 = rng_uniform_f32(r);
