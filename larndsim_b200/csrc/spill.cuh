@@ -23,7 +23,7 @@ struct SpillScratch {                 // per-handle temporaries of the packet st
 
 struct lsb_spill {
     lsb_consts c; lsb_track_layout L;
-    int depth, n_assn;
+    int depth, n_assn, n_sm;
     int serial;                       // 1: every stage of a unit on ONE stream (per-kernel timing)
     lsb_chain* ch[SPILL_MAX_DEPTH];
     SpillScratch sx[SPILL_MAX_DEPTH];
@@ -99,7 +99,8 @@ LSB_EXPORT lsb_spill* lsb_spill_create(const lsb_consts* c, const lsb_track_layo
                                        int32_t Rt, int32_t response_f64, const lsb_readout_tables* rt, int32_t n_assn, int32_t depth) {
     if (!c || !L || !rt || depth < 1 || depth > SPILL_MAX_DEPTH || n_assn < 0) { lsb_fail_arg("spill_create: bad arguments"); return nullptr; }
     lsb_spill* sp = new lsb_spill();
-    sp->c = *c; sp->L = *L; sp->depth = depth; sp->n_assn = n_assn; sp->cap_packets = 0; sp->serial = 0; sp->host_table = nullptr; sp->host_table_cap = 0;
+    sp->c = *c; sp->L = *L; sp->depth = depth; sp->n_assn = n_assn; sp->cap_packets = 0; sp->serial = 0; sp->n_sm = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sp->n_sm, cudaDevAttrMultiProcessorCount, dev); if (sp->n_sm < 1) sp->n_sm = 148; } sp->host_table = nullptr; sp->host_table_cap = 0;
     for (int k = 0; k < SPILL_MAX_DEPTH; k++) { sp->ch[k] = nullptr; sp->ev_export[k] = nullptr; }
     cudaEventCreateWithFlags(&sp->ev_gather, cudaEventDisableTiming);
     for (int k = 0; k < depth; k++) {
@@ -182,7 +183,7 @@ static int spill_export_unit(lsb_spill* sp, int k, const lsb_chain_result* r, lo
                                                     (const long long*)x.offs.p, sp->cap_packets, (lsb_packet*)sp->out_packets.p,
                                                     (long long*)sp->out_src.p, cursor);
     LSB_LAUNCH_CHECK("k_pkt_write");
-    k_pkt_assn<<<148 * 8, 32 * ASSN_WARPS, 0, st>>>(0, (const long long*)sp->out_src.p, A, K, sp->n_assn, (const long long*)x.ev.p,
+    k_pkt_assn<<<sp->n_sm * 8, 32 * ASSN_WARPS, 0, st>>>(0, (const long long*)sp->out_src.p, A, K, sp->n_assn, (const long long*)x.ev.p,
                                                     r->current_fractions, (const long long*)r->track_pixel_map, (const long long*)r->track_pixel_map,
                                                     (char*)sp->out_rows.p, (const long long*)x.total.p, cursor, sp->cap_packets,
                                                     (const long long*)sp->seg_ids.p + gathered_off, (const long long*)sp->traj_ids.p + gathered_off);
