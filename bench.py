@@ -34,13 +34,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CONFIG = "ndlar"
+# the driver runs the defaults; the other BASELINE.json configs are measured by setting these (e.g. configs[2]:
+# LSB_BENCH_CONFIG=2x2 LSB_BENCH_SEGMENTS=200000 LSB_BENCH_TPC_BATCH=2 python bench.py --gpus 4)
+CONFIG = os.environ.get("LSB_BENCH_CONFIG", "ndlar")
 N_SEGMENTS = int(os.environ.get("LSB_BENCH_SEGMENTS", 1_000_000))
 N_EVENTS = int(os.environ.get("LSB_BENCH_EVENTS", 4))
+TPC_BATCH = int(os.environ["LSB_BENCH_TPC_BATCH"]) if os.environ.get("LSB_BENCH_TPC_BATCH") else None
 SEED = 12345
 RAND_SEED = 1
-METRIC = "segments/s quench->ADC (ndlar config, synthetic beam spill of %.0e segments in %d events, (event, TPC pair) batches)" % (N_SEGMENTS, N_EVENTS)
-WORKLOAD = ("ndlar config, synthetic full beam spill (%d segments, %d events, seed %d), charge readout quench->drift->get_pixels->"
+METRIC = "segments/s quench->ADC (%s config, synthetic beam spill of %.0e segments in %d events, (event, TPC pair) batches)" % (CONFIG, N_SEGMENTS, N_EVENTS)
+WORKLOAD = (CONFIG + " config, synthetic full beam spill (%d segments, %d events, seed %d), charge readout quench->drift->get_pixels->"
             "tracks_current_mc->sum_pixel_signals->get_adc_values->digitize->packets, noise on, one fixed spill partitioned by "
             "(event, TPC pair) over the GPUs") % (N_SEGMENTS, N_EVENTS, SEED)
 
@@ -312,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
     snap = lc.snapshot()
     A, K, Tt = int(snap.max_adc_values), int(snap.max_tracks_per_pixel), int(snap.n_time_ticks)
     depth = int(os.environ.get("LSB_BENCH_DEPTH", 3))
-    runner = lspill.SpillRunner(tracks.dtype, response, depth=depth)
+    runner = lspill.SpillRunner(tracks.dtype, response, depth=depth, tpc_batch_size=TPC_BATCH)
     raw = torch.from_numpy(tracks.view(np.uint8).reshape(-1).copy())
     pinned_in = raw.pin_memory()
     n_total = args.warmup + args.steps
@@ -391,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
     kernels = None
     by_kernel = None
     try:
-        prof_runner = lspill.SpillRunner(tracks.dtype, response, depth=1, single_rank=True)      # the other ranks are done: no collective here
+        prof_runner = lspill.SpillRunner(tracks.dtype, response, depth=1, single_rank=True, tpc_batch_size=TPC_BATCH)      # the other ranks are done: no collective here
         prof_runner.set_serial(True)
         d_prof = ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda())
         prof_runner.simulate(ll.DeviceRecords(dtype=tracks.dtype, n=S, buf=pinned_in.cuda()), events=events, rand_seed=RAND_SEED, host_output=False)
