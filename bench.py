@@ -314,7 +314,7 @@ def run_ours(args, rank, world, local_rank):
     events = np.unique(tracks["event_id"])
     snap = lc.snapshot()
     A, K, Tt = int(snap.max_adc_values), int(snap.max_tracks_per_pixel), int(snap.n_time_ticks)
-    depth = int(os.environ.get("LSB_BENCH_DEPTH", 3))
+    depth = int(os.environ.get("LSB_BENCH_DEPTH", 4))
     runner = lspill.SpillRunner(tracks.dtype, response, depth=depth, tpc_batch_size=TPC_BATCH)
     raw = torch.from_numpy(tracks.view(np.uint8).reshape(-1).copy())
     pinned_in = raw.pin_memory()

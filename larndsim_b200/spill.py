@@ -68,7 +68,7 @@ class SpillOutput:
 
 
 class SpillRunner:
-    def __init__(self, track_dtype, response, depth=3, tpc_batch_size=None, event_separator=None, group=None, provider=None,
+    def __init__(self, track_dtype, response, depth=4, tpc_batch_size=None, event_separator=None, group=None, provider=None,
                  single_rank=False):
         """``single_rank=True``: ignore the process group and simulate every unit here (e.g. to check a distributed run)."""
         self._prov = provider or _consts.provider()
