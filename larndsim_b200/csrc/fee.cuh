@@ -129,6 +129,9 @@ __global__ void __launch_bounds__(128) k_fee_rng_chunks(const RngStepTable* __re
 
 struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2* snaps; int NMAX; };
 
+// (Measured and dropped in round 2: a fast path for blocks of ticks without charge and a parallel pre-check of the ticks before the
+// first current -- the response table is non-zero for ~186 us before the arrival of the charge, so a pixel's waveform is non-zero
+// from its first sample window on and there are no quiet stretches worth skipping; profiles/r02_spill_pipeline.md.)
 // The state machine is a serial, data-dependent loop: a global load per draw would expose the full memory
 // latency every tick.  Each thread therefore keeps small windows of its inputs in shared memory
 // ([slot][thread], conflict-free) and refills them with FEE_NBUF / FEE_QBUF independent loads at a time.
@@ -140,12 +143,8 @@ struct FeePre { const double* q_pre; int Tq; const float* nrm; const ulonglong2*
 #define FEE_PPW 8
 #endif
 #define FEE_TRIG_PIX (FEE_TRIG_TPB / 32 * FEE_PPW)          // pixels per block
-#ifndef FEE_NBUF
 #define FEE_NBUF 64         // staged normals per pixel (two per tick); 256 / 128 was measured: 2.55 against 1.69 ms per module0 batch
-#endif
-#ifndef FEE_QBUF
 #define FEE_QBUF 32         // staged FIR values per pixel
-#endif
 #ifndef FEE_WBLK
 #define FEE_WBLK 8          // ticks per block of the watching loop
 #endif
@@ -284,16 +283,6 @@ __global__ void __launch_bounds__(FEE_TRIG_TPB) k_fee_trigger(FeeParams fp, FeeP
                                 qn[u] = (su == 0.0 ? 0.0 : (double)nb[(2 * (k + u)) * FEE_TRIG_PIX] * su) * fp.e;
                                 const double disc_noise = (sd == 0.0 ? 0.0 : (double)nb[(2 * (k + u) + 1) * FEE_TRIG_PIX] * sd) * fp.e;
                                 rhs[u] = thr + disc_noise;
-                            }
-                            // quiet block (no induced charge in these ticks: q == +0.0 exactly, the sums do not move): the
-                            // crossing tests are independent of each other -- no serial add chain -- and almost never fire
-                            bool quiet = true, cross = false;
-#pragma unroll
-                            for (int u = 0; u < FEE_WBLK; u++) { quiet = quiet && qv[u] == 0.0; cross = cross || (q_sum + qn[u] >= rhs[u]); }
-                            if (quiet && !cross) {
-                                adc_busy -= adc_busy < FEE_WBLK ? adc_busy : FEE_WBLK;
-                                k += FEE_WBLK;
-                                continue;
                             }
 #pragma unroll
                             for (int u = 0; u < FEE_WBLK; u++) {
