@@ -67,6 +67,8 @@ struct McParams {
     // sync-free operation (fused chain): the sample total stays on the device; every kernel after the scan
     // returns at once if it exceeds the capacity the caller provisioned (and *overflow is raised)
     const long long* total_dev; long long cap; int* overflow;
+    unsigned int* lohi;         // per live sample: valid ticks lo | hi << 16 (T < 65536); with offs32 it is all the edge path needs, so the
+                                // 24-byte SampleRec is written (and read) for IRREGULAR samples only
     unsigned long long* diag;   // optional device counters {group records, edge (sample, tick) pairs, irregular samples}
     unsigned long long* npairs; // device counter of (segment, pixel) pairs that hold a pixel id (S * P-bar of SURVEY 8d), or null
     unsigned long long* nfma; // device counter of (sample, tick) pairs that pass every test of detsim.py:299,333,341-344 (N_fma of SURVEY 8d), or null
@@ -406,8 +408,9 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int pos = n_live + __popc(m & ((1u << lane) - 1));
-            out[pos] = r;
+            if (r.shift == SHIFT_IRREGULAR) out[pos] = r;
             out32[pos] = (r.shift == SHIFT_IRREGULAR) ? OFF_IRREGULAR : r.rowoff + r.shift;
+            p.lohi[g.sample_off + pos] = (unsigned int)r.lo | ((unsigned int)r.hi << 16);
             if (r.shift != SHIFT_IRREGULAR) { int_lo = r.lo > int_lo ? r.lo : int_lo; int_hi = r.hi < int_hi ? r.hi : int_hi; }
             else n_irr++;
             uni_lo = r.lo < uni_lo ? r.lo : uni_lo; uni_hi = r.hi > uni_hi ? r.hi : uni_hi;
@@ -1134,9 +1137,11 @@ __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long 
                 int ns = n_live - c0 < ACC_CHUNK ? n_live - c0 : ACC_CHUNK;
                 __syncthreads();
                 for (int q = tid; q < ns; q += ACC_TPB) {
-                    const SampleRec r = samples[soff + c0 + q];
+                    const int off = offs32[soff + c0 + q];
+                    const unsigned int lh = p.lohi[soff + c0 + q];
+                    const int lo_s = (int)(lh & 0xffffu), hi_s = (int)(lh >> 16);
                     // irregular samples never pass the range test
-                    s_erec[q] = r.shift == SHIFT_IRREGULAR ? make_int4(0, 0x3fffffff, 0, 0) : make_int4(r.rowoff + r.shift, r.lo, r.hi - r.lo, 0);
+                    s_erec[q] = off == OFF_IRREGULAR ? make_int4(0, 0x3fffffff, 0, 0) : make_int4(off, lo_s, hi_s - lo_s, 0);
                 }
                 __syncthreads();
                 if (!active) continue;
@@ -1180,7 +1185,10 @@ __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long 
             for (int c0 = 0; c0 < n_live; c0 += ACC_TPB) {
                 int ns = n_live - c0 < ACC_TPB ? n_live - c0 : ACC_TPB;
                 __syncthreads();
-                if (tid < ns) s_rec[tid] = samples[soff + c0 + tid];
+                if (tid < ns) {
+                    if (offs32[soff + c0 + tid] == OFF_IRREGULAR) s_rec[tid] = samples[soff + c0 + tid];
+                    else s_rec[tid].shift = 0;                       // regular: skipped below
+                }
                 __syncthreads();
                 if (!active) continue;
                 for (int s = 0; s < ns; s++) {
@@ -1259,9 +1267,9 @@ __global__ void k_mc_replay(McParams p, const PairRec* __restrict__ pairs, const
 struct McWs {
     PairRec* pairs; uint32_t* nsamp; long long* offs; long long* block_sums; long long* total;
     int* perm; int* bucket;   // pairs ordered by descending sample count (k_mc_uniforms), 2 x MC_NBUCKET counters
-    SampleRec* samples; int* offs32; SampleU* uu; long long sample_cap;
+    SampleRec* samples; int* offs32; unsigned int* lohi; SampleU* uu; long long sample_cap;
 };
-#define MC_BYTES_PER_SAMPLE ((long long)(sizeof(SampleRec) + 4 + sizeof(SampleU)))
+#define MC_BYTES_PER_SAMPLE ((long long)(sizeof(SampleRec) + 4 + 4 + sizeof(SampleU)))
 static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 static inline long long mc_fixed_bytes(long long npair) {
     return align_up(npair * (long long)sizeof(PairRec), 256) + align_up(npair * 4, 256) + align_up(npair * 8, 256) +
@@ -1269,12 +1277,12 @@ static inline long long mc_fixed_bytes(long long npair) {
 }
 LSB_EXPORT int64_t lsb_tracks_current_mc_workspace_bytes(int64_t S, int32_t P, int64_t max_steps_total) {
     return mc_fixed_bytes(S * (long long)P) + align_up(max_steps_total * (long long)sizeof(SampleRec), 256) +
-           align_up(max_steps_total * 4, 256) + align_up(max_steps_total * (long long)sizeof(SampleU), 256) + 1024;
+           2 * align_up(max_steps_total * 4, 256) + align_up(max_steps_total * (long long)sizeof(SampleU), 256) + 2048;
 }
 static inline bool mc_carve(void* ws, long long bytes, long long npair, McWs& w) {
     char* p = (char*)ws;
     long long fixed = mc_fixed_bytes(npair);
-    if (bytes < fixed + MC_BYTES_PER_SAMPLE * 64 + 1024) return false;
+    if (bytes < fixed + MC_BYTES_PER_SAMPLE * 64 + 2048) return false;
     w.pairs = (PairRec*)p; p += align_up(npair * (long long)sizeof(PairRec), 256);
     w.nsamp = (uint32_t*)p; p += align_up(npair * 4, 256);
     w.offs = (long long*)p; p += align_up(npair * 8, 256);
@@ -1283,9 +1291,10 @@ static inline bool mc_carve(void* ws, long long bytes, long long npair, McWs& w)
     w.perm = (int*)p; p += align_up(npair * 4, 256);
     w.bucket = (int*)p; p += 1024;
     long long rest = bytes - fixed;
-    w.sample_cap = (rest - 1024) / MC_BYTES_PER_SAMPLE;
+    w.sample_cap = (rest - 2048) / MC_BYTES_PER_SAMPLE;
     w.samples = (SampleRec*)p; p += align_up(w.sample_cap * (long long)sizeof(SampleRec), 256);
     w.offs32 = (int*)p; p += align_up(w.sample_cap * 4, 256);
+    w.lohi = (unsigned int*)p; p += align_up(w.sample_cap * 4, 256);
     w.uu = (SampleU*)p;
     return w.sample_cap > 0;
 }
@@ -1411,6 +1420,7 @@ static int mc_run_range(const Layout& L, const void* tracks, const int32_t* pixe
     LSB_LAUNCH_CHECK("k_mc_bucket_scatter");
     k_mc_uniforms<<<lsb_blocks(npair, UNI_TPB), UNI_TPB, 0, st>>>(p, w.pairs, w.perm, w.uu, rng);
     LSB_LAUNCH_CHECK("k_mc_uniforms");
+    p.lohi = w.lohi;
     k_mc_sampler<<<lsb_blocks(npair, SMP_WARPS), 32 * SMP_WARPS, 0, st>>>(p, w.pairs, w.uu, w.samples, w.offs32);
     LSB_LAUNCH_CHECK("k_mc_sampler");
     if (f64) return mc_launch_accumulate<double>(p, w, (const double*)response, nullptr, signals, st);
@@ -1438,6 +1448,7 @@ LSB_EXPORT int lsb_tracks_current_mc(const lsb_consts* c, const lsb_track_layout
     LSB_REQUIRE(tracks && pixels && signals && response && rng_states && workspace, "tracks_current_mc: null pointer");
     LSB_REQUIRE(Rx > 0 && Ry > 0 && Rt > 0 && (long long)Rx * Ry * Rt < 2147483647LL, "tracks_current_mc: bad response shape");
     LSB_REQUIRE(rng_mode == 0 || rng_mode == 1, "tracks_current_mc: rng_mode must be 0 (cloud) or 1 (replay)");
+    LSB_REQUIRE(rng_mode == 1 || T < 65536, "tracks_current_mc: more than 65535 ticks per waveform");
     if (rng_stride <= 0) rng_stride = S;
     LSB_REQUIRE(n_rng >= (S - 1) + rng_stride * (long long)(P - 1) + 1, "tracks_current_mc: rng_states too short");
     if (require_current_fields(L, true)) return -1;
@@ -1472,6 +1483,7 @@ static int mc_run_nosync(const lsb_consts* c, const lsb_track_layout* L, const v
                          unsigned long long* npairs, unsigned long long* diag, cudaStream_t st) {
     if (S == 0 || P == 0 || T == 0) return 0;
     if (require_current_fields(L, true)) return -1;
+    LSB_REQUIRE(T < 65536, "tracks_current_mc: more than 65535 ticks per waveform");
     int rc = lsb_upload_consts(c, st); if (rc) return rc;
     McParams p;
     p.S = S; p.seg0 = 0; p.rng_stride = rng_stride; p.P = P; p.T = T; p.Rx = Rx; p.Ry = Ry; p.Rt = Rt;
