@@ -56,6 +56,38 @@ def assign_units(sizes, world):
     return out
 
 
+def file_order_blocks(unit_packets, plan, n_event_packets, n_tpc_batches):
+    """Where every block of packets goes in the output file (the order in which the reference's sequential loop appends them:
+    per event its between-batch packets, then its batches in TPC-group order).  ``unit_packets[u]``: packets of unit u;
+    ``plan[r]``: ascending units of rank r (its output buffer holds them back to back); ``n_event_packets[e]``: between-batch
+    packets of event e.  Returns ``(blocks, n_total)`` with blocks = list of ``(source, source_offset, dest_offset, count)``,
+    source = rank number or -1 for the event-level packets (offsets count packets).  Pure host logic: every rank can compute it."""
+    n_units = len(unit_packets)
+    owner = {}
+    for r, lst in enumerate(plan):
+        for u in lst:
+            owner[int(u)] = r
+    run = [0] * len(plan)
+    blocks, pos, ev_off = [], 0, 0
+    n_events = n_units // n_tpc_batches if n_tpc_batches else 0
+    for e in range(n_events):
+        ne = int(n_event_packets[e]) if e < len(n_event_packets) else 0
+        if ne:
+            blocks.append((-1, ev_off, pos, ne))
+            pos += ne
+            ev_off += ne
+        for b in range(n_tpc_batches):
+            u = e * n_tpc_batches + b
+            n = int(unit_packets[u])
+            if n == 0:
+                continue
+            r = owner[u]
+            blocks.append((r, run[r], pos, n))
+            run[r] += n
+            pos += n
+    return blocks, pos
+
+
 class SpillOutput:
     """What rank 0 holds after a spill (other ranks: ``packets is None``)."""
 
@@ -261,30 +293,18 @@ class SpillRunner:
         out.n_packets = n_total
         d_pk = self._buf("final_pk", max(n_total, 1) * pkb)
         d_rw = self._buf("final_rw", max(n_total, 1) * rowb)
-        srcs_p, srcs_r, dsts, nbs = [], [], [], []
-        run_off = {r: 0 for r in range(self.world)}
-        owner = np.full(nU, -1, dtype=np.int64)
-        for r in range(self.world):
-            owner[plan[r]] = r
         ev_blob = np.concatenate(evp) if n_evp else np.zeros(0, dtype=_p.PACKET_DTYPE)
         d_evp = torch.from_numpy(ev_blob.view(np.uint8).reshape(-1)).cuda() if n_evp else None
         ev_rows = _fee._no_truth_rows(1)
-        pos, ev_off, ev_positions = 0, 0, []
-        for e in range(len(events)):
-            ne = len(evp[e])
-            if ne:
-                srcs_p.append(d_evp.data_ptr() + ev_off * pkb); srcs_r.append(0); dsts.append(pos); nbs.append(ne)
-                ev_positions.append((pos, ne))
-                pos += ne; ev_off += ne
-            for b in range(nB):
-                u = e * nB + b
-                n = int(counts_h[u])
-                if n == 0:
-                    continue
-                r = int(owner[u])
-                srcs_p.append(src_pk[r] + run_off[r] * pkb); srcs_r.append(src_rw[r] + run_off[r] * rowb); dsts.append(pos); nbs.append(n)
-                run_off[r] += n
-                pos += n
+        blocks, pos = file_order_blocks(counts_h, plan, [len(x) for x in evp], nB)
+        srcs_p, srcs_r, dsts, nbs, ev_positions = [], [], [], [], []
+        for src, soff, dpos, n in blocks:
+            if src < 0:
+                srcs_p.append(d_evp.data_ptr() + soff * pkb); srcs_r.append(0)
+                ev_positions.append((dpos, n))
+            else:
+                srcs_p.append(src_pk[src] + soff * pkb); srcs_r.append(src_rw[src] + soff * rowb)
+            dsts.append(dpos); nbs.append(n)
         assert pos == n_total
         self._copy_blocks(srcs_p, dsts, nbs, pkb, d_pk)
         keep_r = [(s, dpos, n) for s, dpos, n in zip(srcs_r, dsts, nbs) if s]

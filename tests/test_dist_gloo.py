@@ -148,3 +148,68 @@ def test_unit_outputs_come_back_in_file_order_world2_gloo():
     # single process: same call, no process group
     ids1, recs1 = ldist.gather_unit_records([4, 2, 7], [_unit_records(u) for u in (4, 2, 7)], REC)
     assert ids1 == [2, 4, 7] and np.array_equal(np.concatenate(recs1), np.concatenate([_unit_records(u) for u in (2, 4, 7)]))
+
+
+def _spill_worker(rank, world, port, q):
+    """the exchange + file-order assembly of spill.SpillRunner.simulate, steps (5)-(7), on host tensors over gloo"""
+    import numpy as np
+    from larndsim_b200 import spill
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    nB, n_events = 5, 3
+    sizes = rng.integers(0, 40, nB * n_events)
+    sizes[[2, 9]] = 0
+    n_pk = np.where(sizes > 0, sizes * 2 + 1, 0)                          # packets per unit (a function of the unit only)
+    n_evp = [2, 0, 3]
+    plan = spill.assign_units(sizes, world)
+    mine = plan[rank]
+
+    def unit_bytes(u):                                                    # recognisable content: (unit, running index)
+        return np.stack([np.full(n_pk[u], u, dtype=np.int64), np.arange(n_pk[u], dtype=np.int64)], axis=1)
+    local = np.concatenate([unit_bytes(u) for u in mine]) if len(mine) else np.zeros((0, 2), dtype=np.int64)
+    counts = torch.zeros(len(sizes), dtype=torch.int64)
+    counts[torch.tensor(mine, dtype=torch.int64)] = torch.from_numpy(n_pk[mine])
+    dist.all_reduce(counts)
+    assert np.array_equal(counts.numpy(), n_pk)
+    per_rank = [int(n_pk[plan[r]].sum()) for r in range(world)]
+    bufs = {rank: torch.from_numpy(local)}
+    if rank == 0:
+        works = []
+        for r in range(1, world):
+            bufs[r] = torch.zeros((per_rank[r], 2), dtype=torch.int64)
+            works.append(dist.irecv(bufs[r], r))
+        for w in works:
+            w.wait()
+    else:
+        dist.isend(torch.from_numpy(local), 0).wait()
+    if rank == 0:
+        blocks, total = spill.file_order_blocks(counts.numpy(), plan, n_evp, nB)
+        ev_blob = np.stack([np.full(sum(n_evp), -1, dtype=np.int64), np.arange(sum(n_evp), dtype=np.int64)], axis=1)
+        out = np.zeros((total, 2), dtype=np.int64)
+        for src, soff, dpos, n in blocks:
+            out[dpos:dpos + n] = ev_blob[soff:soff + n] if src < 0 else bufs[src].numpy()[soff:soff + n]
+        # the sequential single-process order
+        want, e_off = [], 0
+        for e in range(n_events):
+            want.append(ev_blob[e_off:e_off + n_evp[e]]); e_off += n_evp[e]
+            for b in range(nB):
+                want.append(unit_bytes(e * nB + b))
+        q.put(bool(np.array_equal(out, np.concatenate(want))) and total == int(n_pk.sum()) + sum(n_evp))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_spill_exchange_and_file_order_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_spill_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
