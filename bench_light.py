@@ -136,4 +136,5 @@ def run(peak_hbm, steps=3, n_segments=20000, n_true=0):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-    print(json.dumps(run(6451.0, steps=2, n_segments=n), indent=1))
+    n_true = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    print(json.dumps(run(6451.0, steps=2, n_segments=n, n_true=n_true), indent=1))
