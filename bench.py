@@ -426,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
         rk = by_kernel.get(top_name, {})
         roofline = {"kernel": top_name, "bound": rk.get("bound"), "achieved": rk.get("achieved"), "peak": rk.get("peak"), "unit": rk.get("unit"),
                     "frac": rk.get("frac"), "traffic": traffic,
-                    "traffic_source": (tj.get("_source") if traffic else None) if os.path.exists(tpath) else None,
+                    "traffic_source": ((ncu.get("_source") or tj.get("_source")) if traffic else None) if os.path.exists(tpath) else None,
                     "timed": "CUDA events on the launching stream around every launch of the kernel: the whole spill on rank 0, one "
                              "batch at a time on one stream (%d launches)" % top_cnt,
                     "share_of_kernel_time": top_ms / total_kernel_ms, "ms_per_launch": top_ms / max(top_cnt, 1), "launches": top_cnt,
@@ -439,7 +439,9 @@ def run_ours(args, rank, world, local_rank):
             onchip = 4.0 * pst["n_fma"] / t_s / 1e12
             roofline["onchip"] = {"what": "table words the algorithmic formulation reads from L1 / shared memory: 4 B x N_fma", "achieved": onchip,
                                   "peak": 148 * 128 * sm_mhz * 1e6 / 1e12, "unit": "TB/s", "frac": onchip / (148 * 128 * sm_mhz * 1e6 / 1e12),
-                                  "ncu_l1tex_throughput_pct": ncu.get("l1tex_throughput_pct"), "ncu_issue_active_pct": ncu.get("issue_active_pct")}
+                                  "ncu_l1tex_throughput_pct": ncu.get("l1tex_throughput_pct"), "ncu_issue_active_pct": ncu.get("issue_active_pct"),
+                                  "ncu_lts_throughput_pct": ncu.get("lts_throughput_pct"), "ncu_l2_to_l1_TBs": ncu.get("l2_to_l1_TBs"),
+                                  "ncu_note": ncu.get("_source")}
             mc_ms = sum(prof[k][1] for k in ("k_mc_pairs", "k_mc_uniforms", "k_mc_sampler", "k_mc_sort", "k_mc_accumulate", "k_mc_fused") if k in prof)
             flops = 2.0 * pst["n_fma"] + 330.0 * pst["n_samples"]
             fp32_peak = FP32_LANES * 2 * sm_mhz * 1e6 / 1e12

@@ -469,16 +469,7 @@ __device__ __forceinline__ void group_store(GroupRecT* dst, int q, const int (&c
 #endif
 #define SORT_MAXKEYS 512
 template <int NR>
-__device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int n, int key_add, int* s_buf, GroupRecT* __restrict__ out,
-                                               int lane) {
-    int v[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const int g = r * 32 + lane;
-        int k = g < n ? keys[g] : 2147483647;
-        if (k != OFF_IRREGULAR && k != 2147483647) k += key_add;
-        v[r] = k;
-    }
+__device__ __forceinline__ void warp_bitonic_to_smem(int (&v)[NR], int* s_buf, int lane) {
 #pragma unroll
     for (int k = 2; k <= 32 * NR; k <<= 1) {
 #pragma unroll
@@ -508,6 +499,19 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
 #pragma unroll
     for (int r = 0; r < NR; r++) { const int pos = lane * NR + r; s_buf[pos + (pos >> 5)] = v[r]; }
     __syncwarp();
+}
+template <int NR>
+__device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int n, int key_add, int* s_buf, GroupRecT* __restrict__ out,
+                                               int lane) {
+    int v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const int g = r * 32 + lane;
+        int k = g < n ? keys[g] : 2147483647;
+        if (k != OFF_IRREGULAR && k != 2147483647) k += key_add;
+        v[r] = k;
+    }
+    warp_bitonic_to_smem<NR>(v, s_buf, lane);
     // group heads: position whose aligned ACC_GW-word block differs from its predecessor's.  Runs are measured with ballots
     // (32 positions at a time); the last run of a row stays "pending" (warp-uniform registers) because it may continue in
     // the next row.
@@ -562,10 +566,74 @@ __device__ __forceinline__ int warp_sort_group(const int* __restrict__ keys, int
     return ng;
 }
 
+
+// ---- run records of the phase-aligned accumulate path (LSB_ACC_ALIGNED, FAST == 4) ---------------------------------------------------
+// The keys are ordered by (key & 3, key >> 2): all offsets of one alignment class d = off mod 4 are neighbours, ascending in the
+// float4 index q.  One 4-byte record q << 10 | count per DISTINCT offset (count <= 512 = one chunk); a chunk is
+//   [header: c1 | c2 << 10 | c3 << 20, n_rec] [n_rec records], class d = records [c_d, c_(d+1)), c_0 = 0, c_4 = n_rec.
+// The words of a pair start at the first 16-byte boundary of its slice of the uniforms buffer (24 bytes per sample):
+// 2 (alignment) + 2 (header) + n_rec <= 6 n words.
+#define RUN_CLASS_SHIFT 28
+#define RUN_COUNT_BITS 10
+#define RUN_MAX_WORDS (1LL << (32 - RUN_COUNT_BITS + 2))           // offsets + ticks representable in a record
+__device__ __forceinline__ const int* run_stream(const void* groups, long long sample_off) {
+    return reinterpret_cast<const int*>((reinterpret_cast<uintptr_t>(groups) + (uintptr_t)sample_off * 24u + 15u) & ~(uintptr_t)15u);
+}
+template <int NR>
+__device__ __forceinline__ int warp_sort_runs(const int* __restrict__ keys, int n, int key_add, int* s_buf, int* __restrict__ out, int lane) {
+    int v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const int g = r * 32 + lane;
+        int k = g < n ? keys[g] : 2147483647;
+        if (k != OFF_IRREGULAR && k != 2147483647) { k += key_add; k = ((k & 3) << RUN_CLASS_SHIFT) | (k >> 2); }
+        v[r] = k;
+    }
+    warp_bitonic_to_smem<NR>(v, s_buf, lane);
+    int key[NR];
+    unsigned headbits = 0;
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const int pos = r * 32 + lane;
+        key[r] = s_buf[pos + (pos >> 5)];
+        const int prev = pos > 0 ? s_buf[pos - 1 + ((pos - 1) >> 5)] : OFF_IRREGULAR;
+        if (pos < n && key[r] != OFF_IRREGULAR && key[r] != prev) headbits |= 1u << r;
+    }
+    __syncwarp();                                                      // every key is in registers: s_buf becomes {head position, key}
+    int nrec = 0, c1 = 0, c2 = 0, c3 = 0;
+    const unsigned below = (1u << lane) - 1u;
+    int* s_pos = s_buf;                                                // [0, 256]: packed two 16-bit positions would do; positions <= 512
+    // positions and keys of the heads: positions in the low half-words of s_buf[0..], keys go straight to the output
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const bool head = (headbits >> r) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        const int cls = key[r] >> RUN_CLASS_SHIFT;
+        c1 += __popc(__ballot_sync(0xffffffffu, head && cls < 1));
+        c2 += __popc(__ballot_sync(0xffffffffu, head && cls < 2));
+        c3 += __popc(__ballot_sync(0xffffffffu, head && cls < 3));
+        if (head) {
+            const int idx = nrec + __popc(m & below);
+            s_pos[idx] = r * 32 + lane;
+            out[2 + idx] = (key[r] & ((1 << RUN_CLASS_SHIFT) - 1)) << RUN_COUNT_BITS;
+        }
+        nrec += __popc(m);
+    }
+    if (lane == 0) { s_pos[nrec] = n; out[0] = c1 | (c2 << 10) | (c3 << 20); out[1] = nrec; }   // irregular keys sort first: runs end at n
+    __syncwarp();
+    for (int i = lane; i < nrec; i += 32) out[2 + i] |= s_pos[i + 1] - s_pos[i];
+    __syncwarp();
+    return 2 + nrec + (nrec & 1);                                      // the next chunk header stays 8-byte aligned
+}
+
 #ifndef SORT_MINB
 #define SORT_MINB 12
 #endif
-__global__ void __launch_bounds__(32 * SORT_WARPS, SORT_MINB) k_mc_sort(McParams p, PairRec* __restrict__ pairs, const int* __restrict__ offs32,
+#ifndef SORT_RUNS_MINB
+#define SORT_RUNS_MINB 10
+#endif
+template <bool RUNS>
+__global__ void __launch_bounds__(32 * SORT_WARPS, RUNS ? SORT_RUNS_MINB : SORT_MINB) k_mc_sort(McParams p, PairRec* __restrict__ pairs, const int* __restrict__ offs32,
                                                              GroupRecT* __restrict__ groups) {
     MC_GUARD(p);
     __shared__ int s_buf[SORT_WARPS][SORT_MAXKEYS + SORT_MAXKEYS / 32];
@@ -579,6 +647,17 @@ __global__ void __launch_bounds__(32 * SORT_WARPS, SORT_MINB) k_mc_sort(McParams
     int ng = 0;
     if (n_reg > 0 && gp->int_lo <= gp->int_hi) {
         const int* keys = offs32 + gp->sample_off;
+        if constexpr (RUNS) {
+            int* out = const_cast<int*>(run_stream(groups, gp->sample_off));
+            for (int c0 = 0; c0 < n_live; c0 += SORT_MAXKEYS) {
+                const int n = n_live - c0 < SORT_MAXKEYS ? n_live - c0 : SORT_MAXKEYS;
+                if (n <= 32) ng += warp_sort_runs<1>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
+                else if (n <= 64) ng += warp_sort_runs<2>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
+                else if (n <= 128) ng += warp_sort_runs<4>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
+                else if (n <= 256) ng += warp_sort_runs<8>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
+                else ng += warp_sort_runs<16>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
+            }
+        } else {
         GroupRecT* out = groups + gp->sample_off;         // <= one record per sample
         for (int c0 = 0; c0 < n_live; c0 += SORT_MAXKEYS) {
             const int n = n_live - c0 < SORT_MAXKEYS ? n_live - c0 : SORT_MAXKEYS;
@@ -587,6 +666,7 @@ __global__ void __launch_bounds__(32 * SORT_WARPS, SORT_MINB) k_mc_sort(McParams
             else if (n <= 128) ng += warp_sort_group<4>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
             else if (n <= 256) ng += warp_sort_group<8>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
             else ng += warp_sort_group<16>(keys + c0, n, key_add, s_buf[warp], out + ng, lane);
+        }
         }
     }
     if (lane == 0) {
@@ -894,6 +974,73 @@ __device__ __forceinline__ void acc_gather8(const float* __restrict__ lut, int n
     for (int j = 0; j < 8; j++) dacc[j] += (double)acc[j];
 }
 
+
+// ---- phase-aligned interior path (FAST == 4) --------------------------------------------------------------------------------------
+// The grouped path above fetches an 8-word window per lane and group because an offset 4q + d with d != 0 straddles two aligned
+// float4s: 2 table words travel from L1 to the registers for every tick of a group, used or not (ncu: the L1 data pipe is the
+// limit, profiles/r02_top_kernels_ndlar_unit.md).  Here the LANES move instead of the window: for the offsets of alignment class d
+// a lane accumulates the four ticks 4 lane - d .. 4 lane - d + 3 of the block, so the words it needs, LUT[4q + d + tick], are the
+// ALIGNED float4 q + lane -- one LDG.128 and four FFMA per distinct offset, 1 word per tick.  A warp's 32 lanes cover the ticks
+// [-d, 128 - d) of its block; blocks are 124 ticks long, so every class covers the block whatever d is (3 % of the lanes' work is
+// redundant) and nothing crosses warps.  When a class is finished its sums move to the lanes that own the ticks in the output
+// (tick 4 lane + i comes from accumulator (i + d) & 3 of the same lane or of lane + 1: d shuffles).
+#define ACC_AL_BLOCK 124
+#ifndef ACC_AL_MINB
+#define ACC_AL_MINB 8
+#endif
+template <int D>
+__device__ __forceinline__ void acc_class_flush(double (&cacc)[4], double (&dacc)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double v = cacc[(i + D) & 3];
+        if (i + D >= 4) v = __shfl_down_sync(0xffffffffu, v, 1);
+        dacc[i] += v;
+        }
+#pragma unroll
+    for (int j = 0; j < 4; j++) cacc[j] = 0.0;
+}
+__device__ __forceinline__ void acc_run_apply(const float4* __restrict__ lut4, int n4m1, int QL, int rec, float& x, float& y, float& z, float& w) {
+    const float4 t = __ldg(lut4 + min((int)((unsigned)rec >> RUN_COUNT_BITS) + QL, n4m1));
+    // the count as a float without a conversion: 2^23 + c has c in its low mantissa bits
+    const float c = __fadd_rn(__int_as_float(0x4B000000 | (rec & ((1 << RUN_COUNT_BITS) - 1))), -8388608.0f);
+    x = __fmaf_rn(c, t.x, x); y = __fmaf_rn(c, t.y, y); z = __fmaf_rn(c, t.z, z); w = __fmaf_rn(c, t.w, w);
+}
+__device__ __forceinline__ void acc_run_apply4(const float4* __restrict__ lut4, int n4m1, int QL, const int4& a, float& x, float& y, float& z, float& w) {
+    acc_run_apply(lut4, n4m1, QL, a.x, x, y, z, w); acc_run_apply(lut4, n4m1, QL, a.y, x, y, z, w);
+    acc_run_apply(lut4, n4m1, QL, a.z, x, y, z, w); acc_run_apply(lut4, n4m1, QL, a.w, x, y, z, w);
+}
+__device__ __forceinline__ void acc_class_run(const float4* __restrict__ lut4, int n4m1, const int* __restrict__ recs, int n, int QL,
+                                              double (&cacc)[4]) {
+    // records one at a time up to the first 16-byte boundary, then eight per trip (two LDG.128 of records fetched one trip ahead,
+    // eight LDG.128 of the table, 32 FFMA, one fold of the <= 8-term float32 sums into float64), then the rest.
+    // Measured and dropped (B200, tracks_current_mc stage of one ND-LAr unit, 8.30 ms as written): `prefetch.global.L1` of the next
+    // trip's table lines 11.1 ms; quads masked at both ends instead of the single-record head and tail 8.50; 80 registers / 6 CTAs
+    // per SM 9.35; 48 registers / 10 CTAs per SM (spills) 10.3.
+    int r = 0;
+    float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
+    const int lead = (int)((16u - ((unsigned)reinterpret_cast<uintptr_t>(recs) & 15u)) & 15u) >> 2;
+    for (; r < n && r < lead; r++) acc_run_apply(lut4, n4m1, QL, __ldg(recs + r), x, y, z, w);
+    if (r > 0) { cacc[0] += (double)x; cacc[1] += (double)y; cacc[2] += (double)z; cacc[3] += (double)w; x = y = z = w = 0.f; }
+    if (r + 8 <= n) {
+        int4 a = __ldg(reinterpret_cast<const int4*>(recs + r)), b = __ldg(reinterpret_cast<const int4*>(recs + r + 4));
+        for (; r + 8 <= n; r += 8) {
+            int4 na = a, nb = b;
+            if (r + 16 <= n) { na = __ldg(reinterpret_cast<const int4*>(recs + r + 8)); nb = __ldg(reinterpret_cast<const int4*>(recs + r + 12)); }
+            acc_run_apply4(lut4, n4m1, QL, a, x, y, z, w);
+            acc_run_apply4(lut4, n4m1, QL, b, x, y, z, w);
+            cacc[0] += (double)x; cacc[1] += (double)y; cacc[2] += (double)z; cacc[3] += (double)w; x = y = z = w = 0.f;
+            a = na; b = nb;
+        }
+    }
+    if (r + 4 <= n) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(recs + r));
+        acc_run_apply4(lut4, n4m1, QL, a, x, y, z, w);
+        r += 4;
+    }
+    for (; r < n; r++) acc_run_apply(lut4, n4m1, QL, __ldg(recs + r), x, y, z, w);
+    cacc[0] += (double)x; cacc[1] += (double)y; cacc[2] += (double)z; cacc[3] += (double)w;
+}
+
 template <typename TL, int STRIDE, int FAST>
 __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long pr, const PairRec* __restrict__ pairs,
                                                    const SampleRec* __restrict__ samples,
@@ -973,6 +1120,35 @@ __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long 
                 }
         }
 #endif
+    }
+    if constexpr (FAST == 4) {
+        constexpr int NW = ACC_TPB / 32;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int n_items = gp->n_groups;
+        const float4* lut4 = reinterpret_cast<const float4*>(lut);
+        const int n4m1 = (int)(((long long)p.Rx * p.Ry * p.Rt) >> 2) - 1;
+        const int* stream = run_stream(groups, soff);
+        for (int tb = int_lo + ACC_AL_BLOCK * warp; tb <= int_hi && n_items > 0; tb += ACC_AL_BLOCK * NW) {
+            const int QL = ((tb - int_lo) >> 2) + lane;
+            double dacc[4] = {0.0, 0.0, 0.0, 0.0}, cacc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int item = 0; item < n_items;) {
+                const int2 hdr = __ldg(reinterpret_cast<const int2*>(stream + item));
+                const int* recs = stream + item + 2;
+                const int c1 = hdr.x & 1023, c2 = (hdr.x >> 10) & 1023, c3 = (hdr.x >> 20) & 1023, c4 = hdr.y;
+                if (c1 > 0) { acc_class_run(lut4, n4m1, recs, c1, QL, cacc); acc_class_flush<0>(cacc, dacc); }
+                if (c2 > c1) { acc_class_run(lut4, n4m1, recs + c1, c2 - c1, QL, cacc); acc_class_flush<1>(cacc, dacc); }
+                if (c3 > c2) { acc_class_run(lut4, n4m1, recs + c2, c3 - c2, QL, cacc); acc_class_flush<2>(cacc, dacc); }
+                if (c4 > c3) { acc_class_run(lut4, n4m1, recs + c3, c4 - c3, QL, cacc); acc_class_flush<3>(cacc, dacc); }
+                item += 2 + c4 + (c4 & 1);                                  // headers stay 8-byte aligned
+            }
+            if (lane < 31) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int it = tb + 4 * lane + j;
+                    if (it <= int_hi) out[it] = __double2float_rn(charge * dacc[j]);
+                }
+            }
+        }
     }
     if constexpr (FAST == 3) {
         constexpr int NW = ACC_TPB / 32, NS = ACC_TMA_STAGES;
@@ -1209,7 +1385,7 @@ __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long 
 // one CTA per (segment, pixel) pair.  (A persistent grid fetching pairs from a device counter was measured on B200: 3.6 % slower
 // alone -- an atomic and two barriers per pair -- and no better with three batches in flight, profiles/r02_spill_pipeline.md.)
 template <typename TL, int STRIDE, int FAST>
-__global__ void __launch_bounds__(ACC_TPB, FAST == 1 ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
+__global__ void __launch_bounds__(ACC_TPB, FAST == 4 ? ACC_AL_MINB : FAST == 1 ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
                                                            const SampleRec* __restrict__ samples,
                                                            const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
                                                            const TL* __restrict__ lut, float* __restrict__ signals,
@@ -1329,7 +1505,19 @@ static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut,
                 // grouped path: equal / adjacent offsets must be neighbours
                 // group records reuse the uniforms buffer (dead after k_mc_sampler; 24 bytes per sample >= one 16-byte record)
                 GroupRecT* groups = reinterpret_cast<GroupRecT*>(w.uu);
-                k_mc_sort<<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
+                // phase-aligned path (LSB_ACC_ALIGNED=1): one record and one LDG.128 per distinct offset; the class bits of its sort key
+                // need offsets + ticks below 2^24 words
+                static int use_aligned = -1;                                  // -2: automatic
+                if (use_aligned == -1) { const char* e = getenv("LSB_ACC_ALIGNED"); use_aligned = !e ? -2 : (e[0] == '1' ? 1 : 0); }
+                const bool aligned = use_aligned == -2 ? p.split == 2 : use_aligned == 1;
+                if (aligned && ACC_GW == 4 && (long long)p.Rx * p.Ry * p.Rt + p.T < RUN_MAX_WORDS) {
+                    k_mc_sort<true><<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
+                    LSB_LAUNCH_CHECK("k_mc_sort");
+                    k_mc_accumulate<TL, 1, 4><<<grid, ACC_TPB, 0, st>>>(p, w.pairs, w.samples, w.offs32, groups, table, signals, lut);
+                    LSB_LAUNCH_CHECK("k_mc_accumulate");
+                    return 0;
+                }
+                k_mc_sort<false><<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                 LSB_LAUNCH_CHECK("k_mc_sort");
                 static int use_tma = -1;
                 if (use_tma < 0) { const char* e = getenv("LSB_ACC_TMA"); use_tma = (e && e[0] == '1') ? 1 : 0; }

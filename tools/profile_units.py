@@ -29,6 +29,30 @@ if which in ("ndlar", "both"):
     out["ndlar"] = dict(S=r.n_segments, P=r.max_neighbors, U=r.n_unique_pixels, T=r.n_ticks, n_samples=r.n_samples, n_fma=r.n_fma,
                         n_pairs=r.n_pairs, n_groups=r.n_groups, n_edge=r.n_edge, n_irregular=r.n_irregular, stage_ms=r.stage_ms)
     ch.close()
+if os.environ.get("KPROF"):
+    # per-kernel times of one more pass over the last unit (event pairs around every launch, lsb_profile_begin/end)
+    import ctypes as C
+    lib = ll.lib()
+    lib.lsb_profile_end.restype = C.c_int64
+    name = "ndlar" if which in ("ndlar", "both") else "module0"
+    if name == "ndlar":
+        ch = lchain.Chain(sub.dtype, resp); data = sub
+    else:
+        ch = lchain.Chain(tr.dtype, synth.response_lut(mod.detector)); data = tr
+    ch.run(ll.DeviceRecords(host=data.copy()), rng_seed=1)
+    torch.cuda.synchronize()
+    lib.lsb_profile_begin(ll.stream())
+    ch.run(ll.DeviceRecords(host=data.copy()), rng_seed=1)
+    torch.cuda.synchronize()
+    buf = C.create_string_buffer(1 << 16)
+    lib.lsb_profile_end(buf, C.c_int64(len(buf)))
+    prof = {}
+    for ln in buf.value.decode().strip().split("\n"):
+        f = ln.split()
+        if len(f) == 3:
+            prof[f[0]] = round(float(f[2]), 4)
+    out[name]["kernel_ms"] = dict(sorted(prof.items(), key=lambda kv: -kv[1])[:12])
+    ch.close()
 for k, v in out.items():
     v["samples_per_group"] = v["n_samples"] / max(v["n_groups"], 1)
     v["edge_share_of_fma"] = v["n_edge"] / max(v["n_fma"], 1)
