@@ -1015,7 +1015,8 @@ __device__ __forceinline__ void acc_class_run(const float4* __restrict__ lut4, i
     // eight LDG.128 of the table, 32 FFMA, one fold of the <= 8-term float32 sums into float64), then the rest.
     // Measured and dropped (B200, tracks_current_mc stage of one ND-LAr unit, 8.30 ms as written): `prefetch.global.L1` of the next
     // trip's table lines 11.1 ms; quads masked at both ends instead of the single-record head and tail 8.50; 80 registers / 6 CTAs
-    // per SM 9.35; 48 registers / 10 CTAs per SM (spills) 10.3.
+    // per SM 9.35; 48 registers / 10 CTAs per SM (spills) 10.3; warp = class instead of warp = block (the four warps walk the
+    // four class lists of the same block together so that they share table lines in L1; sums meet in shared memory) 9.08.
     int r = 0;
     float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
     const int lead = (int)((16u - ((unsigned)reinterpret_cast<uintptr_t>(recs) & 15u)) & 15u) >> 2;
@@ -1385,7 +1386,7 @@ __device__ __forceinline__ void mc_accumulate_pair(const McParams& p, long long 
 // one CTA per (segment, pixel) pair.  (A persistent grid fetching pairs from a device counter was measured on B200: 3.6 % slower
 // alone -- an atomic and two barriers per pair -- and no better with three batches in flight, profiles/r02_spill_pipeline.md.)
 template <typename TL, int STRIDE, int FAST>
-__global__ void __launch_bounds__(ACC_TPB, FAST == 4 ? ACC_AL_MINB : FAST == 1 ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
+__global__ void __launch_bounds__(ACC_TPB, FAST >= 4 ? ACC_AL_MINB : FAST == 1 ? ACC_MINB : 8) k_mc_accumulate(McParams p, const PairRec* __restrict__ pairs,
                                                            const SampleRec* __restrict__ samples,
                                                            const int* __restrict__ offs32, const GroupRecT* __restrict__ groups,
                                                            const TL* __restrict__ lut, float* __restrict__ signals,
@@ -1509,7 +1510,7 @@ static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut,
                 // need offsets + ticks below 2^24 words
                 static int use_aligned = -1;                                  // -2: automatic
                 if (use_aligned == -1) { const char* e = getenv("LSB_ACC_ALIGNED"); use_aligned = !e ? -2 : (e[0] == '1' ? 1 : 0); }
-                const bool aligned = use_aligned == -2 ? p.split == 2 : use_aligned == 1;
+                const int aligned = use_aligned == -2 ? (p.split == 2 ? 1 : 0) : use_aligned;
                 if (aligned && ACC_GW == 4 && (long long)p.Rx * p.Ry * p.Rt + p.T < RUN_MAX_WORDS) {
                     k_mc_sort<true><<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                     LSB_LAUNCH_CHECK("k_mc_sort");
