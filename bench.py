@@ -442,6 +442,15 @@ def run_ours(args, rank, world, local_rank):
                                   "ncu_l1tex_throughput_pct": ncu.get("l1tex_throughput_pct"), "ncu_issue_active_pct": ncu.get("issue_active_pct"),
                                   "ncu_lts_throughput_pct": ncu.get("lts_throughput_pct"), "ncu_l2_to_l1_TBs": ncu.get("l2_to_l1_TBs"),
                                   "ncu_note": ncu.get("_source")}
+            l2p = os.path.join(ROOT, "profiles", "r02_l2_bandwidth.json")
+            if ncu.get("l2_to_l1_bytes_per_fma") and os.path.exists(l2p):
+                with open(l2p) as f:
+                    l2peak = json.load(f)["l2_read_GBs"] / 1e3
+                l2ach = ncu["l2_to_l1_bytes_per_fma"] * pst["n_fma"] / t_s / 1e12
+                roofline["l2"] = {"what": "table bytes that travel L2 -> L1: (lts__t_sectors_srcunit_tex_op_read x 32 B / N_fma of the ncu capture, "
+                                          "profiles/r02_traffic.json) x N_fma of this run / the kernel's time in this run",
+                                  "achieved": l2ach, "peak": l2peak, "unit": "TB/s", "frac": l2ach / l2peak,
+                                  "peak_source": "tools/l2_bandwidth.cu on this pool's B200 (LDG.128 stream over an L2-resident buffer, profiles/r02_l2_bandwidth.json)"}
             mc_ms = sum(prof[k][1] for k in ("k_mc_pairs", "k_mc_uniforms", "k_mc_sampler", "k_mc_sort", "k_mc_accumulate", "k_mc_fused") if k in prof)
             flops = 2.0 * pst["n_fma"] + 330.0 * pst["n_samples"]
             fp32_peak = FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
