@@ -199,6 +199,13 @@ int32_t lsb_mc_get_grouped(void);
  * length (RESPONSE_SAMPLING = TIME_SAMPLING / 2, ND-LAr) take the same path on a phase-split copy of the table. */
 void lsb_mc_set_lane_ticks(int32_t n);
 int32_t lsb_mc_get_lane_ticks(void);
+/* phase-aligned variant of the grouped path: the offsets of a pair are ordered by (offset mod 4, offset / 4) and folded into one
+ * 4-byte record per DISTINCT offset; for alignment class d a lane owns ticks 4 lane - d .. 4 lane - d + 3 of a 124-tick block, so
+ * the table words it needs are one aligned float4 (one LDG.128 + 4 FFMA per distinct offset instead of an 8-word window per
+ * group).  mode: -1 automatic (on when the table is phase-split, i.e. RESPONSE_SAMPLING = TIME_SAMPLING / 2), 0 off, 1 on;
+ * also LSB_ACC_ALIGNED=0/1.  Same results to 1e-5 (summation order differs). */
+void lsb_mc_set_aligned(int32_t mode);
+int32_t lsb_mc_get_aligned(void);
 /* larndsim/detsim.py:351-453  tracks_current(signals, pixels, tracks, response) */
 int lsb_tracks_current(const lsb_consts* c, const lsb_track_layout* L, const void* tracks, int64_t S,
                        const int32_t* pixels, int32_t P, float* signals, int32_t T,

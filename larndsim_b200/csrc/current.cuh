@@ -1486,6 +1486,15 @@ LSB_EXPORT int32_t lsb_mc_get_grouped(void) {
     return g_mc_grouped;
 }
 
+// phase-aligned interior (k_mc_accumulate<float, 1, 4>): -1 = automatic (on for phase-split tables, where few offsets share an aligned
+// 4-word block), 0 = off, 1 = on; LSB_ACC_ALIGNED / lsb_mc_set_aligned.  profiles/r02_acc_aligned.md
+static int g_mc_aligned = -2;
+LSB_EXPORT void lsb_mc_set_aligned(int32_t mode) { g_mc_aligned = mode < 0 ? -1 : (mode ? 1 : 0); }
+LSB_EXPORT int32_t lsb_mc_get_aligned(void) {
+    if (g_mc_aligned == -2) { const char* e = getenv("LSB_ACC_ALIGNED"); g_mc_aligned = !e ? -1 : (e[0] == '1' ? 1 : 0); }
+    return g_mc_aligned;
+}
+
 // ticks per lane of the grouped interior path: 4 (8-word windows; default) or 8 (12-word windows: 1.5 instead of 2 table words per
 // tick, but 64 registers / 32 warps per SM -- measured slower on B200: 7.39 against 6.26 ms per module0 batch, 12.9 against 11.0 ms per
 // ND-LAr unit, profiles/r02_spill_pipeline.md); LSB_ACC_LANE_TICKS / lsb_mc_set_lane_ticks
@@ -1508,9 +1517,8 @@ static int mc_launch_accumulate(const McParams& p, const McWs& w, const TL* lut,
                 GroupRecT* groups = reinterpret_cast<GroupRecT*>(w.uu);
                 // phase-aligned path (LSB_ACC_ALIGNED=1): one record and one LDG.128 per distinct offset; the class bits of its sort key
                 // need offsets + ticks below 2^24 words
-                static int use_aligned = -1;                                  // -2: automatic
-                if (use_aligned == -1) { const char* e = getenv("LSB_ACC_ALIGNED"); use_aligned = !e ? -2 : (e[0] == '1' ? 1 : 0); }
-                const int aligned = use_aligned == -2 ? (p.split == 2 ? 1 : 0) : use_aligned;
+                const int mode = lsb_mc_get_aligned();
+                const bool aligned = mode < 0 ? p.split == 2 : mode == 1;
                 if (aligned && ACC_GW == 4 && (long long)p.Rx * p.Ry * p.Rt + p.T < RUN_MAX_WORDS) {
                     k_mc_sort<true><<<lsb_blocks(p.S * p.P, SORT_WARPS), 32 * SORT_WARPS, 0, st>>>(p, w.pairs, w.offs32, groups);
                     LSB_LAUNCH_CHECK("k_mc_sort");

@@ -1,5 +1,7 @@
 """Parity of every CUDA kernel with the CPU oracle, called through the drop-in modules (which go through
 the C ABI) with the argument kinds the reference CLI uses: host structured arrays and device arrays."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -321,6 +323,28 @@ def test_chain_generic_mc_path_vs_oracle(cuda):
             assert r["adc_mismatch"] == 0 and r["n_hits"] == r["n_hits_oracle"] and r["n_hits"] > 0
     finally:
         lib.lsb_mc_set_grouped(was)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_chain_interior_variants_vs_oracle(cuda, mode):
+    """Both interior strategies of the grouped tracks_current_mc path -- 8-word windows per aligned group (0) and one aligned
+    float4 per distinct offset (1; the default only for phase-split tables) -- forced on every configuration:
+    same waveforms to 1e-5, everything downstream identical."""
+    from larndsim_b200 import _launch as ll
+    lib = ll.lib()
+    lib.lsb_mc_get_aligned.restype = C.c_int32
+    was = lib.lsb_mc_get_aligned()
+    lib.lsb_mc_set_aligned(C.c_int32(mode))
+    try:
+        assert lib.lsb_mc_get_aligned() == mode
+        for config, kind, n in (("module0", "cosmic", 200), ("2x2", "beam", 300), ("ndlar", "beam", 200)):
+            r = h.chain_vs_oracle(n_segments=n, config=config, seed=23, noise=True, kind=kind, exact_fractions=True)
+            assert r["tracks_equal"] and r["shape_equal"] and r["unique_equal"] and r["tpm_equal"]
+            assert r["signals_relerr"] < 1e-5
+            assert r["pixels_signals_equal"] and r["ticks_equal"] and r["adc_pattern_equal"] and r["cf_equal"]
+            assert r["adc_mismatch"] == 0 and r["n_hits"] == r["n_hits_oracle"] and r["n_hits"] > 0
+    finally:
+        lib.lsb_mc_set_aligned(C.c_int32(was))
 
 
 def test_light_chain_medium_vs_oracle(cuda):
