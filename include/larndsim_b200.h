@@ -498,6 +498,14 @@ int lsb_gather_records(const void* src_dev, const int64_t* order_dev, int64_t n,
  * src_dev[b] .. + bytes[b] -> dst_dev + dst_off[b].  Puts the units received from all ranks into file order. */
 int lsb_copy_blocks(int64_t n_blocks, const void* const* src_dev, const int64_t* dst_off, const int64_t* bytes, void* dst_dev,
                     void* stream);
+/* Multi-rank host output on one node: the ranks share one host table (a shared-memory mapping made by the caller).  Each rank
+ * registers the mapping with its CUDA context (lsb_host_register; page-locks it) and copies the blocks of its own units to their
+ * file-order byte offsets (lsb_d2h_blocks: asynchronous on `stream`, src_dev / dst_off / bytes are host arrays) -- the copy the
+ * reference does once per batch in fee.export_to_hdf5 (fee.py:84-359), spread over the ranks' PCIe links. */
+int lsb_host_register(void* host_ptr, int64_t bytes);
+int lsb_host_unregister(void* host_ptr);
+int lsb_d2h_blocks(int64_t n_blocks, const void* const* src_dev, const int64_t* dst_off, const int64_t* bytes, void* dst_host,
+                   void* stream);
 
 #ifdef __cplusplus
 }

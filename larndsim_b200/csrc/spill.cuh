@@ -353,3 +353,29 @@ LSB_EXPORT int lsb_copy_blocks(int64_t n_blocks, const void* const* src_dev, con
     LSB_LAUNCH_CHECK("k_copy_blocks");
     return 0;
 }
+
+// ---- per-rank device -> host copies into a host buffer shared by the ranks of a node ------------------------------------------------
+// With N ranks on one node the packets and truth rows of a spill end in ONE host table (what fee.export_to_hdf5 receives).  Rank 0
+// maps a shared-memory file, every rank registers the same pages with its CUDA context and copies its own units' blocks straight to
+// their file-order positions: N PCIe links instead of one, no gather through rank 0's HBM.
+LSB_EXPORT int lsb_host_register(void* host_ptr, int64_t bytes) {
+    LSB_REQUIRE(host_ptr && bytes > 0, "host_register: null pointer");
+    LSB_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+LSB_EXPORT int lsb_host_unregister(void* host_ptr) {
+    LSB_REQUIRE(host_ptr, "host_unregister: null pointer");
+    LSB_CUDA(cudaHostUnregister(host_ptr));
+    return 0;
+}
+LSB_EXPORT int lsb_d2h_blocks(int64_t n_blocks, const void* const* src_dev, const int64_t* dst_off, const int64_t* bytes, void* dst_host,
+                              void* stream) {
+    if (n_blocks <= 0) return 0;
+    LSB_REQUIRE(src_dev && dst_off && bytes && dst_host, "d2h_blocks: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (long long i = 0; i < n_blocks; i++) {
+        if (bytes[i] <= 0) continue;
+        LSB_CUDA(cudaMemcpyAsync((char*)dst_host + dst_off[i], src_dev[i], (size_t)bytes[i], cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}

@@ -7,13 +7,16 @@ the loop itself native (``lsb_spill_run``, csrc/spill.cuh):
     select_active_volume -> quench, drift (whole file) -> TPCBatcher plan (one device pass) -> units assigned to the
     ranks longest-first -> every rank: its units through ``depth`` chains in flight, packets + ``mc_packets_assn`` rows
     appended on the device -> one NCCL exchange to rank 0 -> blocks put into file order on the device -> (optional) one
-    D2H copy into pinned host arrays.
+    D2H copy into pinned host arrays.  With host output and several ranks on one node the exchange is skipped: the ranks map
+    one shared host table and each copies its own units' blocks straight to their file-order positions (N PCIe links).
 
 Units (event x TPC group) are independent.  Every unit draws from
 ``create_xoroshiro128p_states(n, seed = rand_seed + unit number)``, so the packets of a unit do not depend on which rank or
 chain processed it: the output of N ranks is bit-identical to the output of one.
 """
 import ctypes as C
+import os
+import socket
 
 import numpy as np
 import torch
@@ -88,6 +91,57 @@ def file_order_blocks(unit_packets, plan, n_event_packets, n_tpc_batches):
     return blocks, pos
 
 
+class SharedHostTable:
+    """A byte table in shared memory mapped by every rank of a process group on ONE node, page-locked in every rank's CUDA
+    context (``register(ptr, nbytes)`` / ``unregister(ptr)``; None: plain shared memory, e.g. CPU tests).  ``ensure`` is a
+    collective: every rank calls it with the same size."""
+    _serial = 0
+
+    def __init__(self, group, rank, register=None, unregister=None, directory="/dev/shm"):
+        self.group, self.rank = group, rank
+        self._reg, self._unreg = register, unregister
+        self.dir = directory
+        self.mm = None
+        self.nbytes = 0
+
+    def ensure(self, nbytes):
+        if self.mm is not None and self.nbytes >= nbytes:
+            return self.mm
+        self.close()
+        size = int(nbytes * 1.25) + 4096
+        obj = [None]
+        if self.rank == 0:
+            SharedHostTable._serial += 1
+            path = os.path.join(self.dir, "lsb_%d_%d" % (os.getpid(), SharedHostTable._serial))
+            try:
+                with open(path, "wb") as f:
+                    f.truncate(size)
+                obj = [path]
+            except OSError:
+                obj = [None]
+        dist.broadcast_object_list(obj, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        if obj[0] is None:
+            raise OSError("cannot create a shared-memory file under %s" % self.dir)
+        mm = np.memmap(obj[0], dtype=np.uint8, mode="r+", shape=(size,))
+        dist.barrier(group=self.group)                 # everybody has it mapped: the name can go, the pages stay
+        if self.rank == 0:
+            os.unlink(obj[0])
+        if self._reg is not None:
+            self._reg(mm.ctypes.data, size)
+        self.mm, self.nbytes = mm, size
+        return mm
+
+    def close(self):
+        if self.mm is not None:
+            if self._unreg is not None:
+                try:
+                    self._unreg(self.mm.ctypes.data)
+                except Exception:
+                    pass
+            self.mm = None
+            self.nbytes = 0
+
+
 class SpillOutput:
     """What rank 0 holds after a spill (other ranks: ``packets is None``)."""
 
@@ -127,6 +181,9 @@ class SpillRunner:
             raise _abi.LsbError("lsb_spill_create failed: %s" % lib.lsb_last_error().decode())
         self._cap = 0
         self._stage = {}          # device / pinned staging buffers reused from spill to spill
+        self._shared = None       # host tables shared by the ranks (host output, world > 1, one node); False: not available
+        if self.world > 1 and os.environ.get("LSB_SPILL_SHARED_HOST", "1") == "0":
+            self._shared = False
         f = self.dtype.fields
         self._seg = (f["segment_id"][1], _abi._DTYPE_CODE[np.dtype(f["segment_id"][0])]) if "segment_id" in f else (-1, 0)
         self._traj = (f["file_traj_id"][1], _abi._DTYPE_CODE[np.dtype(f["file_traj_id"][0])]) if "file_traj_id" in f else (-1, 0)
@@ -136,6 +193,10 @@ class SpillRunner:
         _l.check(_l.lib().lsb_spill_set_serial(C.c_void_p(self._h), C.c_int32(1 if on else 0)), "spill_set_serial")
 
     def close(self):
+        if getattr(self, "_shared", None):
+            for t in self._shared:
+                t.close()
+            self._shared = None
         if getattr(self, "_h", None) and _l is not None:
             _l.lib().lsb_spill_destroy(C.c_void_p(self._h))
             self._h = None
@@ -150,6 +211,24 @@ class SpillRunner:
             t = torch.empty(n, dtype=torch.uint8, pin_memory=True) if pinned else torch.empty(n, dtype=torch.uint8, device="cuda")
             self._stage[name] = t
         return t
+
+    def _shared_tables(self):
+        """(packets, truth rows) host tables shared by the ranks, or None when the ranks are not on one node"""
+        if self._shared is None:
+            names = [None] * self.world
+            dist.all_gather_object(names, socket.gethostname(), group=self.group)
+            if len(set(names)) != 1:
+                self._shared = False
+            else:
+                lib = _l.lib()
+
+                def reg(ptr, n):
+                    _l.check(lib.lsb_host_register(C.c_void_p(ptr), C.c_int64(n)), "host_register")
+
+                def unreg(ptr):
+                    lib.lsb_host_unregister(C.c_void_p(ptr))
+                self._shared = (SharedHostTable(self.group, self.rank, reg, unreg), SharedHostTable(self.group, self.rank, reg, unreg))
+        return self._shared or None
 
     def _event_level_packets(self, events, event_times):
         """Packets the reference writes between the batches of its loop (cli/simulate_pixels.py:872-887): the sync packets
@@ -262,6 +341,10 @@ class SpillRunner:
             dist.all_reduce(counts, group=self.group)
         counts_h = counts.cpu().numpy()
         out.unit_packets = counts_h
+        if host_output and self.world > 1:
+            tabs = self._shared_tables()
+            if tabs is not None:
+                return self._finish_shared(out, tabs, res, counts_h, plan, events, event_times, nB, d_sel, S, return_tracks)
         # (6) the ranks' packet / truth-row blocks -> rank 0 (NCCL send / recv of the exact sizes)
         per_rank = [int(counts_h[plan[r]].sum()) if len(plan[r]) else 0 for r in range(self.world)]
         src_pk = {self.rank: int(res.packets or 0)}
@@ -329,6 +412,48 @@ class SpillRunner:
         torch.cuda.current_stream().synchronize()
         out.packets = h_pk[:n_total * pkb].numpy().view(_p.PACKET_DTYPE)
         out.packets_mc_ds = h_rw[:n_total * rowb].numpy().view(self.assn_dtype)
+        if return_tracks:
+            out.tracks = h_tr[:S * self.dtype.itemsize].numpy().view(self.dtype)
+        return out
+
+    def _finish_shared(self, out, tabs, res, counts_h, plan, events, event_times, nB, d_sel, S, return_tracks):
+        """Steps (6)-(8) for host output with several ranks on one node: every rank copies the blocks of its own units from its
+        HBM to their file-order positions in two host tables shared by the ranks; rank 0 adds the between-batch packets."""
+        lib = _l.lib()
+        st = _l.stream()
+        rowb, pkb = self.assn_dtype.itemsize, _p.PACKET_DTYPE.itemsize
+        evp = self._event_level_packets(events, event_times)
+        blocks, n_total = file_order_blocks(counts_h, plan, [len(x) for x in evp], nB)
+        out.n_packets = n_total
+        h_pk = tabs[0].ensure(max(n_total, 1) * pkb)
+        h_rw = tabs[1].ensure(max(n_total, 1) * rowb)
+        mine = [(soff, dpos, n) for src, soff, dpos, n in blocks if src == self.rank]
+        if mine and res.packets:
+            soff = np.asarray([m[0] for m in mine], dtype=np.int64)
+            dpos = np.asarray([m[1] for m in mine], dtype=np.int64)
+            cnt = np.asarray([m[2] for m in mine], dtype=np.int64)
+            for base, item, table in ((int(res.packets), pkb, h_pk), (int(res.assn_rows), rowb, h_rw)):
+                src = (C.c_void_p * len(mine))(*[base + int(o) * item for o in soff])
+                d_off, nb = np.ascontiguousarray(dpos * item), np.ascontiguousarray(cnt * item)
+                _l.check(lib.lsb_d2h_blocks(C.c_int64(len(mine)), src, d_off.ctypes.data_as(C.c_void_p), nb.ctypes.data_as(C.c_void_p),
+                                            C.c_void_p(table.ctypes.data), st), "d2h_blocks")
+        if self.rank == 0:
+            ev_blob = np.concatenate(evp) if len(evp) else np.zeros(0, dtype=_p.PACKET_DTYPE)
+            ev_u8 = ev_blob.view(np.uint8).reshape(-1)
+            blank = np.ascontiguousarray(_fee._no_truth_rows(1)).view(np.uint8).reshape(-1)
+            for src, soff, dpos, n in blocks:
+                if src < 0:                                # between-batch packets; their truth rows are all -1 / 0 (fee.py:413-420)
+                    h_pk[dpos * pkb:(dpos + n) * pkb] = ev_u8[soff * pkb:(soff + n) * pkb]
+                    h_rw[dpos * rowb:(dpos + n) * rowb].reshape(n, rowb)[:] = blank
+            if return_tracks:
+                h_tr = self._buf("host_tracks", max(S, 1) * self.dtype.itemsize, pinned=True)
+                h_tr[:S * self.dtype.itemsize].copy_(d_sel.buf[:S * self.dtype.itemsize], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)                     # every rank's blocks have landed
+        if self.rank != 0:
+            return out
+        out.packets = np.asarray(h_pk[:n_total * pkb]).view(_p.PACKET_DTYPE)
+        out.packets_mc_ds = np.asarray(h_rw[:n_total * rowb]).view(self.assn_dtype)
         if return_tracks:
             out.tracks = h_tr[:S * self.dtype.itemsize].numpy().view(self.dtype)
         return out

@@ -34,10 +34,17 @@ def main():
             out.packets, out.packets_mc_ds, out.tracks = out.packets.copy(), out.packets_mc_ds.copy(), out.tracks.copy()
         again = runner.simulate(tracks.copy(), rand_seed=5)
         if rank == 0:
+            again.packets = again.packets.copy()
+        # result left on the device: the NCCL exchange to rank 0 + device-side file order (host output above went through the
+        # host table shared by the ranks)
+        dev = runner.simulate(tracks.copy(), rand_seed=5, host_output=False)
+        if rank == 0:
             single = spill.SpillRunner(tracks.dtype, resp, depth=2, single_rank=True)
             ref = single.simulate(tracks.copy(), rand_seed=5, return_tracks=True)
             same = (out.packets.tobytes() == ref.packets.tobytes() and out.packets_mc_ds.tobytes() == ref.packets_mc_ds.tobytes()
                     and again.packets.tobytes() == ref.packets.tobytes() and np.array_equal(out.unit_packets, ref.unit_packets)
+                    and dev.packets.cpu().numpy().tobytes() == ref.packets.tobytes()
+                    and dev.packets_mc_ds.cpu().numpy().tobytes() == ref.packets_mc_ds.tobytes()
                     and helpers.records_equal(out.tracks, ref.tracks))          # field-wise: padding bytes are not data
             print("%s: %d ranks, %d units, %d packets, rank-0 output == single-rank output: %s" % (
                 config, world, len(out.unit_sizes), out.n_packets, same), flush=True)

@@ -196,7 +196,28 @@ def _spill_worker(rank, world, port, q):
             want.append(ev_blob[e_off:e_off + n_evp[e]]); e_off += n_evp[e]
             for b in range(nB):
                 want.append(unit_bytes(e * nB + b))
-        q.put(bool(np.array_equal(out, np.concatenate(want))) and total == int(n_pk.sum()) + sum(n_evp))
+        ok_gather = bool(np.array_equal(out, np.concatenate(want))) and total == int(n_pk.sum()) + sum(n_evp)
+    # the same assembly without the exchange: one host table shared by the ranks, every rank writes its own units' blocks
+    # at their file-order positions (SpillRunner._finish_shared; the device -> host copies are plain stores here)
+    blocks, total = spill.file_order_blocks(counts.numpy(), plan, n_evp, nB)
+    table = spill.SharedHostTable(None, rank)
+    ok_shared = True
+    for round_ in range(2):                                               # second round: the table has to grow
+        rep = 1 + 3 * round_
+        mm = table.ensure(total * 16 * rep)
+        view = np.asarray(mm[:total * 16 * rep]).view(np.int64).reshape(rep, total, 2)
+        for src, soff, dpos, n in blocks:
+            if src == rank:
+                view[:, dpos:dpos + n] = local[soff:soff + n]
+            elif src < 0 and rank == 0:
+                view[:, dpos:dpos + n] = ev_blob[soff:soff + n]
+        dist.barrier()
+        if rank == 0:
+            ok_shared = ok_shared and all(np.array_equal(view[k], np.concatenate(want)) for k in range(rep))
+        dist.barrier()
+    table.close()
+    if rank == 0:
+        q.put(ok_gather and ok_shared)
     dist.barrier()
     dist.destroy_process_group()
 
