@@ -80,8 +80,8 @@ __global__ void k_fee_fir_pre(FeeParams fp, const double* __restrict__ pixels_si
 }
 // xoroshiro128+ is sequential per pixel but cheap; the Box-Muller transcendentals are not.  Step every
 // pixel's stream NMAX normals ahead, store the float32 uniform pairs ([i][pixel]: coalesced) and a state
-// snapshot every 64 normals, then turn the pairs into normals with one thread per value.
-#define FEE_SNAP 64
+// snapshot every FEE_SNAP normals, then turn the pairs into normals with one thread per value.
+#define FEE_SNAP (RNG_STEP_UNIT / 2)
 __global__ void k_fee_rng_uniforms(const unsigned long long* __restrict__ rng_states, long long U, int NMAX,
                                    float2* __restrict__ uu, ulonglong2* __restrict__ snaps) {
     long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -106,7 +106,7 @@ __global__ void k_fee_rng_normals(const float2* __restrict__ uu, float* __restri
 
 // The same normals and snapshots in ONE pass with (pixel, chunk) parallelism: thread (g, pixel) jumps the pixel's stream to draw
 // RNG_STEP_UNIT * g (rng.cuh: one GF(2) matrix product per set bit of g; the matrices are shared by the warp, g is warp-uniform),
-// records the snapshot, and turns its 64 uniform pairs into normals.  Pixels are the fast index, so stores are coalesced; the
+// records the snapshot, and turns its FEE_SNAP uniform pairs into normals.  Pixels are the fast index, so stores are coalesced; the
 // 8-byte uniform pairs never reach HBM.  (k_fee_rng_uniforms walked each stream sequentially with one thread per pixel --
 // 15 000 threads on a 300 000-thread machine -- and k_fee_rng_normals re-read its 0.8 GB of output.)
 static_assert(RNG_STEP_UNIT == 2 * FEE_SNAP, "one chunk = FEE_SNAP normals");

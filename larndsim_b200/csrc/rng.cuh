@@ -96,7 +96,9 @@ __global__ void k_rng_create_states(const RngJumpTable* __restrict__ tab, unsign
 // A stream that has to be consumed from many positions at once (the per-pixel noise of get_adc_values: ~13 000 draws per pixel,
 // strictly sequential in the reference) is cut into chunks of RNG_STEP_UNIT draws; the state at the start of chunk g is
 // T^(RNG_STEP_UNIT * g) state 0, one bit-matrix product per set bit of g.
-#define RNG_STEP_UNIT 128            // draws per chunk = 64 Box-Muller normals
+#ifndef RNG_STEP_UNIT
+#define RNG_STEP_UNIT 512            // draws per chunk = 256 Box-Muller normals.  The jump to a chunk costs ~3 matrix products (~1300
+#endif                               // instructions each): k_fee_rng_chunks per ND-LAr unit 0.69 ms at 128, 0.52 at 256, 0.47 at 512
 #define RNG_STEP_LEVELS 20
 struct RngStepTable { uint64_t col[RNG_STEP_LEVELS][128][2]; };
 static const RngStepTable* rng_step_table_host() {

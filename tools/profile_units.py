@@ -22,6 +22,8 @@ if which in ("module0", "both"):
     ch.close()
 if which in ("ndlar", "both"):
     mod, tracks, resp = bench.make_spill()
+    if os.environ.get("THR_SCALE"):          # e.g. 1000: no pixel ever triggers (what the FEE state machine costs without hits)
+        mod.detector.DISCRIMINATION_THRESHOLD *= float(os.environ["THR_SCALE"])
     sub = bench.cpu_sample(tracks, mod, 7000)
     ch = lchain.Chain(sub.dtype, resp, stage_timing=True)
     for _ in range(reps):
