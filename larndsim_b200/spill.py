@@ -91,6 +91,10 @@ def file_order_blocks(unit_packets, plan, n_event_packets, n_tpc_batches):
     return blocks, pos
 
 
+class SharedHostUnavailable(RuntimeError):
+    """raised on EVERY rank of the group when the shared host table cannot be set up on one of them"""
+
+
 class SharedHostTable:
     """A byte table in shared memory mapped by every rank of a process group on ONE node, page-locked in every rank's CUDA
     context (``register(ptr, nbytes)`` / ``unregister(ptr)``; None: plain shared memory, e.g. CPU tests).  ``ensure`` is a
@@ -120,14 +124,30 @@ class SharedHostTable:
             except OSError:
                 obj = [None]
         dist.broadcast_object_list(obj, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
-        if obj[0] is None:
-            raise OSError("cannot create a shared-memory file under %s" % self.dir)
-        mm = np.memmap(obj[0], dtype=np.uint8, mode="r+", shape=(size,))
-        dist.barrier(group=self.group)                 # everybody has it mapped: the name can go, the pages stay
+        if obj[0] is None:                             # (every rank sees the same None: the failure is collective)
+            raise SharedHostUnavailable("cannot create a shared-memory file under %s" % self.dir)
+        mm, err = None, None
+        try:
+            mm = np.memmap(obj[0], dtype=np.uint8, mode="r+", shape=(size,))
+        except (OSError, ValueError) as e:
+            err = "mmap: %s" % e
+        dist.barrier(group=self.group)                 # everybody has tried to map it: the name can go, the pages stay
         if self.rank == 0:
             os.unlink(obj[0])
-        if self._reg is not None:
-            self._reg(mm.ctypes.data, size)
+        registered = False
+        if err is None and self._reg is not None:
+            try:
+                self._reg(mm.ctypes.data, size)
+                registered = True
+            except Exception as e:                     # e.g. a locked-memory limit: must not leave the other ranks waiting
+                err = "register: %s" % e
+        world = dist.get_world_size(self.group)
+        errs = [None] * world
+        dist.all_gather_object(errs, err, group=self.group)
+        if any(e is not None for e in errs):
+            if registered and self._unreg is not None:
+                self._unreg(mm.ctypes.data)
+            raise SharedHostUnavailable("; ".join("rank %d: %s" % (r, e) for r, e in enumerate(errs) if e is not None))
         self.mm, self.nbytes = mm, size
         return mm
 
@@ -344,7 +364,14 @@ class SpillRunner:
         if host_output and self.world > 1:
             tabs = self._shared_tables()
             if tabs is not None:
-                return self._finish_shared(out, tabs, res, counts_h, plan, events, event_times, nB, d_sel, S, return_tracks)
+                try:
+                    return self._finish_shared(out, tabs, res, counts_h, plan, events, event_times, nB, d_sel, S, return_tracks)
+                except SharedHostUnavailable as e:          # collective: every rank lands here together
+                    import warnings
+                    warnings.warn("shared host table not available (%s): gathering through rank 0 instead" % e)
+                    for t in tabs:
+                        t.close()
+                    self._shared = False
         # (6) the ranks' packet / truth-row blocks -> rank 0 (NCCL send / recv of the exact sizes)
         per_rank = [int(counts_h[plan[r]].sum()) if len(plan[r]) else 0 for r in range(self.world)]
         src_pk = {self.rank: int(res.packets or 0)}

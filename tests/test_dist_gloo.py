@@ -216,8 +216,21 @@ def _spill_worker(rank, world, port, q):
             ok_shared = ok_shared and all(np.array_equal(view[k], np.concatenate(want)) for k in range(rep))
         dist.barrier()
     table.close()
+    # a rank that cannot page-lock the mapping must not leave the others waiting: the failure is raised everywhere
+
+    def reg(ptr, n):
+        if rank == 1:
+            raise RuntimeError("no locked memory")
+    bad = spill.SharedHostTable(None, rank, register=reg, unregister=lambda ptr: None)
+    try:
+        bad.ensure(1 << 16)
+        ok_fail = False
+    except spill.SharedHostUnavailable as e:
+        ok_fail = "rank 1" in str(e) and bad.mm is None
     if rank == 0:
-        q.put(ok_gather and ok_shared)
+        q.put(ok_gather and ok_shared and ok_fail)
+    else:
+        assert ok_fail
     dist.barrier()
     dist.destroy_process_group()
 
