@@ -195,9 +195,19 @@ __global__ void k_mc_set_offsets(McParams p, PairRec* __restrict__ pairs, const 
 }
 
 struct SampleGeom { bool live; double t0; int rowoff; };
+// round(a / b - sub) (round half to even, as Python's round on the float64 quotient) without the FP64 division when the answer
+// cannot depend on its last bits: a * (1 / b) is within a few ulp of a / b, so unless the value lies within 1e-9 of a tie the
+// rounded integer is the same; otherwise the exact expression is evaluated.  (A float64 division is ~30 instructions on the
+// FP64 pipe; the sampler used nine per sample.)
+__device__ __forceinline__ long long round_quotient(double a, double b, double inv_b, double sub) {
+    const double v = a * inv_b - sub;
+    const double r = rint(v);
+    if (fabs(fabs(v - r) - 0.5) < 1e-9 || !(fabs(v) < 4.0e9)) return __double2ll_rn(a / b - sub);
+    return (long long)r;
+}
 // one MC sample given its three normals (detsim.py:326-346 without the tick dependence)
 __device__ __forceinline__ SampleGeom mc_sample(const PairRec& g, long long istep, float nz, float nx, float ny,
-                                                int Rx, int Ry, int Rt) {
+                                                int Rx, int Ry, int Rt, double inv_bin) {
     SampleGeom s;
     double f = (double)istep + 0.5;
     double x = g.sub_start[0] + g.step * f * g.dir[0];
@@ -211,8 +221,8 @@ __device__ __forceinline__ SampleGeom mc_sample(const PairRec& g, long long iste
     s.live = true;
     if (x_dist > d_c.response_bin_size * Rx) s.live = false;
     if (y_dist > d_c.response_bin_size * Ry) s.live = false;
-    long long i = __double2ll_rn(x_dist / d_c.response_bin_size - 0.5);
-    long long j = __double2ll_rn(y_dist / d_c.response_bin_size - 0.5);
+    long long i = round_quotient(x_dist, d_c.response_bin_size, inv_bin, 0.5);
+    long long j = round_quotient(y_dist, d_c.response_bin_size, inv_bin, 0.5);
     if (!(0 <= i && i < Rx && 0 <= j && j < Ry)) s.live = false;
     s.rowoff = s.live ? (int)((i * Ry + j) * (long long)Rt) : -1;
     return s;
@@ -343,6 +353,7 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
     const int M = d_c.mc_sample_multiplier;
     const double W = d_c.time_window, TS = d_c.time_sampling;
     const long long n = g.nstep * M;
+    const double inv_TS = 1.0 / TS, inv_bin = 1.0 / d_c.response_bin_size, inv_rs = 1.0 / d_c.response_sampling;
     for (long long i0 = 0; i0 < n; i0 += 32) {
         const long long i = i0 + lane;
         bool keep = false;
@@ -353,12 +364,12 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
             const float nx = normal_from_uniforms(v.u[2], v.u[3]);
             const float ny = normal_from_uniforms(v.u[4], v.u[5]);
             const long long istep = i / M;
-            SampleGeom s = mc_sample(g, istep, nz, nx, ny, p.Rx, p.Ry, p.Rt);
+            SampleGeom s = mc_sample(g, istep, nz, nx, ny, p.Rx, p.Ry, p.Rt, inv_bin);
             if (s.live) {
                 double t0 = s.t0, t0W = t0 + W;
                 // lower bound: first tick with tick>=0, tick>t0 (tick > t0 already implies k = round((tick-t0)/rs) >= 0)
                 double tl = t0 > 0 ? t0 : 0;
-                double e = floor((tl - g.t_start) / TS);
+                double e = floor((tl - g.t_start) * inv_TS);          // an estimate: the two loops below settle the exact tick
                 int lo = e < 0 ? 0 : (e > (double)p.T ? p.T : (int)e);
 #define LOW_OK(it) (tick_time(g.t_start, (it)) >= 0 && t0 < tick_time(g.t_start, (it)))
                 while (lo > 0 && LOW_OK(lo - 1)) lo--;
@@ -366,10 +377,10 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
 #undef LOW_OK
                 // upper bound: last tick with tick < t0+W and k < Rt.  The window test needs no division; k < Rt only
                 // bites when the table is shorter than the window, and k is monotone in the tick index.
-                e = ceil((t0W - g.t_start) / TS);
+                e = ceil((t0W - g.t_start) * inv_TS);                 // (estimate, settled below)
                 int hi = e < -1 ? -1 : (e > (double)(p.T - 1) ? p.T - 1 : (int)e);
 #define HIGH_T(it) (tick_time(g.t_start, (it)) < t0W)
-#define K_OK(it) (resp_k(tick_time(g.t_start, (it)), t0) < p.Rt)
+#define K_OK(it) (round_quotient(tick_time(g.t_start, (it)) - t0, d_c.response_sampling, inv_rs, 0.0) < p.Rt)
                 while (hi < p.T - 1 && HIGH_T(hi + 1)) hi++;
                 while (hi >= 0 && !HIGH_T(hi)) hi--;
                 if (hi >= 0 && !K_OK(hi)) {
@@ -384,7 +395,8 @@ __global__ void __launch_bounds__(32 * SMP_WARPS, SMP_MINB) k_mc_sampler(McParam
                 if (lo <= hi) {
                     int shift = SHIFT_IRREGULAR;
                     if (p.stride > 0) {
-                        long long klo = resp_k(tick_time(g.t_start, lo), t0), khi = resp_k(tick_time(g.t_start, hi), t0);
+                        const long long klo = round_quotient(tick_time(g.t_start, lo) - t0, d_c.response_sampling, inv_rs, 0.0);
+                        const long long khi = round_quotient(tick_time(g.t_start, hi) - t0, d_c.response_sampling, inv_rs, 0.0);
                         long long sh = klo - (long long)p.stride * lo;
                         long long last = khi;                                   // table index (within the row) read at tick hi
                         if (khi == (long long)p.stride * hi + sh) {
