@@ -7,9 +7,10 @@ import numpy as np
 
 def fast_path(a, b, sub):
     inv_b = 1.0 / b
-    v = a * inv_b - sub
-    r = np.rint(v)
-    slow = (np.abs(np.abs(v - r) - 0.5) < 1e-9) | ~(np.abs(v) < 4.0e9)
+    with np.errstate(invalid="ignore"):
+        v = a * inv_b - sub
+        r = np.rint(v)
+        slow = (np.abs(np.abs(v - r) - 0.5) < 1e-9) | ~(np.abs(v) < 4.0e9)
     return r, slow
 
 
