@@ -17,6 +17,12 @@
 //                   adjacent) and applies every sample of the group as a count-weighted FFMA.  About
 //                   1 LDG.128 per 8 FFMA instead of 1 LDG.32 per FADD (the generic path, kept for
 //                   float64 tables and non-unit sampling ratios).
+//                   Phase-aligned variant (default for phase-split tables, where few offsets share an aligned
+//                   block): the offsets are ordered by (offset mod 4, offset / 4) and folded into one 4-byte
+//                   record per DISTINCT offset; for alignment class d a lane owns ticks 4 lane - d .. + 3 of a
+//                   124-tick block, so the words it needs are ONE aligned float4 -- 1 LDG.128 + 4 FFMA per
+//                   distinct offset, half the instructions, bound by L2 -> L1 bandwidth instead of the L1 data
+//                   pipe (profiles/r02_acc_aligned.md).
 //                   The few edge ticks and irregular samples take an exact predicated path.
 // Replay mode (k_mc_replay) is the reference's thread-for-thread draw pattern, sequential per pair.
 #pragma once
